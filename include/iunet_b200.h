@@ -1,0 +1,128 @@
+/* iunet_b200: C ABI of the B200-native volume-prediction engine.
+ *
+ * This is the drop-in boundary for the full-volume prediction path of
+ * laprade117/interactive-unet.  The reference has no FFI of its own: the seam is the Python
+ * callables in `interactive_unet/predict.py` and the `UNet` module in `interactive_unet/unet.py`
+ * (SURVEY.md section 8b).  Each entry point below names the reference lines it replaces; the Python
+ * host side (`interactive-unet_b200/predict.py`, `unet.py`) keeps the reference's signatures and
+ * binds these symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain C types only; every function returns IU_OK (0) or an IU_ERR_* code, the message is
+ *     available from iu_last_error();
+ *   - the caller owns every input / output buffer; the engine owns weights and workspace;
+ *   - pointers documented as "host or device" are classified with cudaPointerGetAttributes;
+ *   - volumes are C-order [z][y][x]; a slice along axis a is image (y,x) | (z,x) | (z,y);
+ *   - all work is issued on the engine's own non-blocking stream; calls return after that stream
+ *     has drained unless IU_FLAG_ASYNC is passed (then call iu_engine_synchronize);
+ *   - an engine is not re-entrant: serialise calls per handle (the Python side holds a lock);
+ *   - there is no CPU fallback: every compute entry fails with IU_ERR_CUDA on a machine
+ *     without an sm_100 GPU.
+ */
+#ifndef IUNET_B200_H_
+#define IUNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IU_ABI_VERSION 1
+
+#define IU_OK 0
+#define IU_ERR_INVALID 1 /* bad argument / unsupported configuration            */
+#define IU_ERR_CUDA 2    /* CUDA runtime / driver failure                        */
+#define IU_ERR_OOM 3     /* device allocation failed: message contains "out of memory" (predict.py:67-72) */
+#define IU_ERR_STATE 4   /* weights not loaded, etc.                             */
+
+#define IU_FLAG_ASYNC 1u
+
+#define IU_DTYPE_U8 0
+#define IU_DTYPE_F32 1
+
+typedef struct iu_engine iu_engine;
+
+int iu_abi_version(void);
+
+/* Message of the last failure on `e` (or of the last failed iu_engine_create when e == NULL). */
+const char* iu_last_error(const iu_engine* e);
+
+/* Create / destroy an engine bound to CUDA device `device`. */
+int iu_engine_create(int device, iu_engine** out);
+void iu_engine_destroy(iu_engine* e);
+
+/* Stream handle (cudaStream_t) the engine launches on, for callers that record their own events. */
+void* iu_engine_stream(iu_engine* e);
+int iu_engine_synchronize(iu_engine* e);
+
+/* Load the weights of smp.Unet('resnet34', in_channels=1, classes=num_classes) -- the model
+ * `unet.py:56-61` builds for architecture='U-Net', encoder_name='resnet34' -- from host fp32
+ * tensors named with smp's state_dict keys WITHOUT the Lightning `model.` prefix
+ * (e.g. "encoder.layer1.0.conv1.weight", "decoder.blocks.0.conv1.1.running_var",
+ * "segmentation_head.0.bias"; `num_batches_tracked` entries may be omitted).  The engine folds every
+ * eval-mode BatchNorm into the preceding conv, converts to bf16 and packs for the tensor cores.
+ * Replaces `UNet.load_from_checkpoint(...).to(device).eval()` (predict.py:22-27,130-135). */
+int iu_engine_load_weights(iu_engine* e, int num_classes, int n_tensors, const char* const* names,
+                           const float* const* data, const int64_t* numel);
+int iu_engine_num_classes(const iu_engine* e);
+
+/* Upper bound on the slices per internal batch (0 = automatic).  Results do not depend on it. */
+int iu_engine_set_max_batch(iu_engine* e, int max_batch);
+/* Device bytes the engine would hold for `batch` slices of h x w (weights + workspace). */
+int64_t iu_engine_workspace_bytes(iu_engine* e, int batch, int h, int w);
+
+/* `UNet.forward` (unet.py:65-69): x fp32 [batch,1,h,w] -> softmax probabilities fp32
+ * [batch,num_classes,h,w] (NCHW).  h, w multiples of 32.  x / probs: host or device. */
+int iu_engine_forward(iu_engine* e, const float* x, int batch, int h, int w, float* probs, unsigned flags);
+
+/* One axis of `predict_block` (predict.py:87-108) on a cubic volume of edge n (uint8 or fp32, host
+ * or device): runs slices [slice_begin, slice_begin+slice_count) along `axis` through the network
+ * and stores their softmax probabilities (fp32, device) slice-major:
+ *   probs[ (((row / row_block) * slice_total + slice_offset + i) * row_block + row % row_block) * n + col ][c]
+ * for slice i (relative to slice_begin), image pixel (row, col).  With row_block == n and
+ * slice_offset == 0 this is simply probs[i][row][col][c]; row_block = n / G lays the buffer out
+ * destination-major for the z-slab all-to-all. */
+int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, int axis, int slice_begin,
+                           int slice_count, float* probs_dev, int slice_offset, int slice_total, int row_block,
+                           unsigned flags);
+
+/* K1 alone (predict.py:91,95,97,237): gather + normalise slices into fp32 [count][n][n] (device). */
+int iu_engine_gather_slices(iu_engine* e, const void* volume_dev, int dtype, int n, int axis, int start, int count,
+                            float* out_dev, unsigned flags);
+
+/* K4 alone: cross-axis accumulate in `order`, divide by n_axes (predict.py:101-110), blend with the
+ * Gaussian window and quantise (predict.py:244-245,255), argmax (predict.py:38).
+ *   p0/p1/p2: per-axis probabilities (device, fp32, layouts as written by iu_engine_predict_axis
+ *             with row_block == n for a single slab; see aux_kernels.cuh), NULL when unused;
+ *   n: volume edge, t: slab thickness in z (t == n on one GPU), z0: first global z of the slab;
+ *   g1d: host pointer to the n-entry 1-D Gaussian factor or NULL (no window: q = trunc(255*mean));
+ *   out_u8 [t][n][n][C], out_labels [t][n][n], out_mean fp32 [t][n][n][C]: device, any may be NULL. */
+int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float* p2, const int* order, int n_axes,
+                     int n, int t, int z0, int num_classes, const float* g1d_host, float gmax, float lo,
+                     uint8_t* out_u8, uint8_t* out_labels, float* out_mean, unsigned flags);
+
+/* Whole single-GPU path (predict.py:79-112 + 244-245,255): volume (uint8 or fp32, host or device,
+ * cubic edge n) -> uint8 probabilities [n][n][n][C], uint8 labels [n][n][n], fp32 mean probabilities
+ * [n][n][n][C]; each output host or device, any may be NULL.  `axes`: n_axes entries from {0,1,2}. */
+int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n, const int* axes, int n_axes,
+                             const float* g1d_host, float gmax, float lo, uint8_t* out_u8, uint8_t* out_labels,
+                             float* out_mean, unsigned flags);
+
+/* Test hook: one tensor-core convolution exactly as the engine runs it.
+ *   src0/src1: device bf16 NHWC [batch][h_in][w_in][cin]; src1 may be NULL (cin1 = 0);
+ *   weight: host fp32 [cout][cin0+cin1][k][k] (PyTorch layout, source 0's channels first),
+ *   bias: host fp32 [cout]; residual: device bf16 NHWC at output geometry or NULL;
+ *   out: device bf16 NHWC [batch][h_out*(1+up2x)][w_out*(1+up2x)][cout]. */
+int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* src1, int cin1, int batch, int h_in,
+                        int w_in, int ksize, int stride, const float* weight, const float* bias, int cout,
+                        const void* residual, int relu, int up2x, void* out);
+
+/* Number of kernels the engine has launched since creation (bench.py's `gpu_launches`). */
+int64_t iu_engine_launch_count(const iu_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IUNET_B200_H_ */

@@ -1,0 +1,316 @@
+// HBM-bound kernels around the conv stack: slice gather (K1), stem conv, max-pool, and the fused
+// cross-axis reduce / quantise / argmax (K4).  All arithmetic that the reference does on the host
+// in fp32 (`predict.py:110,237,244-245,255`) is reproduced with round-to-nearest intrinsics so that
+// no FMA contraction or reciprocal substitution can change a bit.
+#include "aux_kernels.cuh"
+
+namespace iu {
+
+// =========================================================================== K1 gather
+__device__ __forceinline__ float norm_val(uint8_t v) { return __fdiv_rn((float)v, 255.0f); }
+__device__ __forceinline__ float norm_val(float v) { return v; }
+
+// axes 0 and 1: image rows are contiguous in the volume -> 16-element vector copy per thread
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ vol, int n, int axis, int start,
+                                                          int count, float* __restrict__ out) {
+  const int groups_per_row = n / 16;
+  const size_t total = (size_t)count * n * groups_per_row;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(g % groups_per_row);
+    const int r = (int)((g / groups_per_row) % n);
+    const int b = (int)(g / ((size_t)groups_per_row * n));
+    const size_t src_row = (axis == 0) ? ((size_t)(start + b) * n + r) : ((size_t)r * n + (start + b));
+    const T* src = vol + src_row * n + cg * 16;
+    float* dst = out + ((size_t)b * n + r) * n + cg * 16;
+    float v[16];
+    if constexpr (sizeof(T) == 1) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = norm_val((uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xff));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(src) + j);
+        v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+}
+
+// axis 2: slice index is the volume's fastest dimension -> transpose a [64 cols][32 slices] tile in smem
+template <typename T>
+__global__ void __launch_bounds__(256) gather_cols_kernel(const T* __restrict__ vol, int n, int start, int count,
+                                                          float* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int c0 = blockIdx.x * 64;
+  const int r = blockIdx.y;
+  for (int b0 = 0; b0 < count; b0 += 32) {
+    const int bl = threadIdx.x & 31;
+    for (int cl = threadIdx.x >> 5; cl < 64; cl += 8) {
+      if (b0 + bl < count && c0 + cl < n)
+        tile[cl][bl] = norm_val(vol[((size_t)r * n + c0 + cl) * n + start + b0 + bl]);
+    }
+    __syncthreads();
+    const int cl = threadIdx.x & 63;
+    for (int b = threadIdx.x >> 6; b < 32; b += 4) {
+      if (b0 + b < count && c0 + cl < n) out[((size_t)(b0 + b) * n + r) * n + c0 + cl] = tile[cl][b];
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_gather_slices(const void* vol, int vol_is_f32, int n, int axis, int start, int count, float* out,
+                                 cudaStream_t stream) {
+  if (n % 16 != 0 || axis < 0 || axis > 2 || count <= 0) return cudaErrorInvalidValue;
+  if (axis < 2) {
+    const size_t groups = (size_t)count * n * (n / 16);
+    const int blocks = (int)((groups + 255) / 256 < 148 * 16 ? (groups + 255) / 256 : 148 * 16);
+    if (vol_is_f32)
+      gather_rows_kernel<float><<<blocks, 256, 0, stream>>>((const float*)vol, n, axis, start, count, out);
+    else
+      gather_rows_kernel<uint8_t><<<blocks, 256, 0, stream>>>((const uint8_t*)vol, n, axis, start, count, out);
+  } else {
+    dim3 grid((n + 63) / 64, n);
+    if (vol_is_f32)
+      gather_cols_kernel<float><<<grid, 256, 0, stream>>>((const float*)vol, n, start, count, out);
+    else
+      gather_cols_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)vol, n, start, count, out);
+  }
+  return cudaGetLastError();
+}
+
+// =========================================================================== stem conv 7x7/s2 + BN + ReLU
+constexpr int kStemTile = 16;                        // output pixels per block edge
+constexpr int kStemPatch = 2 * kStemTile + 5;        // 37 input pixels per block edge
+constexpr int kStemPitch = kStemPatch + 1;
+
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, int h, int w,
+                                                   const float* __restrict__ wt, const float* __restrict__ bias,
+                                                   __nv_bfloat16* __restrict__ out) {
+  __shared__ float patch[kStemPatch][kStemPitch];
+  __shared__ float4 wsm[49 * 16];
+  const int n = blockIdx.z;
+  const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
+  const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+  const float* img = x + (size_t)n * h * w;
+  for (int i = threadIdx.x; i < kStemPatch * kStemPatch; i += 256) {
+    const int py = i / kStemPatch, px = i % kStemPatch;
+    const int iy = iy0 + py, ix = ix0 + px;
+    patch[py][px] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(img + (size_t)iy * w + ix) : 0.0f;
+  }
+  for (int i = threadIdx.x; i < 49 * 16; i += 256) wsm[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
+  __syncthreads();
+
+  const int txl = threadIdx.x & 15, tyl = threadIdx.x >> 4;
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = 0.0f;
+#pragma unroll 1
+  for (int r = 0; r < 7; ++r) {
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+      const float v = patch[2 * tyl + r][2 * txl + s];
+      const float4* wp = &wsm[(r * 7 + s) * 16];
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 wv = wp[c4];
+        acc[4 * c4 + 0] = fmaf(v, wv.x, acc[4 * c4 + 0]);
+        acc[4 * c4 + 1] = fmaf(v, wv.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(v, wv.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(v, wv.w, acc[4 * c4 + 3]);
+      }
+    }
+  }
+  const int oh = h / 2, ow = w / 2;
+  const int oy = oy0 + tyl, ox = ox0 + txl;
+  if (oy < oh && ox < ow) {
+    uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)n * oh + oy) * ow + ox) * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = 8 * j + 2 * k;
+        const float a0 = fmaxf(acc[c] + __ldg(bias + c), 0.0f);
+        const float a1 = fmaxf(acc[c + 1] + __ldg(bias + c + 1), 0.0f);
+        __nv_bfloat162 p = __floats2bfloat162_rn(a0, a1);
+        pk[k] = *reinterpret_cast<uint32_t*>(&p);
+      }
+      dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+cudaError_t launch_stem(const float* x, int batch, int h, int w, const float* w_tap_major, const float* bias,
+                        __nv_bfloat16* out, cudaStream_t stream) {
+  dim3 grid((w / 2 + kStemTile - 1) / kStemTile, (h / 2 + kStemTile - 1) / kStemTile, batch);
+  stem_kernel<<<grid, 256, 0, stream>>>(x, h, w, w_tap_major, bias, out);
+  return cudaGetLastError();
+}
+
+// =========================================================================== max-pool 3x3/s2/p1 (NHWC bf16)
+__global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ in, int batch, int h, int w,
+                                                      int c, __nv_bfloat16* __restrict__ out) {
+  const int oh = h / 2, ow = w / 2, groups = c / 8;
+  const size_t total = (size_t)batch * oh * ow * groups;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int ox = (int)((i / groups) % ow);
+    const int oy = (int)((i / ((size_t)groups * ow)) % oh);
+    const int n = (int)(i / ((size_t)groups * ow * oh));
+    __nv_bfloat162 m[4];
+    bool first = true;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = 2 * oy - 1 + r;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = 2 * ox - 1 + s;
+        if (ix < 0 || ix >= w) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * h + iy) * w + ix) * c + g * 8));
+        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+        if (first) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[k] = pv[k];
+          first = false;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], pv[k]);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (((size_t)n * oh + oy) * ow + ox) * c + g * 8) = *reinterpret_cast<uint4*>(m);
+  }
+}
+
+cudaError_t launch_maxpool(const __nv_bfloat16* in, int batch, int h, int w, int c, __nv_bfloat16* out,
+                           cudaStream_t stream) {
+  if (c % 8 != 0) return cudaErrorInvalidValue;
+  const size_t total = (size_t)batch * (h / 2) * (w / 2) * (c / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  maxpool_kernel<<<blocks, 256, 0, stream>>>(in, batch, h, w, c, out);
+  return cudaGetLastError();
+}
+
+// =========================================================================== K4 reduce + quantise + argmax
+// Block = one z, a 32(y) x 32(x) tile.  The axis-2 operand is x-major in memory, so its tile is staged
+// through shared memory (coalesced along y) and read back transposed; axes 0 and 1 are read directly.
+template <int C>
+__global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
+  extern __shared__ float tile[];  // [32 x][32*C + 1]
+  constexpr int pitch = 32 * C + 1;
+  const int z = blockIdx.z;
+  const int y0 = blockIdx.y * 32, x0 = blockIdx.x * 32;
+  const int n = a.n, t = a.t;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+
+  if (a.p[2] != nullptr) {
+    for (int xl = wrp; xl < 32; xl += 8) {
+      if (x0 + xl < n) {
+        const float* src = a.p[2] + (((size_t)(x0 + xl) * t + z) * n + y0) * C;
+        const int lim = min(32, n - y0) * C;
+        for (int j = lane; j < lim; j += 32) tile[xl * pitch + j] = __ldg(src + j);
+      }
+    }
+  }
+  __syncthreads();
+
+  const int x = x0 + lane;
+  if (x >= n) return;
+  for (int yl = wrp; yl < 32; yl += 8) {
+    const int y = y0 + yl;
+    if (y >= n) break;
+    float p[3][C];
+    if (a.p[0] != nullptr) {
+      const float* s = a.p[0] + (((size_t)z * n + y) * n + x) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) p[0][c] = __ldg(s + c);
+    }
+    if (a.p[1] != nullptr) {
+      const float* s = a.p[1] + (((size_t)y * t + z) * n + x) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) p[1][c] = __ldg(s + c);
+    }
+    if (a.p[2] != nullptr) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) p[2][c] = tile[lane * pitch + yl * C + c];
+    }
+    float m[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float acc = 0.0f;
+      for (int i = 0; i < a.n_axes; ++i) {
+        const int ax = a.order[i];
+        const float v = ax == 0 ? p[0][c] : (ax == 1 ? p[1][c] : p[2][c]);
+        acc = __fadd_rn(acc, v);                       // predict.py:101-106, in the caller's axis order
+      }
+      m[c] = __fdiv_rn(acc, (float)a.n_axes);          // predict.py:110
+    }
+    const size_t vox = ((size_t)z * n + y) * n + x;
+    if (a.out_mean != nullptr) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) a.out_mean[vox * C + c] = m[c];
+    }
+    if (a.out_labels != nullptr) {
+      int best = 0;
+#pragma unroll
+      for (int c = 1; c < C; ++c)
+        if (m[c] > m[best]) best = c;                  // first maximum wins (np.argmax, predict.py:38)
+      a.out_labels[vox] = (uint8_t)best;
+    }
+    if (a.out_u8 != nullptr) {
+      uint8_t q[C];
+      if (a.g1d != nullptr) {
+        float wgt = __fmul_rn(__fmul_rn(__ldg(a.g1d + a.z0 + z), __ldg(a.g1d + y)), __ldg(a.g1d + x));
+        wgt = __fdiv_rn(wgt, a.gmax);
+        wgt = fminf(fmaxf(wgt, a.lo), 1.0f);           // predict.py:345
+        const float den = fmaxf(wgt, 1e-3f);           // predict.py:253,255
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float pred = __fmul_rn(m[c], wgt);     // predict.py:244
+          q[c] = (uint8_t)(int)__fdiv_rn(__fmul_rn(255.0f, pred), den);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) q[c] = (uint8_t)(int)__fmul_rn(255.0f, m[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) a.out_u8[vox * C + c] = q[c];
+    }
+  }
+}
+
+cudaError_t launch_reduce(const ReduceArgs& args, cudaStream_t stream) {
+  if (args.n_axes < 1 || args.n_axes > 3) return cudaErrorInvalidValue;
+  dim3 grid((args.n + 31) / 32, (args.n + 31) / 32, args.t);
+  const int c = args.num_classes;
+  const size_t smem = (size_t)32 * (32 * c + 1) * sizeof(float);
+#define IU_REDUCE_CASE(C_)                                                                              \
+  case C_:                                                                                              \
+    cudaFuncSetAttribute(reduce_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    reduce_kernel<C_><<<grid, 256, smem, stream>>>(args);                                               \
+    break;
+  switch (c) {
+    IU_REDUCE_CASE(1)
+    IU_REDUCE_CASE(2)
+    IU_REDUCE_CASE(3)
+    IU_REDUCE_CASE(4)
+    IU_REDUCE_CASE(5)
+    IU_REDUCE_CASE(6)
+    IU_REDUCE_CASE(7)
+    IU_REDUCE_CASE(8)
+    IU_REDUCE_CASE(9)
+    IU_REDUCE_CASE(10)
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace iu

@@ -1,0 +1,45 @@
+// Non-tensor-core kernels of the volume-prediction path (HBM-bound byte/element work).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace iu {
+
+// K1: gather `count` slices [start, start+count) of a cubic volume along `axis` into contiguous
+// fp32 images out[b][row][col]; uint8 input is normalised with a true IEEE division by 255
+// (`predict.py:237` / `:30`), float input is copied.  Image (row,col) = (y,x) | (z,x) | (z,y).
+cudaError_t launch_gather_slices(const void* vol, int vol_is_f32, int n, int axis, int start, int count, float* out,
+                                 cudaStream_t stream);
+
+// Stem: 7x7 stride-2 pad-3 conv 1->64 with folded BatchNorm + ReLU, fp32 in, bf16 NHWC out.
+//   w_tap_major: [49][64] fp32, bias: [64] fp32.
+cudaError_t launch_stem(const float* x, int batch, int h, int w, const float* w_tap_major, const float* bias,
+                        __nv_bfloat16* out, cudaStream_t stream);
+
+// 3x3 stride-2 pad-1 max pool on NHWC bf16, C = 64.
+cudaError_t launch_maxpool(const __nv_bfloat16* in, int batch, int h, int w, int c, __nv_bfloat16* out,
+                           cudaStream_t stream);
+
+// K4: fused cross-axis accumulate + average + (Gaussian window blend) + uint8 quantise + argmax.
+//   p[a] : per-axis probabilities, fp32, slice-major, or nullptr if axis a is not used:
+//          p[0][((z*n + y)*n + x)*C + c],  p[1][((y*t + z)*n + x)*C + c],  p[2][((x*t + z)*n + y)*C + c]
+//          with z in [0,t) local to the slab, y,x in [0,n)
+//   order: the axes in accumulation order (`predict.py:87`), n_axes of them
+//   g1d  : the 1-D Gaussian factor (n floats, device) or nullptr for "no window";
+//          window = clip((g[z0+z]*g[y])*g[x] / gmax, lo, 1)   (`predict.py:327-347`)
+//   outputs (any may be nullptr): uint8 probs [t][n][n][C], uint8 labels [t][n][n], fp32 mean [t][n][n][C]
+struct ReduceArgs {
+  const float* p[3];
+  int order[3];
+  int n_axes;
+  int n, t, z0, num_classes;
+  const float* g1d;
+  float gmax, lo;
+  uint8_t* out_u8;
+  uint8_t* out_labels;
+  float* out_mean;
+};
+cudaError_t launch_reduce(const ReduceArgs& args, cudaStream_t stream);
+
+}  // namespace iu

@@ -1,0 +1,301 @@
+// Implicit-GEMM convolution on the sm_100a tensor cores.
+//
+//   D[128 pixels, BN channels] = sum over (segment, tap r,s, channel chunk)  A_tap[128, KC] * W_tap[BN, KC]^T
+//
+// * activations are NHWC bf16; the A tile of one filter tap is ONE 4-D TMA box (KC channels x tw cols x
+//   th rows x nb images) fetched at the tap's offset: out-of-bounds coordinates are zero-filled by the
+//   TMA unit, which is the convolution's zero padding; stride-2 convs use the map's element strides.
+// * weights are pre-packed [Cout_pad][K] bf16 (K ordered exactly like the loop above) and fetched as
+//   2-D TMA boxes; both operands land in the 128B/64B/32B-swizzled K-major layout tcgen05.mma reads.
+// * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator; a ring of
+//   mbarrier-guarded stages decouples the TMA producer warp from the MMA warp.
+// * four epilogue warps read the accumulator with tcgen05.ld and fuse folded-BN bias, residual add,
+//   ReLU, bf16 pack, optional nearest-2x upsampled store, or (head conv) softmax + probability store.
+//
+// Replaces the cuDNN conv2d / batch_norm / relu / add / cat / upsample_nearest2d / softmax launches
+// issued by `smp.Unet.forward` under `/root/reference/interactive_unet/unet.py:67`.
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace iu {
+
+template <int KC, int BN>
+struct ConvCfg {
+  static constexpr int SW = KC * 2;  // bytes per operand row == TMA/UMMA swizzle span
+  static constexpr int A_BYTES = kTileM * KC * 2;
+  static constexpr int B_BYTES = BN * KC * 2;
+  static constexpr int B_ALLOC = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = A_BYTES + B_ALLOC;
+  static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int BAR_BYTES = (2 * STAGES + 2) * 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int CHUNK = BN >= 32 ? 32 : 16;                            // accumulator columns per tcgen05.ld
+};
+
+constexpr int kThreads = 192;  // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+template <int KC, int BN>
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
+  using Cfg = ConvCfg<KC, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t accum_bar = bar_base + 16u * Cfg::STAGES;
+  const uint32_t tmem_slot = accum_bar + 8u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile -> (image group, row block, column block)
+  const int tile = blockIdx.x;
+  const int tx = tile % a.tiles_x;
+  const int ty = (tile / a.tiles_x) % a.tiles_y;
+  const int tn = tile / (a.tiles_x * a.tiles_y);
+  const int x0 = tx * a.tw, y0 = ty * a.th, n0 = tn * a.nb;
+  const int ntile = blockIdx.y;
+
+  int total_iters = 0;
+  for (int s = 0; s < a.nseg; ++s) total_iters += a.seg[s].ksize * a.seg[s].ksize * (a.seg[s].cin / KC);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.amap[0]);
+    if (a.nseg > 1) tma_prefetch_desc(&a.amap[1]);
+    tma_prefetch_desc(&a.bmap);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int s = 0; s < a.nseg; ++s) {
+        const ConvSegment sg = a.seg[s];
+        const int chunks = sg.cin / KC;
+        for (int r = 0; r < sg.ksize; ++r) {
+          for (int q = 0; q < sg.ksize; ++q) {
+            for (int cc = 0; cc < chunks; ++cc, ++it) {
+              const int st = it % Cfg::STAGES;
+              const uint32_t ph = (it / Cfg::STAGES) & 1;
+              mbar_wait(empty_bar(st), ph ^ 1u);
+              mbar_arrive_expect_tx(full_bar(st), Cfg::A_BYTES + Cfg::B_BYTES);
+              const uint32_t sa = base + st * Cfg::STAGE_BYTES;
+              tma_load_4d(sa, &a.amap[s], full_bar(st), cc * KC, x0 * sg.stride - sg.pad + q,
+                          y0 * sg.stride - sg.pad + r, n0);
+              tma_load_2d(sa + Cfg::A_BYTES, &a.bmap, full_bar(st), it * KC, ntile * BN);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+      for (int it = 0; it < total_iters; ++it) {
+        const int st = it % Cfg::STAGES;
+        const uint32_t ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(full_bar(st), ph);
+        tc_fence_after();
+        const uint32_t sa = base + st * Cfg::STAGE_BYTES;
+        const uint64_t adesc = umma_smem_desc<Cfg::SW>(sa);
+        const uint64_t bdesc = umma_smem_desc<Cfg::SW>(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k) {
+          // advancing K by 16 bf16 = 32 bytes inside the swizzle span = +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(st));  // stage reusable once these MMAs have read it
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lanes [32q, 32q+32) are the only ones this warp may read
+    const int row = quarter * 32 + lane;
+    const int per_img = a.th * a.tw;
+    const int n = n0 + row / per_img;
+    const int y = y0 + (row % per_img) / a.tw;
+    const int x = x0 + row % a.tw;
+    const bool valid = (n < a.batch) && (y < a.out_h) && (x < a.out_w);
+
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    if (a.mode == kEpiBf16) {
+      const size_t pix = ((size_t)n * a.out_h + y) * a.out_w + x;
+      const int col0 = ntile * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / Cfg::CHUNK; ++ch) {
+        uint32_t acc[Cfg::CHUNK];
+        if constexpr (Cfg::CHUNK == 32) tmem_ld_32x32(taddr + ch * Cfg::CHUNK, reinterpret_cast<uint32_t(&)[32]>(acc));
+        else tmem_ld_32x16(taddr + ch * Cfg::CHUNK, reinterpret_cast<uint32_t(&)[16]>(acc));
+        tmem_ld_wait();
+        if (valid) {
+          const int c = col0 + ch * Cfg::CHUNK;
+          float v[Cfg::CHUNK];
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(a.bias + c + j);
+            v[j] = __uint_as_float(acc[j]) + b.x;
+            v[j + 1] = __uint_as_float(acc[j + 1]) + b.y;
+            v[j + 2] = __uint_as_float(acc[j + 2]) + b.z;
+            v[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
+          }
+          if (a.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.cout + c);
+#pragma unroll
+            for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
+              const uint4 rv = __ldg(rp + j);
+              v[8 * j + 0] += bf16_lo(rv.x); v[8 * j + 1] += bf16_hi(rv.x);
+              v[8 * j + 2] += bf16_lo(rv.y); v[8 * j + 3] += bf16_hi(rv.y);
+              v[8 * j + 4] += bf16_lo(rv.z); v[8 * j + 5] += bf16_hi(rv.z);
+              v[8 * j + 6] += bf16_lo(rv.w); v[8 * j + 7] += bf16_hi(rv.w);
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < Cfg::CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+          uint4 pk[Cfg::CHUNK / 8];
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
+            pk[j].x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+            pk[j].y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            pk[j].z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+            pk[j].w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+          }
+          __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+          if (!a.up2x) {
+            uint4* dst = reinterpret_cast<uint4*>(outp + pix * a.cout + c);
+#pragma unroll
+            for (int j = 0; j < Cfg::CHUNK / 8; ++j) dst[j] = pk[j];
+          } else {
+            const int oh = 2 * a.out_h, ow = 2 * a.out_w;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+              const size_t up = ((size_t)n * oh + 2 * y + (d >> 1)) * ow + 2 * x + (d & 1);
+              uint4* dst = reinterpret_cast<uint4*>(outp + up * a.cout + c);
+#pragma unroll
+              for (int j = 0; j < Cfg::CHUNK / 8; ++j) dst[j] = pk[j];
+            }
+          }
+        }
+      }
+    } else {
+      // head: logits live in the first num_classes accumulator columns
+      uint32_t acc[16];
+      tmem_ld_32x16(taddr, acc);
+      tmem_ld_wait();
+      if (valid) {
+        const int nc = a.num_classes;
+        float l[16];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          l[j] = (j < nc) ? __uint_as_float(acc[j]) + a.bias[j] : -INFINITY;
+          mx = fmaxf(mx, l[j]);
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          l[j] = (j < nc) ? expf(l[j] - mx) : 0.0f;
+          sum += l[j];
+        }
+        float* outp = reinterpret_cast<float*>(a.out);
+        if (a.mode == kEpiSoftmaxNHWC) {
+          const size_t rowoff =
+              ((size_t)(y / a.row_block) * a.slice_count + a.slice0 + n) * a.row_block + (y % a.row_block);
+          float* dst = outp + (rowoff * a.out_w + x) * nc;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nc) dst[j] = __fdiv_rn(l[j], sum);
+        } else {
+          const size_t plane = (size_t)a.out_h * a.out_w;
+          float* dst = outp + (size_t)n * nc * plane + (size_t)y * a.out_w + x;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nc) dst[j * plane] = __fdiv_rn(l[j], sum);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int KC, int BN>
+static cudaError_t launch_one(const ConvArgs& args, cudaStream_t stream) {
+  using Cfg = ConvCfg<KC, BN>;
+  static bool configured = false;  // per kernel instantiation; the attribute is per device, set again on any change
+  static int configured_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured || configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+    configured_dev = dev;
+  }
+  const int mtiles = args.tiles_x * args.tiles_y * ((args.batch + args.nb - 1) / args.nb);
+  const int cout_pad = (args.mode == kEpiBf16) ? args.cout : BN;
+  dim3 grid(mtiles, cout_pad / BN, 1);
+  conv_tc_kernel<KC, BN><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(args);
+  return cudaGetLastError();
+}
+
+#define IU_CONV_DISPATCH(KC_, BN_) \
+  if (kc == KC_ && bn == BN_) return launch_one<KC_, BN_>(args, stream);
+
+cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream) {
+  IU_CONV_DISPATCH(64, 128)
+  IU_CONV_DISPATCH(64, 64)
+  IU_CONV_DISPATCH(64, 32)
+  IU_CONV_DISPATCH(32, 32)
+  IU_CONV_DISPATCH(32, 16)
+  IU_CONV_DISPATCH(16, 16)
+  return cudaErrorInvalidValue;
+}
+
+int conv_tc_smem_bytes(int kc, int bn) {
+#define IU_CONV_SMEM(KC_, BN_) \
+  if (kc == KC_ && bn == BN_) return ConvCfg<KC_, BN_>::SMEM_BYTES;
+  IU_CONV_SMEM(64, 128)
+  IU_CONV_SMEM(64, 64)
+  IU_CONV_SMEM(64, 32)
+  IU_CONV_SMEM(32, 32)
+  IU_CONV_SMEM(32, 16)
+  IU_CONV_SMEM(16, 16)
+  return -1;
+}
+
+}  // namespace iu

@@ -1,0 +1,56 @@
+// Host-visible description of one tensor-core convolution launch (see conv_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace iu {
+
+constexpr int kTileM = 128;  // output pixels per CTA tile = UMMA M
+
+enum EpilogueMode : int {
+  kEpiBf16 = 0,         // bias (+residual) (+ReLU) -> bf16 NHWC (optionally written 2x nearest-upsampled)
+  kEpiSoftmaxNHWC = 1,  // bias -> softmax over the first num_classes columns -> fp32 [slice][row][col][C]
+  kEpiSoftmaxNCHW = 2,  // bias -> softmax -> fp32 [n][C][row][col]
+};
+
+// One K segment of the implicit GEMM: a source activation tensor (NHWC bf16) read through a
+// k x k window with the given stride / padding.  A conv has 1 or 2 segments:
+//   cat([a, b], dim=1) -> 3x3   = {a, 3, 1, 1} + {b, 3, 1, 1}
+//   conv3x3(t) + downsample(x)  = {t, 3, 1, 1} + {x, 1, 2, 0}
+struct ConvSegment {
+  int cin;     // channels of this source (multiple of the K chunk)
+  int ksize;   // 1 or 3
+  int stride;  // 1 or 2
+  int pad;     // 0 or 1
+};
+
+struct alignas(64) ConvArgs {
+  CUtensorMap amap[2];  // 4-D maps (C, W, H, N) over the segment sources, box = (KC, tw*stride, th*stride, nb)
+  CUtensorMap bmap;     // 2-D map (K, Cout_pad) over the packed weights, box = (KC, BN)
+  ConvSegment seg[2];
+  int nseg;
+  int batch, out_h, out_w;  // output geometry (before the optional 2x upsample)
+  int cout;                 // real output channels (bf16 mode: multiple of BN)
+  int tw, th, nb;           // tile = nb images x th rows x tw cols = 128 pixels
+  int tiles_x, tiles_y;
+  const float* bias;              // [Cout_pad] folded BatchNorm shift (or conv bias)
+  const __nv_bfloat16* residual;  // optional, same geometry as the output
+  void* out;
+  int relu;
+  int up2x;         // bf16 mode: write every pixel to its 2x2 nearest-upsampled positions
+  int mode;         // EpilogueMode
+  int num_classes;  // softmax modes
+  // softmax NHWC addressing (lets one buffer be laid out destination-major for the multi-GPU exchange):
+  //   off(n, y, x) = (((y / row_block) * slice_count + slice0 + n) * row_block + y % row_block) * out_w + x
+  int slice0, slice_count, row_block;
+};
+
+// Launch on `stream`; KC = min(64, cin), BN = min(128, Cout_pad).  Returns cudaGetLastError().
+cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream);
+
+// Shared memory the kernel variant needs (for occupancy planning / tests).
+int conv_tc_smem_bytes(int kc, int bn);
+
+}  // namespace iu

@@ -1,0 +1,977 @@
+// Host side of the engine behind include/iunet_b200.h: weight folding / packing, the layer program of
+// smp.Unet('resnet34'), workspace + TMA descriptor planning, and the C ABI.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "conv_tc.cuh"
+#include "iunet_b200.h"
+
+using namespace iu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TensorSpec {
+  int c;
+  int hdiv;  // spatial size = input size / hdiv
+};
+
+struct ConvLayer {
+  std::string name;
+  int nseg = 1;
+  ConvSegment seg[2];
+  int src[2] = {-1, -1};
+  int out = -1;       // tensor id (bf16 modes); -1 for the head
+  int residual = -1;  // tensor id or -1
+  int relu = 1, up2x = 0, mode = kEpiBf16;
+  int cout = 0, cout_pad = 0, ktot = 0, kc = 0, bn = 0;
+  int out_hdiv = 1;  // output geometry BEFORE the optional 2x upsample
+  __nv_bfloat16* d_w = nullptr;
+  float* d_b = nullptr;
+};
+
+struct Plan {
+  int batch = 0, batch_pad = 0, h = 0, w = 0;
+  std::vector<__nv_bfloat16*> bufs;
+  float* x_in = nullptr;
+  std::vector<ConvArgs> args;
+  size_t bytes = 0;
+};
+
+struct Scratch {
+  void* ptr;
+  size_t bytes;
+  bool used;
+};
+
+uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+bool pick_tile(int cin_min, int cout_pad, int* kc, int* bn) {
+  *kc = cin_min >= 64 ? 64 : cin_min;
+  *bn = cout_pad >= 128 ? 128 : cout_pad;
+  return conv_tc_smem_bytes(*kc, *bn) > 0;
+}
+
+}  // namespace
+
+struct iu_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  EncodeTiledFn encode = nullptr;
+  int num_classes = 0;
+  bool loaded = false;
+  int max_batch = 0;
+  int64_t launches = 0;
+  size_t weight_bytes = 0;
+
+  float* d_stem_w = nullptr;
+  float* d_stem_b = nullptr;
+  std::vector<TensorSpec> tensors;
+  std::vector<ConvLayer> convs;
+  int t_f1 = -1, t_p1 = -1;
+  Plan plan;
+  std::vector<Scratch> scratch;
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char* what) {
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError();
+      return fail(IU_ERR_OOM, std::string("CUDA out of memory (") + what + ")");
+    }
+    return fail(IU_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+};
+
+#define IU_CUDA(e_, call_)                                   \
+  do {                                                       \
+    cudaError_t _err = (call_);                              \
+    if (_err != cudaSuccess) return (e_)->cuda_fail(_err, #call_); \
+  } while (0)
+
+namespace {
+
+// ------------------------------------------------------------------ scratch pool
+int scratch_get(iu_engine* e, size_t bytes, void** out) {
+  int best = -1;
+  for (size_t i = 0; i < e->scratch.size(); ++i)
+    if (!e->scratch[i].used && e->scratch[i].bytes >= bytes &&
+        (best < 0 || e->scratch[i].bytes < e->scratch[best].bytes))
+      best = (int)i;
+  if (best >= 0) {
+    e->scratch[best].used = true;
+    *out = e->scratch[best].ptr;
+    return IU_OK;
+  }
+  void* p = nullptr;
+  cudaError_t ce = cudaMalloc(&p, bytes ? bytes : 16);
+  if (ce != cudaSuccess) {
+    // drop idle cached blocks and retry once
+    for (auto& s : e->scratch)
+      if (!s.used && s.ptr) {
+        cudaFree(s.ptr);
+        s.ptr = nullptr;
+        s.bytes = 0;
+      }
+    cudaGetLastError();
+    ce = cudaMalloc(&p, bytes ? bytes : 16);
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaMalloc(scratch)");
+  }
+  e->scratch.push_back({p, bytes, true});
+  *out = p;
+  return IU_OK;
+}
+void scratch_put(iu_engine* e, void* p) {
+  if (!p) return;
+  for (auto& s : e->scratch)
+    if (s.ptr == p) s.used = false;
+}
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// ------------------------------------------------------------------ weights
+struct HostTensors {
+  std::map<std::string, std::pair<const float*, int64_t>> t;
+  const float* get(const std::string& k, int64_t numel, std::string* err) const {
+    auto it = t.find(k);
+    if (it == t.end()) {
+      *err = "missing tensor '" + k + "'";
+      return nullptr;
+    }
+    if (it->second.second != numel) {
+      *err = "tensor '" + k + "' has " + std::to_string(it->second.second) + " elements, expected " +
+             std::to_string(numel);
+      return nullptr;
+    }
+    return it->second.first;
+  }
+};
+
+// Eval-mode BatchNorm folded into the preceding bias-free conv:
+//   y = (conv(x) - mean) * gamma / sqrt(var + eps) + beta  =  conv_{w * s}(x) + (beta - mean * s)
+bool fold_bn(const HostTensors& ht, const std::string& conv_w, const std::string& bn, int cout, int64_t per_out,
+             std::vector<float>* w, std::vector<float>* b, std::string* err) {
+  const float* cw = ht.get(conv_w, (int64_t)cout * per_out, err);
+  const float* g = ht.get(bn + ".weight", cout, err);
+  const float* be = ht.get(bn + ".bias", cout, err);
+  const float* mu = ht.get(bn + ".running_mean", cout, err);
+  const float* var = ht.get(bn + ".running_var", cout, err);
+  if (!cw || !g || !be || !mu || !var) return false;
+  w->resize((size_t)cout * per_out);
+  b->resize(cout);
+  for (int co = 0; co < cout; ++co) {
+    const double s = (double)g[co] / std::sqrt((double)var[co] + 1e-5);
+    for (int64_t i = 0; i < per_out; ++i) (*w)[co * per_out + i] = (float)((double)cw[co * per_out + i] * s);
+    (*b)[co] = (float)((double)be[co] - (double)mu[co] * s);
+  }
+  return true;
+}
+
+// K order of the implicit GEMM: segment -> tap row -> tap col -> channel (see conv_tc.cu producer loop).
+void pack_segment(std::vector<uint16_t>& dst, int ktot, int kbase, const float* w, int cout, int cin_total, int coff,
+                  int cin_s, int ks) {
+  for (int co = 0; co < cout; ++co)
+    for (int r = 0; r < ks; ++r)
+      for (int q = 0; q < ks; ++q)
+        for (int c = 0; c < cin_s; ++c)
+          dst[(size_t)co * ktot + kbase + (r * ks + q) * cin_s + c] =
+              f2bf(w[(((size_t)co * cin_total + coff + c) * ks + r) * ks + q]);
+}
+
+int upload_conv(iu_engine* e, ConvLayer& L, const std::vector<uint16_t>& packed, const std::vector<float>& bias) {
+  IU_CUDA(e, cudaMalloc(&L.d_w, packed.size() * 2));
+  IU_CUDA(e, cudaMalloc(&L.d_b, (size_t)L.cout_pad * 4));
+  std::vector<float> bp(L.cout_pad, 0.0f);
+  std::copy(bias.begin(), bias.end(), bp.begin());
+  IU_CUDA(e, cudaMemcpy(L.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+  IU_CUDA(e, cudaMemcpy(L.d_b, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+  e->weight_bytes += packed.size() * 2 + bp.size() * 4;
+  return IU_OK;
+}
+
+void free_weights(iu_engine* e) {
+  for (auto& L : e->convs) {
+    if (L.d_w) cudaFree(L.d_w);
+    if (L.d_b) cudaFree(L.d_b);
+  }
+  e->convs.clear();
+  e->tensors.clear();
+  if (e->d_stem_w) cudaFree(e->d_stem_w);
+  if (e->d_stem_b) cudaFree(e->d_stem_b);
+  e->d_stem_w = e->d_stem_b = nullptr;
+  e->loaded = false;
+  e->weight_bytes = 0;
+}
+
+void free_plan(iu_engine* e) {
+  for (auto p : e->plan.bufs)
+    if (p) cudaFree(p);
+  if (e->plan.x_in) cudaFree(e->plan.x_in);
+  e->plan = Plan();
+}
+
+int new_tensor(iu_engine* e, int c, int hdiv) {
+  e->tensors.push_back({c, hdiv});
+  return (int)e->tensors.size() - 1;
+}
+
+// Build one folded conv layer (+ optional fused 1x1/s2 downsample as a second K segment).
+int add_conv(iu_engine* e, const HostTensors& ht, const std::string& name, const std::string& conv_key,
+             const std::string& bn_key, int nsrc, const int* src, const int* src_cin, int ksize, int stride,
+             int cout, int out_tensor, int out_hdiv, int residual, int relu, int up2x, const std::string& ds_conv,
+             const std::string& ds_bn, int ds_src, int ds_cin) {
+  ConvLayer L;
+  L.name = name;
+  L.cout = cout;
+  L.cout_pad = (cout + 15) / 16 * 16;
+  L.out = out_tensor;
+  L.out_hdiv = out_hdiv;
+  L.residual = residual;
+  L.relu = relu;
+  L.up2x = up2x;
+  int cin_total = 0, cin_min = 1 << 30;
+  for (int s = 0; s < nsrc; ++s) {
+    cin_total += src_cin[s];
+    cin_min = std::min(cin_min, src_cin[s]);
+  }
+  std::vector<float> w, b;
+  std::string err;
+  if (!fold_bn(ht, conv_key, bn_key, cout, (int64_t)cin_total * ksize * ksize, &w, &b, &err))
+    return e->fail(IU_ERR_INVALID, err);
+  L.nseg = nsrc;
+  int k = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    L.seg[s] = {src_cin[s], ksize, stride, ksize / 2};
+    L.src[s] = src[s];
+    k += ksize * ksize * src_cin[s];
+  }
+  std::vector<float> wd, bd;
+  if (!ds_conv.empty()) {
+    if (nsrc != 1) return e->fail(IU_ERR_INVALID, "downsample fusion needs a single main source");
+    if (!fold_bn(ht, ds_conv, ds_bn, cout, ds_cin, &wd, &bd, &err)) return e->fail(IU_ERR_INVALID, err);
+    L.nseg = 2;
+    L.seg[1] = {ds_cin, 1, 2, 0};
+    L.src[1] = ds_src;
+    k += ds_cin;
+    cin_min = std::min(cin_min, ds_cin);
+    for (int co = 0; co < cout; ++co) b[co] += bd[co];
+  }
+  L.ktot = k;
+  if (!pick_tile(cin_min, L.cout_pad, &L.kc, &L.bn))
+    return e->fail(IU_ERR_INVALID, "no kernel variant for layer " + name);
+  for (int s = 0; s < L.nseg; ++s)
+    if (L.seg[s].cin % L.kc) return e->fail(IU_ERR_INVALID, "channel count not a multiple of the K chunk: " + name);
+  std::vector<uint16_t> packed((size_t)L.cout_pad * L.ktot, 0);
+  int kbase = 0, coff = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    pack_segment(packed, L.ktot, kbase, w.data(), cout, cin_total, coff, src_cin[s], ksize);
+    kbase += ksize * ksize * src_cin[s];
+    coff += src_cin[s];
+  }
+  if (!ds_conv.empty()) pack_segment(packed, L.ktot, kbase, wd.data(), cout, ds_cin, 0, ds_cin, 1);
+  int rc = upload_conv(e, L, packed, b);
+  if (rc != IU_OK) return rc;
+  e->convs.push_back(L);
+  return IU_OK;
+}
+
+int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
+  std::string err;
+  // ---- stem: encoder.conv1 + bn1 (+ReLU), CUDA-core kernel, fp32 weights tap-major [49][64]
+  {
+    std::vector<float> w, b;
+    if (!fold_bn(ht, "encoder.conv1.weight", "encoder.bn1", 64, 49, &w, &b, &err)) return e->fail(IU_ERR_INVALID, err);
+    std::vector<float> wt(49 * 64);
+    for (int co = 0; co < 64; ++co)
+      for (int tap = 0; tap < 49; ++tap) wt[tap * 64 + co] = w[co * 49 + tap];
+    IU_CUDA(e, cudaMalloc(&e->d_stem_w, wt.size() * 4));
+    IU_CUDA(e, cudaMalloc(&e->d_stem_b, 64 * 4));
+    IU_CUDA(e, cudaMemcpy(e->d_stem_w, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+    IU_CUDA(e, cudaMemcpy(e->d_stem_b, b.data(), 64 * 4, cudaMemcpyHostToDevice));
+    e->weight_bytes += wt.size() * 4 + 256;
+  }
+  e->t_f1 = new_tensor(e, 64, 2);
+  e->t_p1 = new_tensor(e, 64, 4);
+
+  // ---- encoder: torchvision ResNet-34 BasicBlocks [3,4,6,3]
+  const int nblocks[4] = {3, 4, 6, 3};
+  const int chans[4] = {64, 128, 256, 512};
+  int cur = e->t_p1, cur_c = 64, cur_hdiv = 4;
+  int feat[6] = {-1, e->t_f1, -1, -1, -1, -1};
+  for (int li = 0; li < 4; ++li) {
+    const int cout = chans[li];
+    for (int b = 0; b < nblocks[li]; ++b) {
+      const std::string base = "encoder.layer" + std::to_string(li + 1) + "." + std::to_string(b);
+      const bool down = (li > 0 && b == 0);
+      const int stride = down ? 2 : 1;
+      const int hdiv = cur_hdiv * stride;
+      const bool last = (li == 3 && b == nblocks[li] - 1);
+      const int t = new_tensor(e, cout, hdiv);
+      int rc = add_conv(e, ht, base + ".conv1", base + ".conv1.weight", base + ".bn1", 1, &cur, &cur_c, 3, stride,
+                        cout, t, hdiv, -1, 1, 0, "", "", -1, 0);
+      if (rc != IU_OK) return rc;
+      // the last encoder feature is consumed only through the decoder's 2x nearest upsample: write it upsampled
+      const int o = new_tensor(e, cout, last ? hdiv / 2 : hdiv);
+      if (down)
+        rc = add_conv(e, ht, base + ".conv2+downsample", base + ".conv2.weight", base + ".bn2", 1, &t, &cout, 3, 1,
+                      cout, o, hdiv, -1, 1, last ? 1 : 0, base + ".downsample.0.weight", base + ".downsample.1", cur,
+                      cur_c);
+      else
+        rc = add_conv(e, ht, base + ".conv2", base + ".conv2.weight", base + ".bn2", 1, &t, &cout, 3, 1, cout, o,
+                      hdiv, cur, 1, last ? 1 : 0, "", "", -1, 0);
+      if (rc != IU_OK) return rc;
+      cur = o;
+      cur_c = cout;
+      cur_hdiv = hdiv;
+    }
+    feat[li + 2] = cur;
+  }
+  // ---- decoder (smp UnetDecoder): x = cat([up2x(x), skip]) -> conv1 -> conv2; the 2x nearest upsample of
+  //      every block output is produced by its conv2 epilogue (up2x store), so conv1 reads plain tensors.
+  const int dec_out[5] = {256, 128, 64, 32, 16};
+  const int skip_t[5] = {feat[4], feat[3], feat[2], feat[1], -1};
+  const int skip_c[5] = {256, 128, 64, 64, 0};
+  int x = cur, x_c = 512;  // already upsampled to 1/16
+  for (int i = 0; i < 5; ++i) {
+    const int hdiv = 16 >> i;
+    const std::string base = "decoder.blocks." + std::to_string(i);
+    const int t = new_tensor(e, dec_out[i], hdiv);
+    int srcs[2] = {x, skip_t[i]};
+    int cins[2] = {x_c, skip_c[i]};
+    int rc = add_conv(e, ht, base + ".conv1", base + ".conv1.0.weight", base + ".conv1.1", skip_t[i] >= 0 ? 2 : 1,
+                      srcs, cins, 3, 1, dec_out[i], t, hdiv, -1, 1, 0, "", "", -1, 0);
+    if (rc != IU_OK) return rc;
+    const bool up = i < 4;
+    const int o = new_tensor(e, dec_out[i], up ? hdiv / 2 : hdiv);
+    rc = add_conv(e, ht, base + ".conv2", base + ".conv2.0.weight", base + ".conv2.1", 1, &t, &dec_out[i], 3, 1,
+                  dec_out[i], o, hdiv, -1, 1, up ? 1 : 0, "", "", -1, 0);
+    if (rc != IU_OK) return rc;
+    x = o;
+    x_c = dec_out[i];
+  }
+  // ---- segmentation head: Conv2d(16, C, 3, padding=1) with bias, then the reference's Softmax(dim=1)
+  {
+    ConvLayer L;
+    L.name = "segmentation_head.0";
+    L.cout = num_classes;
+    L.cout_pad = 16;
+    L.nseg = 1;
+    L.seg[0] = {16, 3, 1, 1};
+    L.src[0] = x;
+    L.out = -1;
+    L.out_hdiv = 1;
+    L.relu = 0;
+    L.mode = kEpiSoftmaxNHWC;
+    L.ktot = 9 * 16;
+    L.kc = 16;
+    L.bn = 16;
+    const float* w = ht.get("segmentation_head.0.weight", (int64_t)num_classes * 16 * 9, &err);
+    const float* b = ht.get("segmentation_head.0.bias", num_classes, &err);
+    if (!w || !b) return e->fail(IU_ERR_INVALID, err);
+    std::vector<uint16_t> packed((size_t)16 * L.ktot, 0);
+    pack_segment(packed, L.ktot, 0, w, num_classes, 16, 0, 16, 3);
+    int rc = upload_conv(e, L, packed, std::vector<float>(b, b + num_classes));
+    if (rc != IU_OK) return rc;
+    e->convs.push_back(L);
+  }
+  return IU_OK;
+}
+
+// ------------------------------------------------------------------ planning
+int encode_act_map(iu_engine* e, CUtensorMap* m, const void* base, int c, int w, int h, int n, int kc, int boxw,
+                   int boxh, int boxn, int estride) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)boxw, (cuuint32_t)boxh, (cuuint32_t)boxn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  const CUtensorMapSwizzle swz =
+      kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = e->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return e->fail(IU_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed with CUresult " + std::to_string((int)r));
+  return IU_OK;
+}
+int encode_weight_map(iu_engine* e, CUtensorMap* m, const void* base, int ktot, int cout_pad, int kc, int bn) {
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle swz =
+      kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = e->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return e->fail(IU_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed with CUresult " + std::to_string((int)r));
+  return IU_OK;
+}
+
+// Fill the geometry / tile fields of a ConvArgs for an output of out_h x out_w.
+void set_tiling(ConvArgs* a, int batch, int out_h, int out_w) {
+  a->batch = batch;
+  a->out_h = out_h;
+  a->out_w = out_w;
+  a->tw = std::min(16, pow2_ceil(out_w));
+  a->th = std::min(kTileM / a->tw, pow2_ceil(out_h));
+  a->nb = kTileM / (a->tw * a->th);
+  a->tiles_x = (out_w + a->tw - 1) / a->tw;
+  a->tiles_y = (out_h + a->th - 1) / a->th;
+}
+
+size_t plan_bytes(const iu_engine* e, int batch_pad, int h, int w) {
+  size_t total = (size_t)batch_pad * h * w * 4;
+  for (const auto& t : e->tensors) total += (size_t)batch_pad * (h / t.hdiv) * (w / t.hdiv) * t.c * 2;
+  return total;
+}
+
+int ensure_plan(iu_engine* e, int batch, int h, int w) {
+  if (e->plan.batch == batch && e->plan.h == h && e->plan.w == w) return IU_OK;
+  free_plan(e);
+  Plan& p = e->plan;
+  const int bp = (batch + 7) / 8 * 8;  // images are tiled in groups of up to 8: keep every TMA box inside the tensor
+  p.bufs.assign(e->tensors.size(), nullptr);
+  for (size_t i = 0; i < e->tensors.size(); ++i) {
+    const TensorSpec& t = e->tensors[i];
+    const size_t bytes = (size_t)bp * (h / t.hdiv) * (w / t.hdiv) * t.c * 2;
+    cudaError_t ce = cudaMalloc(&p.bufs[i], bytes);
+    if (ce != cudaSuccess) {
+      free_plan(e);
+      return e->cuda_fail(ce, "cudaMalloc(activations)");
+    }
+    cudaMemsetAsync(p.bufs[i], 0, bytes, e->stream);
+    p.bytes += bytes;
+  }
+  {
+    cudaError_t ce = cudaMalloc(&p.x_in, (size_t)bp * h * w * 4);
+    if (ce != cudaSuccess) {
+      free_plan(e);
+      return e->cuda_fail(ce, "cudaMalloc(input slices)");
+    }
+    p.bytes += (size_t)bp * h * w * 4;
+  }
+  p.args.resize(e->convs.size());
+  for (size_t i = 0; i < e->convs.size(); ++i) {
+    const ConvLayer& L = e->convs[i];
+    ConvArgs& a = p.args[i];
+    memset(&a, 0, sizeof(a));
+    set_tiling(&a, batch, h / L.out_hdiv, w / L.out_hdiv);
+    a.nseg = L.nseg;
+    for (int s = 0; s < L.nseg; ++s) {
+      a.seg[s] = L.seg[s];
+      const TensorSpec& ts = e->tensors[L.src[s]];
+      const int st = L.seg[s].stride;
+      int rc = encode_act_map(e, &a.amap[s], p.bufs[L.src[s]], ts.c, w / ts.hdiv, h / ts.hdiv, bp, L.kc, a.tw * st,
+                              a.th * st, a.nb, st);
+      if (rc != IU_OK) {
+        free_plan(e);
+        return rc;
+      }
+    }
+    int rc = encode_weight_map(e, &a.bmap, L.d_w, L.ktot, L.cout_pad, L.kc, L.bn);
+    if (rc != IU_OK) {
+      free_plan(e);
+      return rc;
+    }
+    a.cout = L.cout;
+    a.bias = L.d_b;
+    a.residual = L.residual >= 0 ? p.bufs[L.residual] : nullptr;
+    a.out = L.out >= 0 ? p.bufs[L.out] : nullptr;
+    a.relu = L.relu;
+    a.up2x = L.up2x;
+    a.mode = L.mode;
+    a.num_classes = e->num_classes;
+    a.slice0 = 0;
+    a.slice_count = batch;
+    a.row_block = h;
+  }
+  p.batch = batch;
+  p.batch_pad = bp;
+  p.h = h;
+  p.w = w;
+  return IU_OK;
+}
+
+int auto_batch(const iu_engine* e, int h, int w, int want) {
+  // enough slices that the deepest layers (1/32 resolution) still fill the 148 SMs, bounded for memory
+  double b = 32.0 * (512.0 / h) * (512.0 / w);
+  int nb = (int)std::max(1.0, std::min(128.0, std::floor(b)));
+  if (e->max_batch > 0) nb = std::min(nb, e->max_batch);
+  return std::max(1, std::min(nb, want));
+}
+
+// Run the network on the `batch` slices already in plan.x_in; the head writes according to (mode, out, ...).
+int run_network(iu_engine* e, int batch, int head_mode, float* head_out, int slice0, int slice_count, int row_block) {
+  Plan& p = e->plan;
+  IU_CUDA(e, launch_stem(p.x_in, batch, p.h, p.w, e->d_stem_w, e->d_stem_b, p.bufs[e->t_f1], e->stream));
+  IU_CUDA(e, launch_maxpool(p.bufs[e->t_f1], batch, p.h / 2, p.w / 2, 64, p.bufs[e->t_p1], e->stream));
+  e->launches += 2;
+  for (size_t i = 0; i < e->convs.size(); ++i) {
+    const ConvLayer& L = e->convs[i];
+    ConvArgs a = p.args[i];
+    a.batch = batch;
+    if (L.mode != kEpiBf16) {
+      a.mode = head_mode;
+      a.out = head_out;
+      a.slice0 = slice0;
+      a.slice_count = slice_count;
+      a.row_block = row_block;
+    }
+    cudaError_t ce = launch_conv_tc(a, L.kc, L.bn, e->stream);
+    if (ce != cudaSuccess) return e->cuda_fail(ce, ("launch " + L.name).c_str());
+    e->launches += 1;
+  }
+  return IU_OK;
+}
+
+int finish(iu_engine* e, unsigned flags) {
+  if (flags & IU_FLAG_ASYNC) return IU_OK;
+  IU_CUDA(e, cudaStreamSynchronize(e->stream));
+  return IU_OK;
+}
+
+bool check_engine(iu_engine* e, bool need_weights, int* rc) {
+  if (!e) {
+    *rc = IU_ERR_INVALID;
+    return false;
+  }
+  cudaError_t ce = cudaSetDevice(e->device);
+  if (ce != cudaSuccess) {
+    *rc = e->cuda_fail(ce, "cudaSetDevice");
+    return false;
+  }
+  if (need_weights && !e->loaded) {
+    *rc = e->fail(IU_ERR_STATE, "weights not loaded (call iu_engine_load_weights first)");
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" {
+
+int iu_abi_version(void) { return IU_ABI_VERSION; }
+
+const char* iu_last_error(const iu_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int iu_engine_create(int device, iu_engine** out) {
+  if (!out) return IU_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(ce) +
+                     "); iunet_b200 has no CPU fallback";
+    cudaGetLastError();
+    return IU_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device index out of range";
+    return IU_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor) + "; iunet_b200 kernels are built for sm_100a only";
+    return IU_ERR_CUDA;
+  }
+  ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(ce);
+    return IU_ERR_CUDA;
+  }
+  iu_engine* e = new iu_engine();
+  e->device = device;
+  ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) {
+    g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(ce);
+    delete e;
+    return IU_ERR_CUDA;
+  }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (ce != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    g_create_error = "cuTensorMapEncodeTiled not available from the driver";
+    cudaStreamDestroy(e->stream);
+    delete e;
+    return IU_ERR_CUDA;
+  }
+  e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  *out = e;
+  return IU_OK;
+}
+
+void iu_engine_destroy(iu_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  free_plan(e);
+  free_weights(e);
+  for (auto& s : e->scratch)
+    if (s.ptr) cudaFree(s.ptr);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+void* iu_engine_stream(iu_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int iu_engine_synchronize(iu_engine* e) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  IU_CUDA(e, cudaStreamSynchronize(e->stream));
+  return IU_OK;
+}
+
+int iu_engine_load_weights(iu_engine* e, int num_classes, int n_tensors, const char* const* names,
+                           const float* const* data, const int64_t* numel) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (num_classes < 1 || num_classes > 16) return e->fail(IU_ERR_INVALID, "num_classes must be in [1, 16]");
+  if (!names || !data || !numel) return e->fail(IU_ERR_INVALID, "null tensor table");
+  cudaStreamSynchronize(e->stream);
+  free_plan(e);
+  free_weights(e);
+  HostTensors ht;
+  for (int i = 0; i < n_tensors; ++i) ht.t[names[i]] = {data[i], numel[i]};
+  e->num_classes = num_classes;
+  rc = build_network(e, ht, num_classes);
+  if (rc != IU_OK) {
+    const std::string keep = e->err;
+    free_weights(e);
+    e->err = keep;
+    return rc;
+  }
+  e->loaded = true;
+  return IU_OK;
+}
+
+int iu_engine_num_classes(const iu_engine* e) { return e ? e->num_classes : 0; }
+
+int iu_engine_set_max_batch(iu_engine* e, int max_batch) {
+  if (!e || max_batch < 0) return IU_ERR_INVALID;
+  e->max_batch = max_batch;
+  return IU_OK;
+}
+
+int64_t iu_engine_workspace_bytes(iu_engine* e, int batch, int h, int w) {
+  if (!e || !e->loaded || batch < 1 || h % 32 || w % 32) return -1;
+  return (int64_t)(e->weight_bytes + plan_bytes(e, (batch + 7) / 8 * 8, h, w));
+}
+
+int64_t iu_engine_launch_count(const iu_engine* e) { return e ? e->launches : 0; }
+
+int iu_engine_forward(iu_engine* e, const float* x, int batch, int h, int w, float* probs, unsigned flags) {
+  int rc;
+  if (!check_engine(e, true, &rc)) return rc;
+  if (!x || !probs || batch < 1) return e->fail(IU_ERR_INVALID, "forward: null pointer or empty batch");
+  if (h < 32 || w < 32 || h % 32 || w % 32)
+    return e->fail(IU_ERR_INVALID, "Wrong input shape height=" + std::to_string(h) + ", width=" + std::to_string(w) +
+                                       ". Expected image height and width divisible by 32.");
+  const int c = e->num_classes;
+  const int bs = auto_batch(e, h, w, batch);
+  rc = ensure_plan(e, bs, h, w);
+  if (rc != IU_OK) return rc;
+  const bool x_dev = is_device_ptr(x), out_dev = is_device_ptr(probs);
+  const size_t img = (size_t)h * w;
+  float* stage = nullptr;
+  if (!out_dev) {
+    rc = scratch_get(e, (size_t)batch * c * img * 4, (void**)&stage);
+    if (rc != IU_OK) return rc;
+  }
+  float* out_base = out_dev ? probs : stage;
+  for (int s = 0; s < batch; s += bs) {
+    const int b = std::min(bs, batch - s);
+    cudaError_t ce = cudaMemcpyAsync(e->plan.x_in, x + (size_t)s * img, (size_t)b * img * 4,
+                                     x_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) {
+      scratch_put(e, stage);
+      return e->cuda_fail(ce, "cudaMemcpyAsync(x)");
+    }
+    rc = run_network(e, b, kEpiSoftmaxNCHW, out_base + (size_t)s * c * img, 0, b, h);
+    if (rc != IU_OK) {
+      scratch_put(e, stage);
+      return rc;
+    }
+  }
+  if (!out_dev) {
+    cudaError_t ce = cudaMemcpyAsync(probs, stage, (size_t)batch * c * img * 4, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    scratch_put(e, stage);
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "copy probabilities to host");
+    return IU_OK;
+  }
+  return finish(e, flags);
+}
+
+int iu_engine_gather_slices(iu_engine* e, const void* volume_dev, int dtype, int n, int axis, int start, int count,
+                            float* out_dev, unsigned flags) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!volume_dev || !out_dev || n < 16 || n % 16 || axis < 0 || axis > 2 || start < 0 || count < 1 ||
+      start + count > n || (dtype != IU_DTYPE_U8 && dtype != IU_DTYPE_F32))
+    return e->fail(IU_ERR_INVALID, "gather_slices: bad arguments");
+  IU_CUDA(e, launch_gather_slices(volume_dev, dtype == IU_DTYPE_F32, n, axis, start, count, out_dev, e->stream));
+  e->launches += 1;
+  return finish(e, flags);
+}
+
+int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, int axis, int slice_begin,
+                           int slice_count, float* probs_dev, int slice_offset, int slice_total, int row_block,
+                           unsigned flags) {
+  int rc;
+  if (!check_engine(e, true, &rc)) return rc;
+  if (!volume || !probs_dev || n < 32 || n % 32 || axis < 0 || axis > 2 || slice_begin < 0 || slice_count < 1 ||
+      slice_begin + slice_count > n || (dtype != IU_DTYPE_U8 && dtype != IU_DTYPE_F32) || row_block < 1 ||
+      n % row_block || slice_offset < 0 || slice_offset + slice_count > slice_total)
+    return e->fail(IU_ERR_INVALID, "predict_axis: bad arguments");
+  const size_t esz = dtype == IU_DTYPE_F32 ? 4 : 1;
+  const void* vol_dev = volume;
+  void* staged = nullptr;
+  if (!is_device_ptr(volume)) {
+    rc = scratch_get(e, (size_t)n * n * n * esz, &staged);
+    if (rc != IU_OK) return rc;
+    cudaError_t ce = cudaMemcpyAsync(staged, volume, (size_t)n * n * n * esz, cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) {
+      scratch_put(e, staged);
+      return e->cuda_fail(ce, "cudaMemcpyAsync(volume)");
+    }
+    vol_dev = staged;
+  }
+  const int bs = auto_batch(e, n, n, slice_count);
+  rc = ensure_plan(e, bs, n, n);
+  for (int s = 0; rc == IU_OK && s < slice_count; s += bs) {
+    const int b = std::min(bs, slice_count - s);
+    cudaError_t ce =
+        launch_gather_slices(vol_dev, dtype == IU_DTYPE_F32, n, axis, slice_begin + s, b, e->plan.x_in, e->stream);
+    if (ce != cudaSuccess) {
+      rc = e->cuda_fail(ce, "launch gather_slices");
+      break;
+    }
+    e->launches += 1;
+    rc = run_network(e, b, kEpiSoftmaxNHWC, probs_dev, slice_offset + s, slice_total, row_block);
+  }
+  if (staged) {
+    cudaStreamSynchronize(e->stream);
+    scratch_put(e, staged);
+  }
+  if (rc != IU_OK) return rc;
+  return finish(e, flags);
+}
+
+int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float* p2, const int* order, int n_axes,
+                     int n, int t, int z0, int num_classes, const float* g1d_host, float gmax, float lo,
+                     uint8_t* out_u8, uint8_t* out_labels, float* out_mean, unsigned flags) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!order || n_axes < 1 || n_axes > 3 || n < 1 || t < 1 || z0 < 0 || z0 + t > n || num_classes < 1 ||
+      num_classes > 10)
+    return e->fail(IU_ERR_INVALID, "reduce: bad arguments");
+  ReduceArgs a;
+  a.p[0] = p0;
+  a.p[1] = p1;
+  a.p[2] = p2;
+  for (int i = 0; i < 3; ++i) a.order[i] = 0;
+  for (int i = 0; i < n_axes; ++i) {
+    if (order[i] < 0 || order[i] > 2 || a.p[order[i]] == nullptr)
+      return e->fail(IU_ERR_INVALID, "reduce: axis in `order` has no probability buffer");
+    a.order[i] = order[i];
+  }
+  a.n_axes = n_axes;
+  a.n = n;
+  a.t = t;
+  a.z0 = z0;
+  a.num_classes = num_classes;
+  a.gmax = gmax;
+  a.lo = lo;
+  a.out_u8 = out_u8;
+  a.out_labels = out_labels;
+  a.out_mean = out_mean;
+  float* g_dev = nullptr;
+  if (g1d_host) {
+    rc = scratch_get(e, (size_t)n * 4, (void**)&g_dev);
+    if (rc != IU_OK) return rc;
+    cudaError_t ce = cudaMemcpyAsync(g_dev, g1d_host, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) {
+      scratch_put(e, g_dev);
+      return e->cuda_fail(ce, "cudaMemcpyAsync(window)");
+    }
+  }
+  a.g1d = g_dev;
+  cudaError_t ce = launch_reduce(a, e->stream);
+  e->launches += 1;
+  if (g_dev) {
+    // the window table is tiny; wait so the scratch block can be handed out again safely
+    cudaStreamSynchronize(e->stream);
+    scratch_put(e, g_dev);
+  }
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "launch reduce");
+  return finish(e, flags);
+}
+
+int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n, const int* axes, int n_axes,
+                             const float* g1d_host, float gmax, float lo, uint8_t* out_u8, uint8_t* out_labels,
+                             float* out_mean, unsigned flags) {
+  int rc;
+  if (!check_engine(e, true, &rc)) return rc;
+  if (!volume || !axes || n_axes < 1 || n_axes > 3 || n < 32 || n % 32 ||
+      (dtype != IU_DTYPE_U8 && dtype != IU_DTYPE_F32))
+    return e->fail(IU_ERR_INVALID, "predict_volume: bad arguments");
+  bool seen[3] = {false, false, false};
+  for (int i = 0; i < n_axes; ++i) {
+    if (axes[i] < 0 || axes[i] > 2 || seen[axes[i]])
+      return e->fail(IU_ERR_INVALID, "predict_volume: axes must be distinct values from {0,1,2}");
+    seen[axes[i]] = true;
+  }
+  const int c = e->num_classes;
+  const size_t vox = (size_t)n * n * n;
+  const size_t esz = dtype == IU_DTYPE_F32 ? 4 : 1;
+  std::vector<void*> held;
+  auto release = [&]() {
+    cudaStreamSynchronize(e->stream);
+    for (void* p : held) scratch_put(e, p);
+  };
+  auto grab = [&](size_t bytes, void** out) {
+    int r = scratch_get(e, bytes, out);
+    if (r == IU_OK) held.push_back(*out);
+    return r;
+  };
+  const void* vol_dev = volume;
+  if (!is_device_ptr(volume)) {
+    void* staged = nullptr;
+    if ((rc = grab(vox * esz, &staged)) != IU_OK) { release(); return rc; }
+    cudaError_t ce = cudaMemcpyAsync(staged, volume, vox * esz, cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) { release(); return e->cuda_fail(ce, "cudaMemcpyAsync(volume)"); }
+    vol_dev = staged;
+  }
+  float* p[3] = {nullptr, nullptr, nullptr};
+  for (int i = 0; i < n_axes; ++i) {
+    if ((rc = grab(vox * c * 4, (void**)&p[axes[i]])) != IU_OK) { release(); return rc; }
+  }
+  for (int i = 0; i < n_axes; ++i) {
+    rc = iu_engine_predict_axis(e, vol_dev, dtype, n, axes[i], 0, n, p[axes[i]], 0, n, n, IU_FLAG_ASYNC);
+    if (rc != IU_OK) { release(); return rc; }
+  }
+  const bool u8_dev = out_u8 && is_device_ptr(out_u8);
+  const bool lab_dev = out_labels && is_device_ptr(out_labels);
+  const bool mean_dev = out_mean && is_device_ptr(out_mean);
+  uint8_t* d_u8 = out_u8;
+  uint8_t* d_lab = out_labels;
+  float* d_mean = out_mean;
+  if (out_u8 && !u8_dev && (rc = grab(vox * c, (void**)&d_u8)) != IU_OK) { release(); return rc; }
+  if (out_labels && !lab_dev && (rc = grab(vox, (void**)&d_lab)) != IU_OK) { release(); return rc; }
+  if (out_mean && !mean_dev && (rc = grab(vox * c * 4, (void**)&d_mean)) != IU_OK) { release(); return rc; }
+  rc = iu_engine_reduce(e, p[0], p[1], p[2], axes, n_axes, n, n, 0, c, g1d_host, gmax, lo, d_u8, d_lab, d_mean,
+                        IU_FLAG_ASYNC);
+  if (rc != IU_OK) { release(); return rc; }
+  cudaError_t ce = cudaSuccess;
+  if (out_u8 && !u8_dev) ce = cudaMemcpyAsync(out_u8, d_u8, vox * c, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess && out_labels && !lab_dev)
+    ce = cudaMemcpyAsync(out_labels, d_lab, vox, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess && out_mean && !mean_dev)
+    ce = cudaMemcpyAsync(out_mean, d_mean, vox * c * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (ce != cudaSuccess) { release(); return e->cuda_fail(ce, "copy results to host"); }
+  ce = cudaStreamSynchronize(e->stream);
+  for (void* q : held) scratch_put(e, q);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "predict_volume");
+  return IU_OK;
+}
+
+int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* src1, int cin1, int batch, int h_in,
+                        int w_in, int ksize, int stride, const float* weight, const float* bias, int cout,
+                        const void* residual, int relu, int up2x, void* out) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!src0 || !weight || !bias || !out || batch < 1 || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) ||
+      cin0 < 16 || cout % 16 || (src1 == nullptr) != (cin1 == 0) || batch % 8)
+    return e->fail(IU_ERR_INVALID, "conv_test: bad arguments (batch must be a multiple of 8)");
+  const int nseg = src1 ? 2 : 1;
+  const int cin_total = cin0 + cin1;
+  const int cin_min = src1 ? std::min(cin0, cin1) : cin0;
+  int kc, bn;
+  if (!pick_tile(cin_min, cout, &kc, &bn) || cin0 % kc || cin1 % kc || cout % bn)
+    return e->fail(IU_ERR_INVALID, "conv_test: no kernel variant for these channel counts");
+  const int ktot = ksize * ksize * cin_total;
+  std::vector<uint16_t> packed((size_t)cout * ktot, 0);
+  pack_segment(packed, ktot, 0, weight, cout, cin_total, 0, cin0, ksize);
+  if (src1) pack_segment(packed, ktot, ksize * ksize * cin0, weight, cout, cin_total, cin0, cin1, ksize);
+  void* d_w = nullptr;
+  float* d_b = nullptr;
+  if ((rc = scratch_get(e, packed.size() * 2, &d_w)) != IU_OK) return rc;
+  if ((rc = scratch_get(e, (size_t)cout * 4, (void**)&d_b)) != IU_OK) {
+    scratch_put(e, d_w);
+    return rc;
+  }
+  cudaMemcpyAsync(d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, e->stream);
+  cudaMemcpyAsync(d_b, bias, (size_t)cout * 4, cudaMemcpyHostToDevice, e->stream);
+  const int pad = ksize / 2;
+  const int out_h = (h_in + 2 * pad - ksize) / stride + 1, out_w = (w_in + 2 * pad - ksize) / stride + 1;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  set_tiling(&a, batch, out_h, out_w);
+  a.nseg = nseg;
+  a.seg[0] = {cin0, ksize, stride, pad};
+  a.seg[1] = {cin1, ksize, stride, pad};
+  rc = encode_act_map(e, &a.amap[0], src0, cin0, w_in, h_in, batch, kc, a.tw * stride, a.th * stride, a.nb, stride);
+  if (rc == IU_OK && src1)
+    rc = encode_act_map(e, &a.amap[1], src1, cin1, w_in, h_in, batch, kc, a.tw * stride, a.th * stride, a.nb, stride);
+  if (rc == IU_OK) rc = encode_weight_map(e, &a.bmap, d_w, ktot, cout, kc, bn);
+  if (rc == IU_OK) {
+    a.cout = cout;
+    a.bias = d_b;
+    a.residual = (const __nv_bfloat16*)residual;
+    a.out = out;
+    a.relu = relu;
+    a.up2x = up2x;
+    a.mode = kEpiBf16;
+    cudaError_t ce = launch_conv_tc(a, kc, bn, e->stream);
+    e->launches += 1;
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    if (ce != cudaSuccess) rc = e->cuda_fail(ce, "conv_test");
+  }
+  cudaStreamSynchronize(e->stream);
+  scratch_put(e, d_w);
+  scratch_put(e, d_b);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+"""Python handle on the native engine (`libiunet_b200.so`).
+
+Thin by design: argument marshalling, pointer extraction from numpy arrays (host) and torch CUDA
+tensors (device), and error mapping.  All arithmetic happens in the library's sm_100a kernels.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+
+STATE_DICT_PREFIX = "model."          # attribute name at `unet.py:56` of the reference
+
+
+def gaussian_window_1d(size, sigma=0.125, eps=1e-3):
+    """The 1-D factor, global maximum and lower clip bound of the reference's `gaussian_3d`
+    (`predict.py:327-347`), from which the reduce kernel rebuilds the 3-D window per voxel.
+
+    Returns (g fp32[size], gmax, lo) with window[z,y,x] = clip((g[z]*g[y])*g[x] / gmax, lo, 1)."""
+    s = sigma * size
+    coords = np.arange(size, dtype=np.float32) - (size - 1) / 2.0
+    g = np.exp(-(coords ** 2) / (2 * s ** 2)).astype(np.float32)
+    g /= g.max()
+    gm = g.max()
+    gmax = np.float32(np.float32(gm * gm) * gm)
+    gmin = np.float32(np.float32(np.float32(g.min() * g.min()) * g.min()) / gmax)
+    lo = np.float32(max(gmin, eps))
+    return np.ascontiguousarray(g), float(gmax), float(lo)
+
+
+def _ptr(a):
+    """(pointer, keep-alive object) of a numpy array or torch tensor; None -> NULL."""
+    if a is None:
+        return None, None
+    if isinstance(a, torch.Tensor):
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return ctypes.c_void_p(a.data_ptr()), a
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return ctypes.c_void_p(a.ctypes.data), a
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+def _dtype_code(a):
+    dt = a.dtype
+    if dt in (torch.uint8, np.dtype("uint8")):
+        return _lib.DTYPE_U8
+    if dt in (torch.float32, np.dtype("float32")):
+        return _lib.DTYPE_F32
+    raise TypeError(f"volume dtype must be uint8 or float32, got {dt}")
+
+
+class Engine:
+    """One native engine bound to one CUDA device.  Calls are serialised with a lock because
+    the reference calls the prediction entry points from worker threads (`app.py:737-739`)."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        self._lock = threading.RLock()
+        if isinstance(device, torch.device):
+            device = device.index or 0
+        rc = self._lib.iu_engine_create(int(device), ctypes.byref(self._h))
+        if rc != _lib.IU_OK:
+            msg = self._lib.iu_last_error(None)
+            raise _lib.EngineError(rc, msg.decode() if msg else "iu_engine_create failed")
+        self.device = torch.device("cuda", int(device))
+        self.num_classes = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.iu_engine_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _lib.check(self._lib, self._h, rc)
+
+    def _sync_torch(self, *bufs):
+        # device buffers produced on torch's current stream must be complete before our stream reads them
+        if any(isinstance(b, torch.Tensor) and b.is_cuda for b in bufs):
+            torch.cuda.current_stream(self.device).synchronize()
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict, num_classes):
+        """Upload smp.Unet('resnet34') weights given with the reference's key names (`model.` prefix optional)."""
+        names, arrays = [], []
+        for k, v in state_dict.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            if k.startswith(STATE_DICT_PREFIX):
+                k = k[len(STATE_DICT_PREFIX):]
+            a = v.detach().to("cpu", torch.float32).contiguous().numpy() if isinstance(v, torch.Tensor) \
+                else np.ascontiguousarray(v, dtype=np.float32)
+            names.append(k.encode())
+            arrays.append(a)
+        n = len(names)
+        c_names = (ctypes.c_char_p * n)(*names)
+        c_data = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        c_numel = (ctypes.c_int64 * n)(*[a.size for a in arrays])
+        with self._lock:
+            self._check(self._lib.iu_engine_load_weights(self._h, int(num_classes), n, c_names, c_data, c_numel))
+        self.num_classes = int(num_classes)
+
+    def set_max_batch(self, max_batch):
+        self._check(self._lib.iu_engine_set_max_batch(self._h, int(max_batch or 0)))
+
+    def workspace_bytes(self, batch, h, w):
+        return int(self._lib.iu_engine_workspace_bytes(self._h, batch, h, w))
+
+    def launch_count(self):
+        return int(self._lib.iu_engine_launch_count(self._h))
+
+    def stream_handle(self):
+        return int(self._lib.iu_engine_stream(self._h) or 0)
+
+    def synchronize(self):
+        self._check(self._lib.iu_engine_synchronize(self._h))
+
+    # ------------------------------------------------------------------ network
+    def forward(self, x, out=None):
+        """`UNet.forward`: fp32 [B,1,H,W] -> probabilities fp32 [B,C,H,W]; numpy in -> numpy out,
+        CUDA tensor in -> CUDA tensor out."""
+        b, ch, h, w = x.shape
+        if ch != 1:
+            raise ValueError("the engine supports num_channels=1 only")
+        if isinstance(x, torch.Tensor):
+            x = x.to(torch.float32).contiguous()
+            if out is None:
+                out = torch.empty((b, self.num_classes, h, w), dtype=torch.float32, device=x.device)
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            if out is None:
+                out = np.empty((b, self.num_classes, h, w), dtype=np.float32)
+        xp, _ = _ptr(x)
+        op, _ = _ptr(out)
+        with self._lock:
+            self._sync_torch(x, out)
+            self._check(self._lib.iu_engine_forward(self._h, xp, b, h, w, op, 0))
+        return out
+
+    # ------------------------------------------------------------------ volume path
+    def gather_slices(self, volume, axis, start, count):
+        n = volume.shape[0]
+        out = torch.empty((count, n, n), dtype=torch.float32, device=self.device)
+        vp, _ = _ptr(volume)
+        with self._lock:
+            self._sync_torch(volume, out)
+            self._check(self._lib.iu_engine_gather_slices(self._h, vp, _dtype_code(volume), n, int(axis), int(start),
+                                                          int(count), ctypes.c_void_p(out.data_ptr()), 0))
+        return out
+
+    def predict_axis(self, volume, axis, slice_begin=0, slice_count=None, out=None, slice_offset=0,
+                     slice_total=None, row_block=None, asynchronous=False):
+        """Probabilities of the slices [slice_begin, slice_begin+slice_count) along `axis` (device fp32)."""
+        n = volume.shape[0]
+        slice_count = n - slice_begin if slice_count is None else slice_count
+        slice_total = slice_count if slice_total is None else slice_total
+        row_block = n if row_block is None else row_block
+        if out is None:
+            out = torch.empty((slice_total, n, n, self.num_classes), dtype=torch.float32, device=self.device)
+        vp, _ = _ptr(volume)
+        with self._lock:
+            self._sync_torch(volume, out)
+            self._check(self._lib.iu_engine_predict_axis(
+                self._h, vp, _dtype_code(volume), n, int(axis), int(slice_begin), int(slice_count),
+                ctypes.c_void_p(out.data_ptr()), int(slice_offset), int(slice_total), int(row_block),
+                _lib.FLAG_ASYNC if asynchronous else 0))
+        return out
+
+    def reduce(self, probs, order, n, t=None, z0=0, window=None, out_u8=None, out_labels=None, out_mean=None,
+               asynchronous=False):
+        """K4.  `probs`: dict axis -> device fp32 tensor; `order`: accumulation order (`predict.py:87`);
+        `window`: None or (g1d, gmax, lo) from `gaussian_window_1d`."""
+        t = n if t is None else t
+        ptrs = [ctypes.c_void_p(probs[a].data_ptr()) if a in probs and probs[a] is not None else None
+                for a in (0, 1, 2)]
+        c_order = (ctypes.c_int * len(order))(*[int(a) for a in order])
+        g, gmax, lo = (None, 1.0, 0.0) if window is None else window
+        gp, _g = _ptr(g)
+        with self._lock:
+            self._sync_torch(*[p for p in probs.values() if p is not None], out_u8, out_labels, out_mean)
+            self._check(self._lib.iu_engine_reduce(
+                self._h, ptrs[0], ptrs[1], ptrs[2], c_order, len(order), int(n), int(t), int(z0),
+                int(self.num_classes), gp, float(gmax), float(lo), _ptr(out_u8)[0], _ptr(out_labels)[0],
+                _ptr(out_mean)[0], _lib.FLAG_ASYNC if asynchronous else 0))
+
+    def predict_volume(self, volume, axes=(0, 1, 2), window=None, out_u8=None, out_labels=None, out_mean=None):
+        """Whole single-GPU path; every buffer may live on the host (numpy) or on the device (torch)."""
+        n = volume.shape[0]
+        if tuple(volume.shape) != (n, n, n):
+            raise ValueError("the engine predicts cubic blocks only (predict.py:81)")
+        c_axes = (ctypes.c_int * len(axes))(*[int(a) for a in axes])
+        g, gmax, lo = (None, 1.0, 0.0) if window is None else window
+        vp, _ = _ptr(volume)
+        gp, _g = _ptr(g)
+        with self._lock:
+            self._sync_torch(volume, out_u8, out_labels, out_mean)
+            self._check(self._lib.iu_engine_predict_volume(
+                self._h, vp, _dtype_code(volume), n, c_axes, len(axes), gp, float(gmax), float(lo),
+                _ptr(out_u8)[0], _ptr(out_labels)[0], _ptr(out_mean)[0], 0))
+
+    # ------------------------------------------------------------------ test hook
+    def conv_test(self, src0, src1, weight, bias, ksize, stride, residual=None, relu=True, up2x=False):
+        """One tensor-core conv on bf16 NHWC CUDA tensors, exactly as the engine runs its layers."""
+        b, h, w, c0 = src0.shape
+        c1 = 0 if src1 is None else src1.shape[3]
+        cout = weight.shape[0]
+        pad = ksize // 2
+        oh, ow = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
+        f = 2 if up2x else 1
+        out = torch.zeros((b, oh * f, ow * f, cout), dtype=torch.bfloat16, device=src0.device)
+        wt = np.ascontiguousarray(weight, dtype=np.float32)
+        bs = np.ascontiguousarray(bias, dtype=np.float32)
+        with self._lock:
+            self._sync_torch(src0)
+            self._check(self._lib.iu_engine_conv_test(
+                self._h, _ptr(src0)[0], c0, _ptr(src1)[0], c1, b, h, w, ksize, stride, _ptr(wt)[0], _ptr(bs)[0],
+                cout, _ptr(residual)[0], int(relu), int(up2x), _ptr(out)[0]))
+        return out

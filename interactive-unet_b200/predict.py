@@ -1,0 +1,180 @@
+"""Drop-in for the prediction entry points of `/root/reference/interactive_unet/predict.py`.
+
+`predict_slice` (`:16-47`), `find_max_batch_size` (`:49-77`), `predict_block` (`:79-112`) and
+`predict_volumes` (`:114-266`) keep the reference's signatures, return types and on-disk side effects;
+the arithmetic between "uint8 volume" and "uint8 probabilities / labels" runs in the native sm_100a
+engine (`libiunet_b200.so`): slice gather + normalise, the U-Net, per-slice softmax, cross-axis
+accumulate / average, Gaussian-window blend, uint8 quantise and argmax.  No stage falls back to
+PyTorch or the CPU; if the library or the GPU is missing these functions raise.
+
+`predict_volume_array` is the in-memory core that `predict_volumes` calls per Zarr volume.
+"""
+import glob
+import os
+import threading
+import time
+
+import numpy as np
+import torch
+
+from . import unet
+from .engine import gaussian_window_1d
+
+# utils.COLORS of the reference (utils.py:304-306): class i is drawn with COLORS[i + 1]
+COLORS = np.array([[0, 0, 0], [230, 25, 75], [60, 180, 75], [255, 225, 25], [0, 130, 200], [245, 130, 48],
+                   [145, 30, 180], [70, 240, 240], [240, 50, 230], [210, 245, 60], [170, 255, 195]], dtype=np.uint8)
+
+_model_cache = {}
+_model_cache_lock = threading.Lock()
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("interactive_unet_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+    return torch.device('cuda')
+
+
+def _load_model(num_channels, num_classes, device):
+    """`predict.py:21-27,127-135`: the checkpoint if present, else a fresh model.  The reference reloads
+    the file on every call; here the loaded model (and its engine-resident weights) is cached and
+    refreshed when the trainer rewrites the file (`trainer.py:42-49`)."""
+    model_path = os.path.join('model', 'model.ckpt')
+    if os.path.isfile(model_path):
+        st = os.stat(model_path)
+        key = (os.path.abspath(model_path), st.st_mtime_ns, st.st_size, str(device))
+        with _model_cache_lock:
+            model = _model_cache.get(key)
+            if model is None:
+                model = unet.UNet.load_from_checkpoint(checkpoint_path=model_path).to(device)
+                model.eval()
+                _model_cache.clear()
+                _model_cache[key] = model
+        return model
+    model = unet.UNet(num_channels=num_channels, num_classes=num_classes).to(device)
+    model.eval()
+    return model
+
+
+def categorical_to_colored(mask):
+    """`utils.py:351-357`."""
+    colored = np.zeros((mask.shape[0], mask.shape[1], 3), dtype='uint8')
+    for i in range(mask.shape[-1]):
+        colored[mask[:, :, i] == 255, :] = COLORS[i + 1]
+    return colored
+
+
+def predict_slice(image_slice, num_channels=1, num_classes=2, return_probabilities=False):
+    """`predict.py:16-47`: uint8 `[H,W]` -> colour overlay uint8 `[H,W,3]` (or probabilities `[1,H,W,C]`)."""
+    device = _require_cuda()
+    model = _load_model(num_channels, num_classes, device)
+    x = (image_slice[None, None, :, :] / 255).astype('float32')
+    with torch.inference_mode():
+        y_prob = model(torch.from_numpy(np.ascontiguousarray(x)).to(device)).cpu().numpy()
+    y_prob = np.moveaxis(y_prob, 1, -1)
+    y_pred = np.argmax(y_prob[0, :, :, :num_classes], axis=-1)
+    y_pred = np.stack([y_pred == i for i in range(num_classes)], -1)
+    y_pred = (y_pred * 255).astype('uint8')
+    y_pred = categorical_to_colored(y_pred)
+    return y_prob if return_probabilities else y_pred
+
+
+def find_max_batch_size(model, input_size=256, start=4, max_limit=512):
+    """`predict.py:49-77`: the largest power-of-two multiple of `start` (<= max_limit) whose activations
+    fit.  The engine allocates its workspace up front, so this is a capacity query plus one real
+    allocation probe per size instead of timed trial forwards."""
+    batch_size, best = start, start
+    device = model.device
+    while batch_size <= max_limit:
+        try:
+            with torch.inference_mode():
+                test_batch = torch.zeros((batch_size, 1, input_size, input_size), dtype=torch.float32, device=device)
+                model.engine().set_max_batch(batch_size)
+                _ = model(test_batch)
+            best = batch_size
+            batch_size *= 2
+            torch.cuda.empty_cache()
+        except RuntimeError as e:
+            if "out of memory" in str(e):
+                torch.cuda.empty_cache()
+                break
+            raise
+    model.engine().set_max_batch(0)
+    torch.cuda.empty_cache()
+    return best
+
+
+def predict_block(model, block, num_classes=2, batch_size=8, axes=[0, 1, 2]):
+    """`predict.py:79-112`: fp32 block `[S,S,S]` (values = uint8/255) -> mean probabilities fp32 `[S,S,S,C]`."""
+    block = block.detach() if isinstance(block, torch.Tensor) else torch.as_tensor(np.asarray(block))
+    size = block.shape[0]
+    if tuple(block.shape) != (size, size, size):
+        raise ValueError("predict_block expects a cubic block (predict.py:81)")
+    eng = model.engine()
+    if eng.num_classes != num_classes:
+        raise ValueError(f"model has {eng.num_classes} classes, num_classes={num_classes} requested")
+    eng.set_max_batch(batch_size)
+    out = np.empty((size, size, size, num_classes), dtype=np.float32)
+    vol = block.to(torch.float32).contiguous()
+    vol = vol if vol.is_cuda else vol.numpy()
+    try:
+        eng.predict_volume(vol, axes=list(axes), window=None, out_mean=out)
+    finally:
+        eng.set_max_batch(0)
+    return out
+
+
+def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=0.25, batch_size=None,
+                         axes=[0, 1, 2], return_labels=False):
+    """In-memory core of `predict_volumes` (`predict.py:153,201,235-256`): uint8 volume `[N,N,N]`
+    (numpy, or a CUDA tensor to keep everything device-resident) -> uint8 probabilities `[N,N,N,C]`
+    (and uint8 argmax labels `[N,N,N]` with `return_labels=True`), same container kind as the input."""
+    n = volume.shape[0]
+    input_size = n if input_size is None else input_size
+    if tuple(volume.shape) != (n, n, n) or input_size != n:
+        raise NotImplementedError(
+            "volumes larger than input_size (tiled / blended mode, predict.py:201,235-245) are not on the "
+            "device path yet: call with input_size == volume edge")
+    eng = model.engine()
+    if eng.num_classes != num_classes:
+        raise ValueError(f"model has {eng.num_classes} classes, num_classes={num_classes} requested")
+    eng.set_max_batch(batch_size or 0)
+    window = gaussian_window_1d(input_size, sigma=0.125)               # predict.py:153
+    if isinstance(volume, torch.Tensor):
+        out = torch.empty((n, n, n, num_classes), dtype=torch.uint8, device=volume.device)
+        lab = torch.empty((n, n, n), dtype=torch.uint8, device=volume.device) if return_labels else None
+    else:
+        volume = np.ascontiguousarray(volume)
+        out = np.empty((n, n, n, num_classes), dtype=np.uint8)
+        lab = np.empty((n, n, n), dtype=np.uint8) if return_labels else None
+    try:
+        eng.predict_volume(volume, axes=list(axes), window=window, out_u8=out, out_labels=lab)
+    finally:
+        eng.set_max_batch(0)
+    return (out, lab) if return_labels else out
+
+
+def predict_volumes(input_size=256, num_channels=1, num_classes=2, overlap=0.25, chunk_size=128, shard_size=256,
+                    batch_size=None, axes=[0, 1, 2]):
+    """`predict.py:114-266`: predict every `data/image_volumes/*.zarr` into `data/predicted_volumes/`."""
+    try:
+        import zarr
+    except ImportError as e:
+        raise RuntimeError("predict_volumes reads and writes Zarr stores; the `zarr` package is not installed. "
+                           "Use predict_volume_array for in-memory volumes.") from e
+    device = _require_cuda()
+    model = _load_model(num_channels, num_classes, device)
+    volume_files = np.sort(glob.glob('data/image_volumes/*.zarr'))
+    for f in volume_files:
+        start_time = time.time()
+        volume = np.asarray(zarr.open(f, mode='r')['0'][:])
+        save_path = f.replace('image_volumes', 'predicted_volumes')
+        root = zarr.open(save_path, mode='w')
+        final = root.create_array(name='0', shape=list(volume.shape) + [num_classes],
+                                  chunks=(chunk_size, chunk_size, chunk_size, num_classes),
+                                  shards=(shard_size, shard_size, shard_size, num_classes), dtype='uint8',
+                                  overwrite=True)
+        print(f'\nSegmenting {os.path.basename(f)}...')
+        final[:] = predict_volume_array(model, volume, input_size=input_size, num_classes=num_classes,
+                                        overlap=overlap, batch_size=batch_size, axes=axes)
+        print(f'Completed volume {os.path.basename(f)} {tuple(volume.shape)} in {time.time() - start_time}.')
+    print('\nAll volumes segmented.\n')

@@ -1,0 +1,137 @@
+"""Drop-in for the reference's `UNet` module (`/root/reference/interactive_unet/unet.py:10-69`).
+
+Same constructor arguments, same `forward` contract (fp32 `[B,1,H,W]` in `[0,1]` -> softmax
+probabilities fp32 `[B,C,H,W]`), same `state_dict()` keys (`model.<smp key>`), `.device`, `.eval()`,
+`.to()` and `load_from_checkpoint(checkpoint_path=...)`.  In eval mode `forward` runs entirely in the
+native sm_100a engine; there is no PyTorch or CPU fallback for inference -- a missing library or a
+non-CUDA input raises.  Training mode keeps stock autograd so the reference's trainer still works.
+
+Accelerated configuration: `architecture='U-Net'`, `encoder_name='resnet34'`, `num_channels=1`
+(SURVEY.md section 8a).  Other configurations raise `NotImplementedError`.
+"""
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+from .engine import Engine
+from .network import SmpUnetResnet34
+
+try:                                    # the reference subclasses LightningModule (unet.py:9)
+    import lightning as _L
+    _Base = _L.LightningModule
+except Exception:                       # lightning is not installed in this image
+    _L = None
+
+    class _Base(nn.Module):
+        def save_hyperparameters(self, *args, **kwargs):
+            return None
+
+        def log(self, *args, **kwargs):
+            return None
+
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+
+def _install_pickle_shims():
+    """Reference checkpoints pickle `loss_function=interactive_unet.metrics.<fn>` (unet.py:17,23).
+    Make that module path resolvable so `torch.load` can unpickle hyper-parameters."""
+    if "interactive_unet.metrics" in sys.modules:
+        return
+    try:
+        import interactive_unet.metrics  # noqa: F401
+        return
+    except Exception:
+        pass
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+
+            def _placeholder(*a, **k):
+                raise RuntimeError(f"interactive_unet.metrics.{name} is a checkpoint placeholder")
+            _placeholder.__name__ = name
+            setattr(self, name, _placeholder)
+            return _placeholder
+
+    pkg = sys.modules.setdefault("interactive_unet", types.ModuleType("interactive_unet"))
+    mod = _Any("interactive_unet.metrics")
+    sys.modules["interactive_unet.metrics"] = mod
+    pkg.metrics = mod
+
+
+def _default_loss(*args, **kwargs):
+    raise RuntimeError("no loss function configured; pass loss_function= (the reference uses metrics.mcc_ce_loss)")
+
+
+class UNet(_Base):
+    """The UNet model (B200 engine behind the reference's interface)."""
+
+    def __init__(self, lr=0.0001, num_channels=1, num_classes=2, loss_function=_default_loss,
+                 architecture='U-Net', encoder_name='resnet34', pretrained=False):
+        super().__init__()
+        self.save_hyperparameters()
+        self.lr = lr
+        self.loss_function = loss_function
+        if architecture != 'U-Net' or encoder_name != 'resnet34':
+            raise NotImplementedError(
+                f"interactive_unet_b200 accelerates architecture='U-Net' with encoder_name='resnet34' only "
+                f"(got {architecture!r}, {encoder_name!r}); use the stock interactive_unet.unet.UNet for others")
+        if pretrained:
+            raise NotImplementedError("ImageNet weights cannot be downloaded here; load a checkpoint instead")
+        self.num_channels = num_channels
+        self.num_classes = num_classes
+        self.model = SmpUnetResnet34(num_channels, num_classes)      # attribute name = checkpoint key prefix
+        self.softmax = nn.Softmax(dim=1)
+        self._engine = None
+        self._engine_key = None
+
+    # ---- engine management ----------------------------------------------------------------
+    def _weights_key(self):
+        return tuple((id(t), t._version) for t in self.model.state_dict(keep_vars=True).values())
+
+    def engine(self):
+        """The native engine holding the current weights (created / refreshed lazily)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("interactive_unet_b200 runs on CUDA (sm_100a) only: move the model with "
+                               ".to('cuda'); there is no CPU fallback")
+        if self._engine is None or self._engine.device != torch.device("cuda", dev.index or 0):
+            self._engine = Engine(dev.index or 0)
+            self._engine_key = None
+        key = self._weights_key()
+        if key != self._engine_key:
+            self._engine.load_state_dict(self.model.state_dict(), self.num_classes)
+            self._engine_key = key
+        return self._engine
+
+    # ---- reference interface -----------------------------------------------------------------
+    def forward(self, x):
+        if self.training:
+            return self.softmax(self.model.forward_train(x))        # unet.py:67 (autograd path)
+        if not x.is_cuda:
+            raise RuntimeError("interactive_unet_b200 inference needs a CUDA input tensor; there is no CPU fallback")
+        return self.engine().forward(x)
+
+    def configure_optimizers(self):
+        return torch.optim.AdamW(self.parameters(), lr=self.lr)      # unet.py:71-73
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, **kwargs):
+        """Lightning's classmethod re-implemented on `torch.load` (lightning is not installed here)."""
+        _install_pickle_shims()
+        ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(kwargs)
+        hp["pretrained"] = False
+        allowed = ("lr", "num_channels", "num_classes", "loss_function", "architecture", "encoder_name", "pretrained")
+        model = cls(**{k: v for k, v in hp.items() if k in allowed})
+        model.load_state_dict(ckpt["state_dict"], strict=True)
+        return model
