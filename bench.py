@@ -1,0 +1,351 @@
+"""Benchmark of the full-volume prediction path (BASELINE.json: voxels/s, 3-axis prediction of a
+synthetic uint8 volume; N=1 workload = configs[1], 512^3, 2 classes).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one complete 3-axis prediction of the volume (gather -> U-Net -> softmax -> cross-axis
+reduce -> uint8 probabilities + labels).  Prints ONE JSON line on rank 0.
+
+  value        device-resident throughput (volume already in HBM, outputs left in HBM), CUDA events
+               on the engine's stream, max over ranks
+  e2e          the same prediction through the public drop-in API (`predict.predict_volume_array`)
+               with pinned HOST buffers: host->device copy of the volume and device->host copy of the
+               uint8 probabilities + labels inside the timed region
+  roofline     the tcgen05 conv kernels (tensor bound): algorithmic conv FLOPs / their summed device
+               time (CUDA events around every launch, separate profiled pass); HBM-bound kernels
+               (gather K1, reduce K4) are reported in `roofline_hbm`
+  cpu_baseline the oracle (fp32 restatement of the reference network + port of predict.py) on this
+               box's host cores, on a bounded sample of the same workload
+`--impl reference` times that CPU path as its own arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_VOXEL_AXIS = {2: 235.62e3, 4: 236.19e3}          # BASELINE.md section 3 (dense conv FLOPs per pixel per axis)
+WEAK_EDGES = {1: 512, 2: 640, 4: 800, 8: 1024}             # ~512^3 voxels per GPU (edge % 32 == 0, edge % G == 0)
+AXES = (0, 1, 2)
+
+
+def flops_per_voxel(classes, n_axes=3):
+    per_axis = FLOP_PER_VOXEL_AXIS.get(classes, 235.62e3 + (classes - 2) * 0.285e3)
+    return per_axis * n_axes
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tc_tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained)")
+    return dict(hbm_gbs=6650.0, tc_tflops=1590.0, source="fallback of B200_PROFILING.md (6.65 TB/s, 1.59 PFLOP/s)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+_CPU_SETUP = {}
+
+
+def cpu_reference_sample(edge, classes, slices_per_axis, threads, repeats=1):
+    """Oracle on host cores: `slices_per_axis` slices of edge^2 along each of the 3 axes of the bench
+    volume through the fp32 network + the port's scatter / average / quantise.  Returns voxels/s where one
+    voxel = one 3-axis prediction (3 slice-pixels), and the seconds of the best repeat."""
+    from oracle import predict_port as pp
+    from oracle import synth
+    torch.set_num_threads(threads)
+    key = (edge, classes)
+    if key not in _CPU_SETUP:                       # weights / volume are set-up, not part of the timed sample
+        _CPU_SETUP[key] = (synth.make_model(classes), synth.noise_volume(edge, 1))
+    model, vol = _CPU_SETUP[key]
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        acc = np.zeros((slices_per_axis, edge, edge, classes), np.float32)
+        with torch.inference_mode():
+            for axis in AXES:
+                x = pp.slice_batch(pp.normalise_u8(np.moveaxis(vol, axis, 0)[:slices_per_axis]), 0, 0, slices_per_axis)
+                p = model(torch.from_numpy(x)).numpy()
+                acc += np.moveaxis(p, 1, -1)
+        acc /= np.float32(len(AXES))
+        w = pp.gaussian_3d(edge)[:slices_per_axis] if edge <= 256 else np.ones((slices_per_axis, edge, edge), np.float32)
+        pp.quantise(acc * w[..., None], w)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    voxels = slices_per_axis * edge * edge
+    return voxels / best, best
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    edge = WEAK_EDGES.get(args.gpus, 512) if args.edge is None else args.edge
+    threads = os.cpu_count() or 1
+    spa = args.cpu_slices
+    for _ in range(args.warmup):
+        cpu_reference_sample(edge, args.classes, 1, threads)
+    t0 = time.perf_counter()
+    vals = [cpu_reference_sample(edge, args.classes, spa, threads)[0] for _ in range(args.steps)]
+    total = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    sample = f"{spa} slices of {edge}x{edge} per axis x 3 axes per step (of {edge} per axis), fp32, torch CPU"
+    line = {
+        "impl": "reference", "metric": "voxels/sec, full 3-axis volume prediction", "value": value, "unit": "voxels/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"3-axis prediction of a synthetic {edge}^3 uint8 volume, {args.classes} classes",
+                   "edge": edge, "classes": args.classes, "axes": list(AXES),
+                   "network": "smp.Unet(resnet34) restated (oracle/), reference predict.py arithmetic (port)"},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import interactive_unet_b200 as iu
+    from interactive_unet_b200 import distributed as iud
+    from oracle import synth                      # seeded synthetic weights / volume generators only
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    classes = args.classes
+    edge = WEAK_EDGES.get(world, 512) if args.edge is None else args.edge
+    if edge % world or edge % 32:
+        raise SystemExit(f"edge {edge} must be divisible by 32 and by the number of GPUs {world}")
+    t_slab = edge // world
+    ref = synth.make_model(classes)                                   # random-init weights of the named architecture
+    model = iu.UNet(num_classes=classes)
+    model.precision = args.precision
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev).eval()
+    eng = model.engine()
+    window = iu.gaussian_window_1d(edge)
+
+    vol_host = torch.from_numpy(synth.noise_volume(edge, 1)).pin_memory()
+    vol_dev = vol_host.to(dev)
+    stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident step
+    if world == 1:
+        out_u8 = torch.empty((edge, edge, edge, classes), dtype=torch.uint8, device=dev)
+        out_lab = torch.empty((edge, edge, edge), dtype=torch.uint8, device=dev)
+
+        def step():
+            eng.predict_volume(vol_dev, axes=AXES, window=window, out_u8=out_u8, out_labels=out_lab)
+    else:
+        def step():
+            return iud.predict_volume_sharded(eng, vol_dev, axes=AXES, window=window)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = eng.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+        dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+
+    # ---- end-to-end step: pinned host volume in, pinned host uint8 probabilities + labels out
+    if world == 1:
+        h_u8 = torch.empty((edge, edge, edge, classes), dtype=torch.uint8).pin_memory()
+        h_lab = torch.empty((edge, edge, edge), dtype=torch.uint8).pin_memory()
+
+        def e2e_step():
+            iu.predict.predict_volume_array(model, vol_host.numpy(), num_classes=classes, axes=list(AXES),
+                                            return_labels=True, out=h_u8.numpy(), out_labels=h_lab.numpy())
+        h2d, d2h = edge ** 3, edge ** 3 * (classes + 1)
+    else:
+        h_u8 = torch.empty((t_slab, edge, edge, classes), dtype=torch.uint8).pin_memory()
+        h_lab = torch.empty((t_slab, edge, edge), dtype=torch.uint8).pin_memory()
+
+        def e2e_step():
+            v = vol_host.to(dev, non_blocking=True)
+            res = iud.predict_volume_sharded(eng, v, axes=AXES, window=window)
+            h_u8.copy_(res["u8"], non_blocking=True)
+            h_lab.copy_(res["labels"], non_blocking=True)
+            torch.cuda.synchronize(dev)
+        h2d, d2h = edge ** 3 * world, edge ** 3 * (classes + 1)       # volume replicated on every rank
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- per-kernel-class device time (separate, profiled pass; not part of `value`)
+    eng.profile(True)
+    eng.profile_read(reset=True)
+    prof_steps = max(1, min(args.steps, 3))
+    for _ in range(prof_steps):
+        step()
+    prof = eng.profile_read(reset=True)
+    eng.profile(False)
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    if rank != 0:
+        return
+    voxels = float(edge) ** 3
+    peaks = measured_peaks()
+    value = voxels * args.steps / (dev_ms * 1e-3)
+    conv_ms, conv_n = prof["conv"]
+    conv_flops = flops_per_voxel(classes) * voxels / world * prof_steps        # this rank's share
+    conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    gather_ms, gather_n = prof["gather"]
+    reduce_ms, reduce_n = prof["reduce"]
+    share = voxels / world * prof_steps
+    gather_gbs = share * 3 * (1 + 4) / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
+    reduce_bytes_per_voxel = 3 * classes * 4 + classes + 1
+    reduce_gbs = share * reduce_bytes_per_voxel / (reduce_ms * 1e-3) / 1e9 if reduce_ms > 0 else 0.0
+    total_prof_ms = sum(v[0] for v in prof.values())
+    line = {
+        "metric": "voxels/sec, full 3-axis volume prediction", "value": value, "unit": "voxels/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "impl": "ours",
+        "config": {"workload": f"3-axis prediction of a synthetic {edge}^3 uint8 volume, {classes} classes, "
+                               f"{'1 B200' if world == 1 else f'z-slab sharded across {world} B200'}",
+                   "edge": edge, "classes": classes, "axes": list(AXES), "network": "smp.Unet(resnet34), random init",
+                   "storage": f"{args.precision} activations/weights, fp32 accumulate (TMEM), fp32 tail",
+                   "l2": "inputs_exceed_l2 (per-step working set of several GB >> 126 MB L2; no explicit flush)",
+                   "slices_per_gpu_per_axis": t_slab},
+        "e2e": {"value": voxels * args.steps / (e2e_ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                "api": "interactive_unet_b200.predict.predict_volume_array (pinned host buffers)" if world == 1
+                       else "interactive_unet_b200.distributed.predict_volume_sharded + pinned host copies"},
+        "gpu_launches": int(launches),
+        "algorithmic_tflops": flops_per_voxel(classes) * value / 1e12,
+        "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM, all conv layers + head)", "bound": "tensor",
+                     "achieved": conv_tflops, "peak": peaks["tc_tflops"], "unit": "TFLOP/s",
+                     "frac": conv_tflops / peaks["tc_tflops"], "traffic": None, "peak_source": peaks["source"],
+                     "flops_per_voxel": flops_per_voxel(classes), "launches": int(conv_n),
+                     "kernel_ms_per_step": conv_ms / prof_steps,
+                     "share_of_step": conv_ms / total_prof_ms if total_prof_ms else None},
+        "roofline_hbm": {
+            "gather": {"bound": "hbm", "achieved": gather_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": gather_gbs / peaks["hbm_gbs"], "bytes_per_voxel_per_axis": 5,
+                       "kernel_ms_per_step": gather_ms / prof_steps, "launches": int(gather_n)},
+            "reduce": {"bound": "hbm", "achieved": reduce_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": reduce_gbs / peaks["hbm_gbs"], "bytes_per_voxel": reduce_bytes_per_voxel,
+                       "kernel_ms_per_step": reduce_ms / prof_steps, "launches": int(reduce_n)}},
+        "kernel_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()},
+        "clocks": clocks.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, secs = cpu_reference_sample(edge, classes, args.cpu_slices, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.cpu_slices} slices of {edge}x{edge} per axis x 3 axes "
+                                          f"({secs:.1f} s), fp32 oracle network + port of predict.py, torch CPU"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--edge", type=int, default=None, help="volume edge (default: 512 at 1 GPU, weak-scaled above)")
+    ap.add_argument("--classes", type=int, default=2)
+    ap.add_argument("--precision", default=os.environ.get("IU_PRECISION", "fp16"), choices=["fp16", "bf16"])
+    ap.add_argument("--cpu-slices", type=int, default=4, help="slices per axis in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,11 @@ extern "C" {
 #define IU_DTYPE_U8 0
 #define IU_DTYPE_F32 1
 
+/* 16-bit storage format of weights and inter-layer activations (accumulation is always fp32 in TMEM).
+ * Both run the same tcgen05 kind::f16 instruction at the same rate and move the same bytes. */
+#define IU_PRECISION_FP16 0 /* default: 11-bit significand, ~8x smaller rounding error than bf16 */
+#define IU_PRECISION_BF16 1
+
 typedef struct iu_engine iu_engine;
 
 int iu_abi_version(void);
@@ -67,6 +72,10 @@ int iu_engine_synchronize(iu_engine* e);
 int iu_engine_load_weights(iu_engine* e, int num_classes, int n_tensors, const char* const* names,
                            const float* const* data, const int64_t* numel);
 int iu_engine_num_classes(const iu_engine* e);
+
+/* Select the storage format; call BEFORE iu_engine_load_weights (changing it drops loaded weights). */
+int iu_engine_set_precision(iu_engine* e, int precision);
+int iu_engine_precision(const iu_engine* e);
 
 /* Upper bound on the slices per internal batch (0 = automatic).  Results do not depend on it. */
 int iu_engine_set_max_batch(iu_engine* e, int max_batch);
@@ -121,6 +130,18 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
 
 /* Number of kernels the engine has launched since creation (bench.py's `gpu_launches`). */
 int64_t iu_engine_launch_count(const iu_engine* e);
+
+/* Per-kernel-class device timing: while enabled every launch is bracketed by CUDA events recorded on
+ * the engine's stream.  iu_engine_profile_read drains the stream and returns, per class, the summed
+ * kernel milliseconds and launch counts accumulated so far (arrays of IU_PROF_CLASSES entries). */
+#define IU_PROF_GATHER 0 /* K1 slice gather + normalise                */
+#define IU_PROF_STEM 1   /* 7x7/s2 stem conv + BN + ReLU               */
+#define IU_PROF_POOL 2   /* 3x3/s2 max-pool                            */
+#define IU_PROF_CONV 3   /* tcgen05 implicit-GEMM convs (incl. head)   */
+#define IU_PROF_REDUCE 4 /* K4 accumulate / blend / quantise / argmax  */
+#define IU_PROF_CLASSES 5
+int iu_engine_profile(iu_engine* e, int enable);
+int iu_engine_profile_read(iu_engine* e, double* ms, int64_t* count, int reset);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@ The directory is named `interactive-unet_b200/` (repo layout contract); it is im
 
     from interactive_unet_b200 import predict, unet      # same names as the reference's modules
 """
-from . import _lib, engine, network, predict, unet  # noqa: F401
+from . import _lib, distributed, engine, network, predict, unet  # noqa: F401
 from .engine import Engine, gaussian_window_1d  # noqa: F401
 from .unet import UNet  # noqa: F401
 

@@ -14,6 +14,7 @@ ABI_VERSION = 1
 IU_OK, IU_ERR_INVALID, IU_ERR_CUDA, IU_ERR_OOM, IU_ERR_STATE = 0, 1, 2, 3, 4
 FLAG_ASYNC = 1
 DTYPE_U8, DTYPE_F32 = 0, 1
+PRECISIONS = {"fp16": 0, "bf16": 1}
 
 _c = ctypes
 _engine_p = _c.c_void_p
@@ -29,6 +30,8 @@ SIGNATURES = {
     "iu_engine_load_weights": (_c.c_int, [_engine_p, _c.c_int, _c.c_int, _c.POINTER(_c.c_char_p),
                                           _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int64)]),
     "iu_engine_num_classes": (_c.c_int, [_engine_p]),
+    "iu_engine_set_precision": (_c.c_int, [_engine_p, _c.c_int]),
+    "iu_engine_precision": (_c.c_int, [_engine_p]),
     "iu_engine_set_max_batch": (_c.c_int, [_engine_p, _c.c_int]),
     "iu_engine_workspace_bytes": (_c.c_int64, [_engine_p, _c.c_int, _c.c_int, _c.c_int]),
     "iu_engine_forward": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint]),
@@ -46,7 +49,10 @@ SIGNATURES = {
                                        _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,
                                        _c.c_int, _c.c_int, _c.c_void_p]),
     "iu_engine_launch_count": (_c.c_int64, [_engine_p]),
+    "iu_engine_profile": (_c.c_int, [_engine_p, _c.c_int]),
+    "iu_engine_profile_read": (_c.c_int, [_engine_p, _c.POINTER(_c.c_double), _c.POINTER(_c.c_int64), _c.c_int]),
 }
+PROF_CLASSES = ("gather", "stem", "pool", "conv", "reduce")
 
 _lib = None
 _lock = threading.Lock()

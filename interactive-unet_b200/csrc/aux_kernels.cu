@@ -91,7 +91,7 @@ constexpr int kStemPitch = kStemPatch + 1;
 
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, int h, int w,
                                                    const float* __restrict__ wt, const float* __restrict__ bias,
-                                                   __nv_bfloat16* __restrict__ out) {
+                                                   __nv_bfloat16* __restrict__ out, int fp16) {
   __shared__ float patch[kStemPatch][kStemPitch];
   __shared__ float4 wsm[49 * 16];
   const int n = blockIdx.z;
@@ -138,8 +138,13 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
         const int c = 8 * j + 2 * k;
         const float a0 = fmaxf(acc[c] + __ldg(bias + c), 0.0f);
         const float a1 = fmaxf(acc[c + 1] + __ldg(bias + c + 1), 0.0f);
-        __nv_bfloat162 p = __floats2bfloat162_rn(a0, a1);
-        pk[k] = *reinterpret_cast<uint32_t*>(&p);
+        if (fp16) {
+          __half2 p = __floats2half2_rn(fminf(a0, 65504.0f), fminf(a1, 65504.0f));
+          pk[k] = *reinterpret_cast<uint32_t*>(&p);
+        } else {
+          __nv_bfloat162 p = __floats2bfloat162_rn(a0, a1);
+          pk[k] = *reinterpret_cast<uint32_t*>(&p);
+        }
       }
       dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
@@ -147,13 +152,13 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
 }
 
 cudaError_t launch_stem(const float* x, int batch, int h, int w, const float* w_tap_major, const float* bias,
-                        __nv_bfloat16* out, cudaStream_t stream) {
+                        __nv_bfloat16* out, int fp16, cudaStream_t stream) {
   dim3 grid((w / 2 + kStemTile - 1) / kStemTile, (h / 2 + kStemTile - 1) / kStemTile, batch);
-  stem_kernel<<<grid, 256, 0, stream>>>(x, h, w, w_tap_major, bias, out);
+  stem_kernel<<<grid, 256, 0, stream>>>(x, h, w, w_tap_major, bias, out, fp16);
   return cudaGetLastError();
 }
 
-// =========================================================================== max-pool 3x3/s2/p1 (NHWC bf16)
+// =========================================================================== max-pool 3x3/s2/p1 (NHWC 16-bit, values >= 0)
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ in, int batch, int h, int w,
                                                       int c, __nv_bfloat16* __restrict__ out) {
   const int oh = h / 2, ow = w / 2, groups = c / 8;
@@ -163,8 +168,7 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
     const int ox = (int)((i / groups) % ow);
     const int oy = (int)((i / ((size_t)groups * ow)) % oh);
     const int n = (int)(i / ((size_t)groups * ow * oh));
-    __nv_bfloat162 m[4];
-    bool first = true;
+    uint32_t m[4] = {0u, 0u, 0u, 0u};   // +0.0 in both formats: identity of max over non-negative values
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int iy = 2 * oy - 1 + r;
@@ -174,18 +178,13 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
         const int ix = 2 * ox - 1 + s;
         if (ix < 0 || ix >= w) continue;
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * h + iy) * w + ix) * c + g * 8));
-        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
-        if (first) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) m[k] = pv[k];
-          first = false;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], pv[k]);
-        }
+        m[0] = __vmaxu2(m[0], v.x);
+        m[1] = __vmaxu2(m[1], v.y);
+        m[2] = __vmaxu2(m[2], v.z);
+        m[3] = __vmaxu2(m[3], v.w);
       }
     }
-    *reinterpret_cast<uint4*>(out + (((size_t)n * oh + oy) * ow + ox) * c + g * 8) = *reinterpret_cast<uint4*>(m);
+    *reinterpret_cast<uint4*>(out + (((size_t)n * oh + oy) * ow + ox) * c + g * 8) = make_uint4(m[0], m[1], m[2], m[3]);
   }
 }
 

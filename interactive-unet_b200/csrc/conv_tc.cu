@@ -36,12 +36,19 @@ struct ConvCfg {
 
 constexpr int kThreads = 192;  // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+// 16-bit storage helpers: `fp16` selects IEEE half (clamped to the finite range) or bfloat16.
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
+  if (fp16) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.0f), 65504.0f), fminf(fmaxf(hi, -65504.0f), 65504.0f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ float2 unpack16(uint32_t v, int fp16) {
+  if (fp16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
 
 template <int KC, int BN>
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
@@ -116,7 +123,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+      const uint32_t idesc = umma_idesc_f16(kTileM, BN, a.fp16);
       for (int it = 0; it < total_iters; ++it) {
         const int st = it % Cfg::STAGES;
         const uint32_t ph = (it / Cfg::STAGES) & 1;
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 #pragma unroll
         for (int k = 0; k < KC / 16; ++k) {
           // advancing K by 16 bf16 = 32 bytes inside the swizzle span = +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(st));  // stage reusable once these MMAs have read it
       }
@@ -173,10 +180,12 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 #pragma unroll
             for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
               const uint4 rv = __ldg(rp + j);
-              v[8 * j + 0] += bf16_lo(rv.x); v[8 * j + 1] += bf16_hi(rv.x);
-              v[8 * j + 2] += bf16_lo(rv.y); v[8 * j + 3] += bf16_hi(rv.y);
-              v[8 * j + 4] += bf16_lo(rv.z); v[8 * j + 5] += bf16_hi(rv.z);
-              v[8 * j + 6] += bf16_lo(rv.w); v[8 * j + 7] += bf16_hi(rv.w);
+              const float2 r0 = unpack16(rv.x, a.fp16), r1 = unpack16(rv.y, a.fp16);
+              const float2 r2 = unpack16(rv.z, a.fp16), r3 = unpack16(rv.w, a.fp16);
+              v[8 * j + 0] += r0.x; v[8 * j + 1] += r0.y;
+              v[8 * j + 2] += r1.x; v[8 * j + 3] += r1.y;
+              v[8 * j + 4] += r2.x; v[8 * j + 5] += r2.y;
+              v[8 * j + 6] += r3.x; v[8 * j + 7] += r3.y;
             }
           }
           if (a.relu) {
@@ -186,10 +195,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
           uint4 pk[Cfg::CHUNK / 8];
 #pragma unroll
           for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
-            pk[j].x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-            pk[j].y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-            pk[j].z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-            pk[j].w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            pk[j].x = pack16(v[8 * j + 0], v[8 * j + 1], a.fp16);
+            pk[j].y = pack16(v[8 * j + 2], v[8 * j + 3], a.fp16);
+            pk[j].z = pack16(v[8 * j + 4], v[8 * j + 5], a.fp16);
+            pk[j].w = pack16(v[8 * j + 6], v[8 * j + 7], a.fp16);
           }
           __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
           if (!a.up2x) {

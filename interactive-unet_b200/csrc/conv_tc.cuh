@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -10,7 +11,7 @@ namespace iu {
 constexpr int kTileM = 128;  // output pixels per CTA tile = UMMA M
 
 enum EpilogueMode : int {
-  kEpiBf16 = 0,         // bias (+residual) (+ReLU) -> bf16 NHWC (optionally written 2x nearest-upsampled)
+  kEpiBf16 = 0,         // bias (+residual) (+ReLU) -> 16-bit NHWC (optionally written 2x nearest-upsampled)
   kEpiSoftmaxNHWC = 1,  // bias -> softmax over the first num_classes columns -> fp32 [slice][row][col][C]
   kEpiSoftmaxNCHW = 2,  // bias -> softmax -> fp32 [n][C][row][col]
 };
@@ -39,7 +40,8 @@ struct alignas(64) ConvArgs {
   const __nv_bfloat16* residual;  // optional, same geometry as the output
   void* out;
   int relu;
-  int up2x;         // bf16 mode: write every pixel to its 2x2 nearest-upsampled positions
+  int fp16;         // 16-bit storage format of activations / weights: 1 = IEEE fp16, 0 = bf16
+  int up2x;         // 16-bit mode: write every pixel to its 2x2 nearest-upsampled positions
   int mode;         // EpilogueMode
   int num_classes;  // softmax modes
   // softmax NHWC addressing (lets one buffer be laid out destination-major for the multi-GPU exchange):

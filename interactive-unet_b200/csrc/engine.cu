@@ -2,6 +2,7 @@
 // smp.Unet('resnet34'), workspace + TMA descriptor planning, and the C ABI.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -59,12 +60,22 @@ struct Scratch {
   bool used;
 };
 
+struct ProfSpan {
+  cudaEvent_t begin, end;
+  int cls;
+};
+
 uint16_t f2bf(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
   u += 0x7FFFu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
+uint16_t f2h(float f) {
+  f = std::max(-65504.0f, std::min(65504.0f, f));
+  return __half_as_ushort(__float2half_rn(f));
+}
+uint16_t to16(float f, int fp16) { return fp16 ? f2h(f) : f2bf(f); }
 
 int pow2_ceil(int v) {
   int p = 1;
@@ -88,6 +99,7 @@ struct iu_engine {
   int num_classes = 0;
   bool loaded = false;
   int max_batch = 0;
+  int fp16 = 1;  // 16-bit storage format of weights / activations: 1 = IEEE fp16 (default), 0 = bf16
   int64_t launches = 0;
   size_t weight_bytes = 0;
 
@@ -98,6 +110,13 @@ struct iu_engine {
   int t_f1 = -1, t_p1 = -1;
   Plan plan;
   std::vector<Scratch> scratch;
+
+  // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers)
+  bool prof = false;
+  std::vector<ProfSpan> spans;
+  size_t spans_used = 0;
+  double prof_ms[IU_PROF_CLASSES] = {0, 0, 0, 0, 0};
+  int64_t prof_n[IU_PROF_CLASSES] = {0, 0, 0, 0, 0};
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -119,6 +138,42 @@ struct iu_engine {
   } while (0)
 
 namespace {
+
+// ------------------------------------------------------------------ profiling spans
+void prof_flush(iu_engine* e) {
+  if (e->spans_used == 0) return;
+  cudaStreamSynchronize(e->stream);
+  for (size_t i = 0; i < e->spans_used; ++i) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, e->spans[i].begin, e->spans[i].end) == cudaSuccess) {
+      e->prof_ms[e->spans[i].cls] += ms;
+      e->prof_n[e->spans[i].cls] += 1;
+    }
+  }
+  cudaGetLastError();
+  e->spans_used = 0;
+}
+void prof_begin(iu_engine* e, int cls) {
+  if (!e->prof) return;
+  if (e->spans_used == e->spans.size()) {
+    if (e->spans.size() >= 16384) {
+      prof_flush(e);
+    } else {
+      ProfSpan s;
+      cudaEventCreate(&s.begin);
+      cudaEventCreate(&s.end);
+      s.cls = cls;
+      e->spans.push_back(s);
+    }
+  }
+  e->spans[e->spans_used].cls = cls;
+  cudaEventRecord(e->spans[e->spans_used].begin, e->stream);
+}
+void prof_end(iu_engine* e) {
+  if (!e->prof) return;
+  cudaEventRecord(e->spans[e->spans_used].end, e->stream);
+  e->spans_used += 1;
+}
 
 // ------------------------------------------------------------------ scratch pool
 int scratch_get(iu_engine* e, size_t bytes, void** out) {
@@ -203,14 +258,14 @@ bool fold_bn(const HostTensors& ht, const std::string& conv_w, const std::string
 }
 
 // K order of the implicit GEMM: segment -> tap row -> tap col -> channel (see conv_tc.cu producer loop).
-void pack_segment(std::vector<uint16_t>& dst, int ktot, int kbase, const float* w, int cout, int cin_total, int coff,
-                  int cin_s, int ks) {
+void pack_segment(std::vector<uint16_t>& dst, int fp16, int ktot, int kbase, const float* w, int cout, int cin_total,
+                  int coff, int cin_s, int ks) {
   for (int co = 0; co < cout; ++co)
     for (int r = 0; r < ks; ++r)
       for (int q = 0; q < ks; ++q)
         for (int c = 0; c < cin_s; ++c)
           dst[(size_t)co * ktot + kbase + (r * ks + q) * cin_s + c] =
-              f2bf(w[(((size_t)co * cin_total + coff + c) * ks + r) * ks + q]);
+              to16(w[(((size_t)co * cin_total + coff + c) * ks + r) * ks + q], fp16);
 }
 
 int upload_conv(iu_engine* e, ConvLayer& L, const std::vector<uint16_t>& packed, const std::vector<float>& bias) {
@@ -299,11 +354,11 @@ int add_conv(iu_engine* e, const HostTensors& ht, const std::string& name, const
   std::vector<uint16_t> packed((size_t)L.cout_pad * L.ktot, 0);
   int kbase = 0, coff = 0;
   for (int s = 0; s < nsrc; ++s) {
-    pack_segment(packed, L.ktot, kbase, w.data(), cout, cin_total, coff, src_cin[s], ksize);
+    pack_segment(packed, e->fp16, L.ktot, kbase, w.data(), cout, cin_total, coff, src_cin[s], ksize);
     kbase += ksize * ksize * src_cin[s];
     coff += src_cin[s];
   }
-  if (!ds_conv.empty()) pack_segment(packed, L.ktot, kbase, wd.data(), cout, ds_cin, 0, ds_cin, 1);
+  if (!ds_conv.empty()) pack_segment(packed, e->fp16, L.ktot, kbase, wd.data(), cout, ds_cin, 0, ds_cin, 1);
   int rc = upload_conv(e, L, packed, b);
   if (rc != IU_OK) return rc;
   e->convs.push_back(L);
@@ -404,7 +459,7 @@ int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
     const float* b = ht.get("segmentation_head.0.bias", num_classes, &err);
     if (!w || !b) return e->fail(IU_ERR_INVALID, err);
     std::vector<uint16_t> packed((size_t)16 * L.ktot, 0);
-    pack_segment(packed, L.ktot, 0, w, num_classes, 16, 0, 16, 3);
+    pack_segment(packed, e->fp16, L.ktot, 0, w, num_classes, 16, 0, 16, 3);
     int rc = upload_conv(e, L, packed, std::vector<float>(b, b + num_classes));
     if (rc != IU_OK) return rc;
     e->convs.push_back(L);
@@ -421,7 +476,7 @@ int encode_act_map(iu_engine* e, CUtensorMap* m, const void* base, int c, int w,
   cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   const CUtensorMapSwizzle swz =
       kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = e->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = e->encode(m, e->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -435,7 +490,7 @@ int encode_weight_map(iu_engine* e, CUtensorMap* m, const void* base, int ktot, 
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapSwizzle swz =
       kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = e->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = e->encode(m, e->fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -514,6 +569,7 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
     a.residual = L.residual >= 0 ? p.bufs[L.residual] : nullptr;
     a.out = L.out >= 0 ? p.bufs[L.out] : nullptr;
     a.relu = L.relu;
+    a.fp16 = e->fp16;
     a.up2x = L.up2x;
     a.mode = L.mode;
     a.num_classes = e->num_classes;
@@ -539,8 +595,12 @@ int auto_batch(const iu_engine* e, int h, int w, int want) {
 // Run the network on the `batch` slices already in plan.x_in; the head writes according to (mode, out, ...).
 int run_network(iu_engine* e, int batch, int head_mode, float* head_out, int slice0, int slice_count, int row_block) {
   Plan& p = e->plan;
-  IU_CUDA(e, launch_stem(p.x_in, batch, p.h, p.w, e->d_stem_w, e->d_stem_b, p.bufs[e->t_f1], e->stream));
+  prof_begin(e, IU_PROF_STEM);
+  IU_CUDA(e, launch_stem(p.x_in, batch, p.h, p.w, e->d_stem_w, e->d_stem_b, p.bufs[e->t_f1], e->fp16, e->stream));
+  prof_end(e);
+  prof_begin(e, IU_PROF_POOL);
   IU_CUDA(e, launch_maxpool(p.bufs[e->t_f1], batch, p.h / 2, p.w / 2, 64, p.bufs[e->t_p1], e->stream));
+  prof_end(e);
   e->launches += 2;
   for (size_t i = 0; i < e->convs.size(); ++i) {
     const ConvLayer& L = e->convs[i];
@@ -553,7 +613,9 @@ int run_network(iu_engine* e, int batch, int head_mode, float* head_out, int sli
       a.slice_count = slice_count;
       a.row_block = row_block;
     }
+    prof_begin(e, IU_PROF_CONV);
     cudaError_t ce = launch_conv_tc(a, L.kc, L.bn, e->stream);
+    prof_end(e);
     if (ce != cudaSuccess) return e->cuda_fail(ce, ("launch " + L.name).c_str());
     e->launches += 1;
   }
@@ -649,6 +711,10 @@ void iu_engine_destroy(iu_engine* e) {
   free_weights(e);
   for (auto& s : e->scratch)
     if (s.ptr) cudaFree(s.ptr);
+  for (auto& s : e->spans) {
+    cudaEventDestroy(s.begin);
+    cudaEventDestroy(s.end);
+  }
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -687,6 +753,22 @@ int iu_engine_load_weights(iu_engine* e, int num_classes, int n_tensors, const c
 
 int iu_engine_num_classes(const iu_engine* e) { return e ? e->num_classes : 0; }
 
+int iu_engine_set_precision(iu_engine* e, int precision) {
+  if (!e) return IU_ERR_INVALID;
+  if (precision != IU_PRECISION_FP16 && precision != IU_PRECISION_BF16)
+    return e->fail(IU_ERR_INVALID, "precision must be IU_PRECISION_FP16 or IU_PRECISION_BF16");
+  const int fp16 = precision == IU_PRECISION_FP16;
+  if (fp16 != e->fp16 && e->loaded) {
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    free_plan(e);
+    free_weights(e);  // packed weights are format specific: the caller must load them again
+  }
+  e->fp16 = fp16;
+  return IU_OK;
+}
+int iu_engine_precision(const iu_engine* e) { return e ? (e->fp16 ? IU_PRECISION_FP16 : IU_PRECISION_BF16) : -1; }
+
 int iu_engine_set_max_batch(iu_engine* e, int max_batch) {
   if (!e || max_batch < 0) return IU_ERR_INVALID;
   e->max_batch = max_batch;
@@ -699,6 +781,30 @@ int64_t iu_engine_workspace_bytes(iu_engine* e, int batch, int h, int w) {
 }
 
 int64_t iu_engine_launch_count(const iu_engine* e) { return e ? e->launches : 0; }
+
+int iu_engine_profile(iu_engine* e, int enable) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  prof_flush(e);
+  e->prof = enable != 0;
+  return IU_OK;
+}
+
+int iu_engine_profile_read(iu_engine* e, double* ms, int64_t* count, int reset) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!ms || !count) return e->fail(IU_ERR_INVALID, "profile_read: null output");
+  prof_flush(e);
+  for (int i = 0; i < IU_PROF_CLASSES; ++i) {
+    ms[i] = e->prof_ms[i];
+    count[i] = e->prof_n[i];
+    if (reset) {
+      e->prof_ms[i] = 0;
+      e->prof_n[i] = 0;
+    }
+  }
+  return IU_OK;
+}
 
 int iu_engine_forward(iu_engine* e, const float* x, int batch, int h, int w, float* probs, unsigned flags) {
   int rc;
@@ -750,7 +856,9 @@ int iu_engine_gather_slices(iu_engine* e, const void* volume_dev, int dtype, int
   if (!volume_dev || !out_dev || n < 16 || n % 16 || axis < 0 || axis > 2 || start < 0 || count < 1 ||
       start + count > n || (dtype != IU_DTYPE_U8 && dtype != IU_DTYPE_F32))
     return e->fail(IU_ERR_INVALID, "gather_slices: bad arguments");
+  prof_begin(e, IU_PROF_GATHER);
   IU_CUDA(e, launch_gather_slices(volume_dev, dtype == IU_DTYPE_F32, n, axis, start, count, out_dev, e->stream));
+  prof_end(e);
   e->launches += 1;
   return finish(e, flags);
 }
@@ -781,8 +889,10 @@ int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, i
   rc = ensure_plan(e, bs, n, n);
   for (int s = 0; rc == IU_OK && s < slice_count; s += bs) {
     const int b = std::min(bs, slice_count - s);
+    prof_begin(e, IU_PROF_GATHER);
     cudaError_t ce =
         launch_gather_slices(vol_dev, dtype == IU_DTYPE_F32, n, axis, slice_begin + s, b, e->plan.x_in, e->stream);
+    prof_end(e);
     if (ce != cudaSuccess) {
       rc = e->cuda_fail(ce, "launch gather_slices");
       break;
@@ -837,7 +947,9 @@ int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float
     }
   }
   a.g1d = g_dev;
+  prof_begin(e, IU_PROF_REDUCE);
   cudaError_t ce = launch_reduce(a, e->stream);
+  prof_end(e);
   e->launches += 1;
   if (g_dev) {
     // the window table is tiny; wait so the scratch block can be handed out again safely
@@ -932,8 +1044,8 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
     return e->fail(IU_ERR_INVALID, "conv_test: no kernel variant for these channel counts");
   const int ktot = ksize * ksize * cin_total;
   std::vector<uint16_t> packed((size_t)cout * ktot, 0);
-  pack_segment(packed, ktot, 0, weight, cout, cin_total, 0, cin0, ksize);
-  if (src1) pack_segment(packed, ktot, ksize * ksize * cin0, weight, cout, cin_total, cin0, cin1, ksize);
+  pack_segment(packed, e->fp16, ktot, 0, weight, cout, cin_total, 0, cin0, ksize);
+  if (src1) pack_segment(packed, e->fp16, ktot, ksize * ksize * cin0, weight, cout, cin_total, cin0, cin1, ksize);
   void* d_w = nullptr;
   float* d_b = nullptr;
   if ((rc = scratch_get(e, packed.size() * 2, &d_w)) != IU_OK) return rc;
@@ -961,6 +1073,7 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
     a.residual = (const __nv_bfloat16*)residual;
     a.out = out;
     a.relu = relu;
+    a.fp16 = e->fp16;
     a.up2x = up2x;
     a.mode = kEpiBf16;
     cudaError_t ce = launch_conv_tc(a, kc, bn, e->stream);

@@ -4,6 +4,7 @@ Thin by design: argument marshalling, pointer extraction from numpy arrays (host
 tensors (device), and error mapping.  All arithmetic happens in the library's sm_100a kernels.
 """
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -58,16 +59,24 @@ class Engine:
     """One native engine bound to one CUDA device.  Calls are serialised with a lock because
     the reference calls the prediction entry points from worker threads (`app.py:737-739`)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, precision=None):
+        """`precision`: 16-bit storage format of weights / activations, "fp16" (default) or "bf16"
+        (env `IU_PRECISION` overrides the default).  Accumulation is fp32 either way."""
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         self._lock = threading.RLock()
         if isinstance(device, torch.device):
             device = device.index or 0
+        precision = precision or os.environ.get("IU_PRECISION", "fp16")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         rc = self._lib.iu_engine_create(int(device), ctypes.byref(self._h))
         if rc != _lib.IU_OK:
             msg = self._lib.iu_last_error(None)
             raise _lib.EngineError(rc, msg.decode() if msg else "iu_engine_create failed")
+        self._check(self._lib.iu_engine_set_precision(self._h, _lib.PRECISIONS[precision]))
+        self.precision = precision
+        self.act_dtype = torch.float16 if precision == "fp16" else torch.bfloat16
         self.device = torch.device("cuda", int(device))
         self.num_classes = 0
 
@@ -119,6 +128,18 @@ class Engine:
 
     def launch_count(self):
         return int(self._lib.iu_engine_launch_count(self._h))
+
+    def profile(self, enable=True):
+        """Bracket every kernel launch with CUDA events on the engine's stream (per-class timing)."""
+        self._check(self._lib.iu_engine_profile(self._h, int(bool(enable))))
+
+    def profile_read(self, reset=True):
+        """dict class -> (kernel milliseconds, launches) accumulated while profiling was enabled."""
+        n = len(_lib.PROF_CLASSES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        self._check(self._lib.iu_engine_profile_read(self._h, ms, cnt, int(bool(reset))))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROF_CLASSES)}
 
     def stream_handle(self):
         return int(self._lib.iu_engine_stream(self._h) or 0)
@@ -218,7 +239,9 @@ class Engine:
         pad = ksize // 2
         oh, ow = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
         f = 2 if up2x else 1
-        out = torch.zeros((b, oh * f, ow * f, cout), dtype=torch.bfloat16, device=src0.device)
+        if src0.dtype != self.act_dtype:
+            raise TypeError(f"engine precision is {self.precision}: tensors must be {self.act_dtype}")
+        out = torch.zeros((b, oh * f, ow * f, cout), dtype=self.act_dtype, device=src0.device)
         wt = np.ascontiguousarray(weight, dtype=np.float32)
         bs = np.ascontiguousarray(bias, dtype=np.float32)
         with self._lock:

@@ -124,10 +124,11 @@ def predict_block(model, block, num_classes=2, batch_size=8, axes=[0, 1, 2]):
 
 
 def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=0.25, batch_size=None,
-                         axes=[0, 1, 2], return_labels=False):
+                         axes=[0, 1, 2], return_labels=False, out=None, out_labels=None):
     """In-memory core of `predict_volumes` (`predict.py:153,201,235-256`): uint8 volume `[N,N,N]`
     (numpy, or a CUDA tensor to keep everything device-resident) -> uint8 probabilities `[N,N,N,C]`
-    (and uint8 argmax labels `[N,N,N]` with `return_labels=True`), same container kind as the input."""
+    (and uint8 argmax labels `[N,N,N]` with `return_labels=True`), same container kind as the input.
+    `out` / `out_labels` may be preallocated (e.g. pinned host arrays) to avoid per-call allocation."""
     n = volume.shape[0]
     input_size = n if input_size is None else input_size
     if tuple(volume.shape) != (n, n, n) or input_size != n:
@@ -139,13 +140,18 @@ def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=
         raise ValueError(f"model has {eng.num_classes} classes, num_classes={num_classes} requested")
     eng.set_max_batch(batch_size or 0)
     window = gaussian_window_1d(input_size, sigma=0.125)               # predict.py:153
+    lab = out_labels
     if isinstance(volume, torch.Tensor):
-        out = torch.empty((n, n, n, num_classes), dtype=torch.uint8, device=volume.device)
-        lab = torch.empty((n, n, n), dtype=torch.uint8, device=volume.device) if return_labels else None
+        if out is None:
+            out = torch.empty((n, n, n, num_classes), dtype=torch.uint8, device=volume.device)
+        if lab is None and return_labels:
+            lab = torch.empty((n, n, n), dtype=torch.uint8, device=volume.device)
     else:
         volume = np.ascontiguousarray(volume)
-        out = np.empty((n, n, n, num_classes), dtype=np.uint8)
-        lab = np.empty((n, n, n), dtype=np.uint8) if return_labels else None
+        if out is None:
+            out = np.empty((n, n, n, num_classes), dtype=np.uint8)
+        if lab is None and return_labels:
+            lab = np.empty((n, n, n), dtype=np.uint8)
     try:
         eng.predict_volume(volume, axes=list(axes), window=window, out_u8=out, out_labels=lab)
     finally:

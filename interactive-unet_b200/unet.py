@@ -57,7 +57,8 @@ def _install_pickle_shims():
 
             def _placeholder(*a, **k):
                 raise RuntimeError(f"interactive_unet.metrics.{name} is a checkpoint placeholder")
-            _placeholder.__name__ = name
+            _placeholder.__name__ = _placeholder.__qualname__ = name
+            _placeholder.__module__ = "interactive_unet.metrics"
             setattr(self, name, _placeholder)
             return _placeholder
 
@@ -92,6 +93,7 @@ class UNet(_Base):
         self.softmax = nn.Softmax(dim=1)
         self._engine = None
         self._engine_key = None
+        self.precision = None          # None -> engine default ("fp16", or env IU_PRECISION); or "bf16"
 
     # ---- engine management ----------------------------------------------------------------
     def _weights_key(self):
@@ -103,8 +105,9 @@ class UNet(_Base):
         if dev.type != "cuda":
             raise RuntimeError("interactive_unet_b200 runs on CUDA (sm_100a) only: move the model with "
                                ".to('cuda'); there is no CPU fallback")
-        if self._engine is None or self._engine.device != torch.device("cuda", dev.index or 0):
-            self._engine = Engine(dev.index or 0)
+        if (self._engine is None or self._engine.device != torch.device("cuda", dev.index or 0)
+                or (self.precision is not None and self._engine.precision != self.precision)):
+            self._engine = Engine(dev.index or 0, precision=self.precision)
             self._engine_key = None
         key = self._weights_key()
         if key != self._engine_key:

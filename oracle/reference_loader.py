@@ -84,6 +84,10 @@ def load():
     if not available():
         raise RuntimeError(f"reference tree not present under {REFERENCE_ROOT}")
     _install_placeholders()
+    # the product's checkpoint-unpickling shim may have registered a path-less stand-in package
+    if not hasattr(sys.modules.get("interactive_unet"), "__path__"):
+        for name in [m for m in sys.modules if m == "interactive_unet" or m.startswith("interactive_unet.")]:
+            del sys.modules[name]
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     _cached = importlib.import_module("interactive_unet.predict")

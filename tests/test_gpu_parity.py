@@ -1,0 +1,410 @@
+"""GPU parity tests (run with `-m gpu` on a B200).  Everything goes through the C ABI of
+`libiunet_b200.so`; the oracle (`oracle/`, committed golden vectors, PyTorch fp32 on the same GPU
+with TF32 disabled) is only the checker.
+
+Tolerances (BASELINE.json north_star / BASELINE.md section 5):
+  * integer / byte / index work (gather, reduce, quantise, labels): bit-exact;
+  * probabilities vs the strict-fp32 oracle: max-abs error <= 1e-2;
+  * argmax agreement >= 99.9 %, every disagreement a near-tie (top-2 gap <= 2e-2).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-2
+NEAR_TIE = 2e-2
+MIN_AGREEMENT = 0.999
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (there is no CPU fallback to test)")
+    torch.backends.cudnn.allow_tf32 = False          # strict fp32 oracle
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def iu(built_library):
+    import interactive_unet_b200
+    return interactive_unet_b200
+
+
+@pytest.fixture(scope="module")
+def fitted(dev, iu):
+    """Oracle networks fitted for 100 AdamW steps on synthetic blobs (decisive softmax), plus the
+    drop-in modules loaded from their state_dicts."""
+    from oracle import synth
+    vol, lab = synth.blob_volume(64, 1)
+    out = {}
+    for c in (2, 4):
+        ref = synth.fit_decisive(synth.make_model(c), vol, lab % c if c == 2 else (lab + 2 * (vol > 128)) % c,
+                                 steps=100, batch=8, device=dev).to(dev).eval()
+        model = iu.UNet(num_classes=c)
+        model.load_state_dict(ref.state_dict())
+        out[c] = (ref, model.to(dev).eval())
+    return out
+
+
+# --------------------------------------------------------------------------- tensor-core conv kernel
+CONV_CASES = [
+    # name, batch, h, w, cin0, cin1, cout, ksize, stride, residual, relu, up2x
+    ("k64n64", 8, 16, 16, 64, 0, 64, 3, 1, False, True, False),
+    ("k64n128", 8, 32, 32, 128, 0, 128, 3, 1, False, True, False),
+    ("k64n128_deep", 8, 16, 16, 512, 0, 512, 3, 1, True, True, False),
+    ("cat_k64n32", 8, 32, 32, 64, 64, 32, 3, 1, False, True, False),
+    ("cat_k64n128", 8, 16, 16, 512, 256, 256, 3, 1, False, True, False),
+    ("k32n32", 8, 32, 32, 32, 0, 32, 3, 1, False, True, False),
+    ("k32n16", 8, 64, 64, 32, 0, 16, 3, 1, False, True, False),
+    ("k16n16", 8, 64, 64, 16, 0, 16, 3, 1, False, True, False),
+    ("stride2_3x3", 8, 32, 32, 64, 0, 128, 3, 2, False, True, False),
+    ("stride2_1x1", 8, 32, 32, 128, 0, 256, 1, 2, False, False, False),
+    ("residual_up2x", 8, 16, 16, 64, 0, 64, 3, 1, True, True, True),
+    ("tiny_4x4", 8, 4, 4, 512, 0, 512, 3, 1, True, True, True),
+    ("ragged_24x24", 8, 24, 24, 64, 0, 64, 3, 1, False, True, False),
+    ("ragged_3x3", 8, 3, 3, 256, 0, 256, 3, 1, False, True, False),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_matches_fp32_reference(dev, iu, case, precision):
+    _, b, h, w, c0, c1, cout, k, stride, residual, relu, up2x = case
+    act = torch.float16 if precision == "fp16" else torch.bfloat16
+    eng = iu.Engine(0, precision=precision)
+    g = torch.Generator().manual_seed(hash(case[0]) % 1000)
+    src0 = torch.randn(b, h, w, c0, generator=g).to(dev).to(act)
+    src1 = torch.randn(b, h, w, c1, generator=g).to(dev).to(act) if c1 else None
+    cin = c0 + c1
+    wt = (torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)).numpy()
+    bias = (0.1 * torch.randn(cout, generator=g)).numpy()
+    oh, ow = (h + 2 * (k // 2) - k) // stride + 1, (w + 2 * (k // 2) - k) // stride + 1
+    res = torch.randn(b, oh, ow, cout, generator=g).to(dev).to(act) if residual else None
+    got = eng.conv_test(src0, src1, wt, bias, k, stride, residual=res, relu=relu, up2x=up2x).float()
+
+    x = (src0 if src1 is None else torch.cat([src0, src1], 3)).float().permute(0, 3, 1, 2)
+    y = F.conv2d(x, torch.from_numpy(wt).to(dev).to(act).float(), torch.from_numpy(bias).to(dev), stride=stride,
+                 padding=k // 2)
+    if res is not None:
+        y = y + res.float().permute(0, 3, 1, 2)
+    if relu:
+        y = torch.relu(y)
+    if up2x:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    want = y.permute(0, 2, 3, 1)
+    ulp = 2.0 ** -10 if precision == "fp16" else 2.0 ** -7         # one output rounding + accumulation order
+    assert got.shape == want.shape
+    assert torch.all((got - want).abs() <= 2e-3 + ulp * want.abs())
+
+
+# --------------------------------------------------------------------------- K1 gather (bit-exact)
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_gather_slices_bit_exact(dev, iu, axis):
+    from oracle import predict_port as pp
+    eng = iu.Engine(0)
+    rng = np.random.default_rng(11 + axis)
+    n = 96
+    vol = rng.integers(0, 256, (n, n, n), dtype=np.uint8)
+    vol_d = torch.from_numpy(vol).to(dev)
+    norm = pp.normalise_u8(vol)
+    for start, count in ((0, 32), (5, 40), (95, 1), (0, 96)):
+        got = eng.gather_slices(vol_d, axis, start, count).cpu().numpy()
+        assert np.array_equal(got, pp.slice_batch(norm, axis, start, count)[:, 0])
+    volf = rng.random((n, n, n), dtype=np.float32)
+    got = eng.gather_slices(torch.from_numpy(volf).to(dev), axis, 7, 33).cpu().numpy()
+    assert np.array_equal(got, pp.slice_batch(volf, axis, 7, 33)[:, 0])
+
+
+def test_gather_covers_all_256_values(dev, iu):
+    eng = iu.Engine(0)
+    vol = np.tile(np.arange(256, dtype=np.uint8), 32 * 32 * 32 // 256).reshape(32, 32, 32)
+    got = eng.gather_slices(torch.from_numpy(vol).to(dev), 0, 0, 32).cpu().numpy()
+    assert np.array_equal(got, (vol / 255).astype(np.float32))      # predict.py:30 form of the division
+
+
+# --------------------------------------------------------------------------- K4 reduce / quantise / argmax
+def _axis_probs_from_toy(vol_u8, c):
+    """Per-axis slice-major probabilities of the exact toy model, [slice][row][col][C]."""
+    from oracle import predict_port as pp
+    from oracle.make_golden import toy_model_numpy
+    x = pp.normalise_u8(vol_u8)
+    n = vol_u8.shape[0]
+    return {a: np.ascontiguousarray(np.moveaxis(toy_model_numpy(pp.slice_batch(x, a, 0, n), c), 1, -1))
+            for a in (0, 1, 2)}
+
+
+@pytest.mark.parametrize("name", ["block_s16_c2_a012", "block_s16_c4_a012", "block_s16_c3_a20", "block_s8_c2_a1"])
+def test_reduce_matches_reference_predict_block_golden(dev, iu, golden_dir, name):
+    """Mean probabilities recorded from the VERBATIM reference `predict_block` (toy model)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    c, axes = int(g["num_classes"]), [int(a) for a in g["axes"]]
+    n = g["volume"].shape[0]
+    eng = iu.Engine(0)
+    eng.num_classes = c
+    probs = {a: torch.from_numpy(p).to(dev) for a, p in _axis_probs_from_toy(g["volume"], c).items() if a in axes}
+    mean = torch.zeros((n, n, n, c), dtype=torch.float32, device=dev)
+    eng.reduce(probs, axes, n, out_mean=mean)
+    assert np.array_equal(mean.cpu().numpy(), g["mean_probs"])
+
+
+@pytest.mark.parametrize("name", ["volume_single_s32_c2", "volume_single_s32_c4"])
+def test_reduce_quantise_matches_reference_predict_volumes_golden(dev, iu, golden_dir, name):
+    """uint8 output recorded from the VERBATIM reference `predict_volumes` (single-block case)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    c, axes = int(g["num_classes"]), [int(a) for a in g["axes"]]
+    n = g["volume"].shape[0]
+    eng = iu.Engine(0)
+    eng.num_classes = c
+    probs = {a: torch.from_numpy(p).to(dev) for a, p in _axis_probs_from_toy(g["volume"], c).items() if a in axes}
+    out = torch.zeros((n, n, n, c), dtype=torch.uint8, device=dev)
+    eng.reduce(probs, axes, n, window=iu.gaussian_window_1d(n), out_u8=out)
+    assert np.array_equal(out.cpu().numpy(), g["out_u8"])
+
+
+@pytest.mark.parametrize("c,order", [(2, [0, 1, 2]), (4, [0, 1, 2]), (3, [2, 0]), (5, [1]), (10, [2, 1, 0])])
+def test_reduce_random_probabilities_bit_exact(dev, iu, c, order):
+    from oracle import predict_port as pp
+    rng = np.random.default_rng(c)
+    n = 48                                              # ragged against the kernel's 32x32 tile
+    p = {a: rng.random((n, n, n, c), dtype=np.float32) for a in order}
+    acc = np.zeros((n, n, n, c), np.float32)
+    for a in order:
+        pp.scatter_batch(acc, p[a], a, 0)
+    mean = acc / np.float32(len(order))
+    want_u8 = pp.quantise(*pp.blend_single_block(mean, pp.gaussian_3d(n)))
+    eng = iu.Engine(0)
+    eng.num_classes = c
+    out_u8 = torch.zeros((n, n, n, c), dtype=torch.uint8, device=dev)
+    out_lab = torch.zeros((n, n, n), dtype=torch.uint8, device=dev)
+    out_mean = torch.zeros((n, n, n, c), dtype=torch.float32, device=dev)
+    eng.reduce({a: torch.from_numpy(v).to(dev) for a, v in p.items()}, order, n, window=iu.gaussian_window_1d(n),
+               out_u8=out_u8, out_labels=out_lab, out_mean=out_mean)
+    assert np.array_equal(out_mean.cpu().numpy(), mean)
+    assert np.array_equal(out_u8.cpu().numpy(), want_u8)
+    assert np.array_equal(out_lab.cpu().numpy(), pp.labels_from_probs(mean, c).astype(np.uint8))
+
+
+def test_reduce_ties_and_saturation(dev, iu):
+    """Exact ties pick the first class (np.argmax); probability 1.0 follows the reference's
+    255*(m*w)/w arithmetic (which yields 254 for some window values) bit for bit."""
+    from oracle import predict_port as pp
+    n, c = 32, 3
+    p = np.zeros((n, n, n, c), np.float32)
+    p[..., 1] = 0.5
+    p[..., 2] = 0.5
+    p[: n // 2, ..., :] = (1.0, 0.0, 0.0)
+    eng = iu.Engine(0)
+    eng.num_classes = c
+    out_u8 = torch.zeros((n, n, n, c), dtype=torch.uint8, device=dev)
+    out_lab = torch.zeros((n, n, n), dtype=torch.uint8, device=dev)
+    eng.reduce({0: torch.from_numpy(p).to(dev)}, [0], n, window=iu.gaussian_window_1d(n), out_u8=out_u8,
+               out_labels=out_lab)
+    assert np.array_equal(out_lab.cpu().numpy(), np.argmax(p, -1).astype(np.uint8))
+    assert np.array_equal(out_u8.cpu().numpy(), pp.quantise(*pp.blend_single_block(p, pp.gaussian_3d(n))))
+
+
+# --------------------------------------------------------------------------- the network (UNet.forward)
+def _check_probs(got, want):
+    err = (got - want).abs().max().item()
+    assert err <= PROB_TOL, f"max-abs probability error {err}"
+    dis = got.argmax(1) != want.argmax(1)
+    agreement = 1.0 - dis.float().mean().item()
+    assert agreement >= MIN_AGREEMENT, f"argmax agreement {agreement}"
+    if dis.any():
+        top2 = want.topk(2, dim=1).values
+        gap = (top2[:, 0] - top2[:, 1])[dis]
+        assert gap.max().item() <= NEAR_TIE, f"disagreement at top-2 gap {gap.max().item()}"
+    return err, agreement
+
+
+@pytest.mark.parametrize("c", [2, 4])
+@pytest.mark.parametrize("size", [64, 128, 256, 512])
+def test_forward_matches_fp32_oracle(dev, fitted, c, size):
+    from oracle import synth
+    ref, model = fitted[c]
+    vol, _ = synth.blob_volume(64, 5) if size == 64 else synth.blob_volume(128, 5)
+    img = np.tile(vol[:2], (1, (size + vol.shape[1] - 1) // vol.shape[1], (size + vol.shape[2] - 1) // vol.shape[2]))
+    x = torch.from_numpy(img[:, :size, :size].astype(np.float32) / 255.0)[:, None].to(dev)
+    with torch.inference_mode():
+        want = ref(x)
+        got = model(x)
+    assert got.shape == want.shape and got.dtype == torch.float32
+    _check_probs(got, want)
+    assert torch.allclose(got.sum(1), torch.ones_like(got[:, 0]), atol=1e-5)
+
+
+def test_forward_rectangular_and_ragged_batch(dev, fitted):
+    ref, model = fitted[2]
+    x = torch.rand(5, 1, 96, 160, device=dev)
+    with torch.inference_mode():
+        _check_probs(model(x), ref(x))
+
+
+def test_forward_rejects_bad_shapes(dev, fitted):
+    _, model = fitted[2]
+    with pytest.raises(RuntimeError, match="divisible by 32"):
+        model(torch.rand(1, 1, 48, 64, device=dev))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.rand(1, 1, 64, 64))
+
+
+def test_bf16_storage_mode_is_close(dev, fitted, iu):
+    """bf16 storage (selectable) sits at the edge of the 1e-2 gate; it must stay within 2e-2 and agree on labels."""
+    ref, _ = fitted[2]
+    model = iu.UNet(num_classes=2)
+    model.precision = "bf16"
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev).eval()
+    x = torch.rand(2, 1, 128, 128, device=dev)
+    with torch.inference_mode():
+        want, got = ref(x), model(x)
+    assert (got - want).abs().max().item() <= 2e-2
+    assert (got.argmax(1) == want.argmax(1)).float().mean().item() >= 0.999
+
+
+# --------------------------------------------------------------------------- predict_block / predict_volumes
+@pytest.mark.parametrize("c,axes", [(2, [0, 1, 2]), (4, [0, 1, 2]), (2, [0]), (2, [2, 0])])
+def test_predict_block_matches_reference_algorithm(dev, fitted, iu, c, axes):
+    """Drop-in `predict_block` vs the port of `predict.py:79-112` driven by the fp32 oracle network."""
+    from oracle import predict_port as pp
+    from oracle import synth
+    ref, model = fitted[c]
+    n = 64
+    vol, _ = synth.blob_volume(n, 9)
+
+    def fwd(x):
+        with torch.inference_mode():
+            return ref(torch.from_numpy(x).to(dev)).cpu().numpy()
+    want = pp.predict_block(fwd, pp.normalise_u8(vol), c, 16, tuple(axes))
+    got = iu.predict.predict_block(model, torch.tensor(vol.astype("float32") / 255.0), num_classes=c, batch_size=16,
+                                   axes=axes)
+    assert got.dtype == np.float32 and got.shape == (n, n, n, c)
+    assert np.abs(got - want).max() <= PROB_TOL
+    dis = got.argmax(-1) != want.argmax(-1)
+    assert 1.0 - dis.mean() >= MIN_AGREEMENT
+    if dis.any():
+        s = np.sort(want, -1)
+        assert (s[..., -1] - s[..., -2])[dis].max() <= NEAR_TIE
+
+
+def test_predict_volume_array_tail_is_bit_exact(dev, fitted, iu):
+    """uint8 probabilities and labels are bit-exact functions (predict.py:244-245,255,38) of the
+    engine's own fp32 mean probabilities; host (numpy) and device (torch) entry agree bit for bit."""
+    from oracle import predict_port as pp
+    from oracle import synth
+    _, model = fitted[2]
+    n = 64
+    vol, _ = synth.blob_volume(n, 10)
+    mean = iu.predict.predict_block(model, torch.tensor(vol.astype("float32") / 255.0), 2, 8, [0, 1, 2])
+    u8, lab = iu.predict.predict_volume_array(model, vol, num_classes=2, return_labels=True)
+    assert np.array_equal(u8, pp.quantise(*pp.blend_single_block(mean, pp.gaussian_3d(n))))
+    assert np.array_equal(lab, mean.argmax(-1).astype(np.uint8))
+    u8_d, lab_d = iu.predict.predict_volume_array(model, torch.from_numpy(vol).to(dev), num_classes=2,
+                                                  return_labels=True)
+    assert np.array_equal(u8_d.cpu().numpy(), u8) and np.array_equal(lab_d.cpu().numpy(), lab)
+
+
+def test_batch_size_independence_and_determinism(dev, fitted, iu):
+    from oracle import synth
+    _, model = fitted[2]
+    vol = torch.from_numpy(synth.noise_volume(64, 3)).to(dev)
+    a = iu.predict.predict_volume_array(model, vol, num_classes=2, batch_size=8)
+    b = iu.predict.predict_volume_array(model, vol, num_classes=2, batch_size=24)      # ragged last batch
+    c = iu.predict.predict_volume_array(model, vol, num_classes=2)
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_predict_slice_drop_in(dev, fitted, iu, tmp_path, monkeypatch):
+    """`predict_slice` (predict.py:16-47) with a checkpoint in the reference's on-disk layout."""
+    ref, _ = fitted[2]
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("model")
+    torch.save({"state_dict": ref.state_dict(),
+                "hyper_parameters": dict(lr=1e-4, num_channels=1, num_classes=2, architecture="U-Net",
+                                         encoder_name="resnet34", pretrained=False)}, "model/model.ckpt")
+    img = np.random.default_rng(0).integers(0, 256, (128, 96), dtype=np.uint8)
+    overlay = iu.predict.predict_slice(img, num_classes=2)
+    probs = iu.predict.predict_slice(img, num_classes=2, return_probabilities=True)
+    assert overlay.shape == (128, 96, 3) and overlay.dtype == np.uint8
+    assert probs.shape == (1, 128, 96, 2)
+    with torch.inference_mode():
+        want = ref(torch.from_numpy((img[None, None] / 255).astype("float32")).to(dev)).cpu().numpy()
+    assert np.abs(np.moveaxis(probs, -1, 1) - want).max() <= PROB_TOL
+    lab = probs[0].argmax(-1)
+    assert np.array_equal(overlay[lab == 0], np.tile(iu.predict.COLORS[1], ((lab == 0).sum(), 1)))
+
+
+def test_find_max_batch_size(dev, fitted, iu):
+    _, model = fitted[2]
+    assert iu.predict.find_max_batch_size(model, input_size=64, start=4, max_limit=16) == 16
+
+
+# --------------------------------------------------------------------------- sharded path on one GPU
+def test_z_slab_partition_is_bit_identical(dev, fitted, iu):
+    """The G-way z-slab partition executed rank by rank on ONE GPU, with the
+    all-to-all done by slicing, must equal the single-GPU output bit for bit."""
+    from oracle import synth
+    _, model = fitted[2]
+    eng = model.engine()
+    n, g, c = 64, 4, 2
+    t = n // g
+    vol = torch.from_numpy(synth.blob_volume(n, 12)[0]).to(dev)
+    window = iu.gaussian_window_1d(n)
+    want_u8 = torch.empty((n, n, n, c), dtype=torch.uint8, device=dev)
+    want_lab = torch.empty((n, n, n), dtype=torch.uint8, device=dev)
+    eng.predict_volume(vol, axes=(0, 1, 2), window=window, out_u8=want_u8, out_labels=want_lab)
+    send = {a: [torch.empty((g, t, t, n, c), dtype=torch.float32, device=dev) for _ in range(g)] for a in (1, 2)}
+    p0 = []
+    for r in range(g):
+        p0.append(eng.predict_axis(vol, 0, slice_begin=r * t, slice_count=t))
+        for a in (1, 2):
+            eng.predict_axis(vol, a, slice_begin=r * t, slice_count=t, out=send[a][r], slice_total=t, row_block=t)
+    for h in range(g):
+        recv = {a: torch.stack([send[a][src][h] for src in range(g)]).contiguous() for a in (1, 2)}   # all-to-all
+        u8 = torch.empty((t, n, n, c), dtype=torch.uint8, device=dev)
+        lab = torch.empty((t, n, n), dtype=torch.uint8, device=dev)
+        eng.reduce({0: p0[h], 1: recv[1], 2: recv[2]}, [0, 1, 2], n, t=t, z0=h * t, window=window, out_u8=u8,
+                   out_labels=lab)
+        assert torch.equal(u8, want_u8[h * t:(h + 1) * t])
+        assert torch.equal(lab, want_lab[h * t:(h + 1) * t])
+
+
+# --------------------------------------------------------------------------- full-size properties (512^3)
+@pytest.fixture(scope="module")
+def big_run(dev, fitted, iu):
+    from oracle import synth
+    _, model = fitted[2]
+    n = 512
+    vol = torch.from_numpy(synth.noise_volume(n, 1)).to(dev)
+    u8, lab = iu.predict.predict_volume_array(model, vol, num_classes=2, return_labels=True)
+    return model, vol, u8, lab
+
+
+def test_full_size_outputs_are_consistent(big_run):
+    """BASELINE config 2 (512^3, 2 classes, 3 axes): size-independent properties of the output."""
+    _, vol, u8, lab = big_run
+    s = u8.to(torch.int32).sum(-1)
+    assert int(s.min()) >= 253 and int(s.max()) <= 255        # trunc(255p)+trunc(255(1-p)) with the window round trip
+    decided = (u8[..., 0].to(torch.int32) - u8[..., 1].to(torch.int32)).abs() > 1
+    assert torch.equal(lab[decided], u8.argmax(-1).to(torch.uint8)[decided])
+
+
+def test_full_size_axis_swap_equivariance(big_run, iu):
+    """Swapping z and y of the volume maps axis-0 slices onto axis-1 slices with the SAME image
+    orientation, so predict(V^T, axes=[0,1]) must equal predict(V, axes=[1,0])^T bit for bit."""
+    model, vol, _, _ = big_run
+    a = iu.predict.predict_volume_array(model, vol, num_classes=2, axes=[1, 0])
+    b = iu.predict.predict_volume_array(model, vol.transpose(0, 1).contiguous(), num_classes=2, axes=[0, 1])
+    assert torch.equal(b, a.transpose(0, 1))
+
+
+def test_full_size_is_deterministic(big_run, iu):
+    model, vol, u8, lab = big_run
+    u8b, labb = iu.predict.predict_volume_array(model, vol, num_classes=2, return_labels=True)
+    assert torch.equal(u8, u8b) and torch.equal(lab, labb)

@@ -18,12 +18,13 @@ import interactive_unet_b200 as iu  # noqa: E402
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda:0")
+ACT = torch.float16
 
 
 def ref_conv(src0, src1, w, b, ksize, stride, residual, relu, up2x):
     x = src0 if src1 is None else torch.cat([src0, src1], dim=3)
     x = x.float().permute(0, 3, 1, 2)
-    wq = torch.from_numpy(w).to(dev).bfloat16().float()
+    wq = torch.from_numpy(w).to(dev).to(ACT).float()
     y = F.conv2d(x, wq, torch.from_numpy(b).to(dev), stride=stride, padding=ksize // 2)
     if residual is not None:
         y = y + residual.float().permute(0, 3, 1, 2)
@@ -37,8 +38,8 @@ def ref_conv(src0, src1, w, b, ksize, stride, residual, relu, up2x):
 def conv_case(eng, name, b, h, w, c0, c1, cout, ksize, stride, residual=False, relu=True, up2x=False, seed=0,
               weight_kind="rand"):
     g = torch.Generator(device="cpu").manual_seed(seed)
-    src0 = torch.randn(b, h, w, c0, generator=g).to(dev).bfloat16()
-    src1 = torch.randn(b, h, w, c1, generator=g).to(dev).bfloat16() if c1 else None
+    src0 = torch.randn(b, h, w, c0, generator=g).to(dev).to(ACT)
+    src1 = torch.randn(b, h, w, c1, generator=g).to(dev).to(ACT) if c1 else None
     cin = c0 + c1
     if weight_kind == "delta":
         wt = np.zeros((cout, cin, ksize, ksize), np.float32)
@@ -49,7 +50,7 @@ def conv_case(eng, name, b, h, w, c0, c1, cout, ksize, stride, residual=False, r
     bias = (0.1 * torch.randn(cout, generator=g)).numpy() if weight_kind != "delta" else np.zeros(cout, np.float32)
     pad = ksize // 2
     oh, ow = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
-    res = torch.randn(b, oh, ow, cout, generator=g).to(dev).bfloat16() if residual else None
+    res = torch.randn(b, oh, ow, cout, generator=g).to(dev).to(ACT) if residual else None
     try:
         t0 = time.time()
         out = eng.conv_test(src0, src1, wt, bias, ksize, stride, residual=res, relu=relu, up2x=up2x)
@@ -158,17 +159,23 @@ def probe_tail(eng):
     return ok_all
 
 
-def probe_network(eng_unused, sizes=(64, 128)):
-    """Whole network vs the fp32 oracle (strict fp32 on the GPU)."""
+def probe_network(precision, sizes=(64, 128, 256)):
+    """Whole network vs the fp32 oracle (strict fp32 on the GPU), random-init and fitted weights."""
     from oracle import synth
     ok_all = True
-    for c in (2, 4):
-        ref = synth.make_model(c).to(dev)
+    vol, lab = synth.blob_volume(64, 1)
+    vol2, _ = synth.blob_volume(256, 2)
+    for c, fitted in ((2, False), (2, True), (4, True)):
+        ref = synth.make_model(c)
+        if fitted:
+            ref = synth.fit_decisive(ref, vol, lab % c, steps=100, batch=8, device=dev)
+        ref = ref.to(dev).eval()
         model = iu.UNet(num_classes=c)
+        model.precision = precision
         model.load_state_dict(ref.state_dict())
         model = model.to(dev).eval()
         for s in sizes:
-            x = torch.rand(3, 1, s, s, device=dev)
+            x = torch.from_numpy(vol2[:3, :s, :s].astype("float32") / 255.0)[:, None].to(dev)
             with torch.inference_mode():
                 want = ref(x)
                 t0 = time.time()
@@ -179,27 +186,74 @@ def probe_network(eng_unused, sizes=(64, 128)):
             agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
             ok = err < 1e-2
             ok_all &= ok
-            print(f"[network] C={c} S={s}: max|dp| {err:.4g} argmax agreement {agree:.5f} "
+            print(f"[network {precision}] C={c} fitted={fitted} S={s}: max|dp| {err:.4g} argmax agreement {agree:.5f} "
                   f"prob range [{want.min().item():.3f},{want.max().item():.3f}] {'OK' if ok else 'FAIL'} ({dt*1e3:.1f} ms)")
     return ok_all
 
 
+def probe_volume(precision):
+    """predict_volume end to end vs the oracle port driven by the fp32 oracle network on the GPU; then timing."""
+    from oracle import predict_port as pp
+    from oracle import synth
+    n, c = 64, 2
+    vol, lab = synth.blob_volume(n, 1)
+    ref = synth.fit_decisive(synth.make_model(c), vol, lab, steps=100, batch=8, device=dev).to(dev).eval()
+    model = iu.UNet(num_classes=c)
+    model.precision = precision
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev).eval()
+
+    def fwd(x):
+        with torch.inference_mode():
+            return ref(torch.from_numpy(x).to(dev)).cpu().numpy()
+    want_mean = pp.predict_block(fwd, pp.normalise_u8(vol), c, 16, (0, 1, 2))
+    want_u8 = pp.quantise(*pp.blend_single_block(want_mean, pp.gaussian_3d(n)))
+    got_mean = iu.predict.predict_block(model, torch.tensor(vol.astype("float32") / 255.0), c, 16, [0, 1, 2])
+    got_u8, got_lab = iu.predict.predict_volume_array(model, vol, num_classes=c, return_labels=True)
+    d = np.abs(got_mean - want_mean)
+    agree = (got_lab == want_mean.argmax(-1)).mean()
+    du8 = np.abs(got_u8.astype(int) - want_u8.astype(int))
+    print(f"[volume {precision}] N={n}: mean-prob max err {d.max():.4g}  label agreement {agree:.5f}  "
+          f"u8 max diff {du8.max()}  u8 exact {(du8 == 0).mean():.4f}")
+    # bit-exactness of the tail given the engine's own mean probabilities
+    self_u8 = pp.quantise(*pp.blend_single_block(got_mean, pp.gaussian_3d(n)))
+    print(f"[volume {precision}] quantise(own mean) bit-exact: {np.array_equal(self_u8, got_u8)}; "
+          f"labels from own mean exact: {np.array_equal(got_lab, got_mean.argmax(-1).astype(np.uint8))}")
+    for nn in (128, 256):
+        v = torch.from_numpy(synth.noise_volume(nn, 3)).to(dev)
+        out = torch.empty((nn, nn, nn, c), dtype=torch.uint8, device=dev)
+        eng = model.engine()
+        for it in range(2):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            eng.predict_volume(v, axes=(0, 1, 2), window=iu.gaussian_window_1d(nn), out_u8=out)
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            print(f"[volume {precision}] N={nn} iter {it}: {dt*1e3:.1f} ms  {nn**3/dt/1e6:.1f} Mvox/s  "
+                  f"{nn**3*706.85e3/dt/1e12:.1f} TFLOP/s")
+
+
 def main():
+    global ACT
     quick = "--quick" in sys.argv
     print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
-    eng = iu.Engine(0)
-    res = probe_convs(eng, quick)
-    print("conv summary:", {k: v for k, v in res})
-    try:
-        print("tail ok:", probe_tail(eng))
-    except Exception as e:  # noqa: BLE001
-        print("tail EXCEPTION:", repr(e))
-    try:
-        print("network ok:", probe_network(eng))
-    except Exception as e:  # noqa: BLE001
-        import traceback
-        traceback.print_exc()
-        print("network EXCEPTION:", repr(e))
+    for precision in ("fp16", "bf16"):
+        ACT = torch.float16 if precision == "fp16" else torch.bfloat16
+        eng = iu.Engine(0, precision=precision)
+        res = probe_convs(eng, quick)
+        print(f"conv summary {precision}: all ok = {all(v for _, v in res)}", {k: v for k, v in res if not v})
+        if precision == "fp16":
+            try:
+                print("tail ok:", probe_tail(eng))
+            except Exception as e:  # noqa: BLE001
+                print("tail EXCEPTION:", repr(e))
+        for fn in (probe_network, probe_volume):
+            try:
+                fn(precision)
+            except Exception as e:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                print(fn.__name__, "EXCEPTION:", repr(e))
 
 
 if __name__ == "__main__":
