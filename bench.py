@@ -321,7 +321,7 @@ def main():
     ap.add_argument("--edge", type=int, default=None, help="volume edge (default: 512 at 1 GPU, weak-scaled above)")
     ap.add_argument("--classes", type=int, default=2)
     ap.add_argument("--precision", default=os.environ.get("IU_PRECISION", "fp16"), choices=["fp16", "bf16"])
-    ap.add_argument("--cpu-slices", type=int, default=4, help="slices per axis in the CPU baseline sample")
+    ap.add_argument("--cpu-slices", type=int, default=32, help="slices per axis in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

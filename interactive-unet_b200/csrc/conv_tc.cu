@@ -1,16 +1,19 @@
-// Implicit-GEMM convolution on the sm_100a tensor cores.
+// Implicit-GEMM convolution on the sm_100a tensor cores (persistent, warp-specialised).
 //
-//   D[128 pixels, BN channels] = sum over (segment, tap r,s, channel chunk)  A_tap[128, KC] * W_tap[BN, KC]^T
+//   D[128 pixels, BN channels] = sum over (segment, tap r,q, channel chunk)  A_tap[128, KC] * W_tap[BN, KC]^T
 //
-// * activations are NHWC bf16; the A tile of one filter tap is ONE 4-D TMA box (KC channels x tw cols x
+// * activations are NHWC fp16/bf16; the A tile of one filter tap is ONE 4-D TMA box (KC channels x tw cols x
 //   th rows x nb images) fetched at the tap's offset: out-of-bounds coordinates are zero-filled by the
 //   TMA unit, which is the convolution's zero padding; stride-2 convs use the map's element strides.
-// * weights are pre-packed [Cout_pad][K] bf16 (K ordered exactly like the loop above) and fetched as
-//   2-D TMA boxes; both operands land in the 128B/64B/32B-swizzled K-major layout tcgen05.mma reads.
-// * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator; a ring of
-//   mbarrier-guarded stages decouples the TMA producer warp from the MMA warp.
-// * four epilogue warps read the accumulator with tcgen05.ld and fuse folded-BN bias, residual add,
-//   ReLU, bf16 pack, optional nearest-2x upsampled store, or (head conv) softmax + probability store.
+// * weights are pre-packed [Cout_pad][K] (K ordered exactly like the loop above) and fetched as 2-D TMA
+//   boxes; both operands land in the 128B/64B/32B-swizzled K-major layout tcgen05.mma reads.
+// * persistent CTAs (2 per SM) walk the tile list; three pipelines overlap inside a CTA:
+//     TMA producer warp  --(smem stage ring, full/empty mbarriers)-->  MMA thread
+//     MMA thread         --(2 TMEM accumulators, full/empty mbarriers)-->  2 epilogue warp groups
+//   so the loads of tile i+1 and the math of tile i+1 run under the epilogue of tile i.
+//   Small-K layers (KC <= 32) put the 3 taps of a filter row into one stage to cut barrier traffic.
+// * the epilogue reads the accumulator with tcgen05.ld and fuses folded-BN bias, residual add, ReLU,
+//   16-bit pack, optional nearest-2x upsampled store, or (head conv) softmax + probability store.
 //
 // Replaces the cuDNN conv2d / batch_norm / relu / add / cat / upsample_nearest2d / softmax launches
 // issued by `smp.Unet.forward` under `/root/reference/interactive_unet/unet.py:67`.
@@ -19,22 +22,28 @@
 
 namespace iu {
 
+constexpr int kSmemBudget = 100 * 1024;  // per CTA, so that two CTAs fit in the 227 KB of an SM
+
 template <int KC, int BN>
 struct ConvCfg {
   static constexpr int SW = KC * 2;  // bytes per operand row == TMA/UMMA swizzle span
   static constexpr int A_BYTES = kTileM * KC * 2;
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int B_ALLOC = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int STAGE_BYTES = A_BYTES + B_ALLOC;
-  static constexpr int STAGES_RAW = (96 * 1024) / STAGE_BYTES;
+  static constexpr int TAP_BYTES = A_BYTES + B_ALLOC;
+  static constexpr int TPS = KC <= 32 ? 3 : 1;  // taps per pipeline stage (3x3 layers only)
+  static constexpr int STAGE_BYTES = TPS * TAP_BYTES;
+  static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int BAR_BYTES = (2 * STAGES + 2) * 8;
+  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;  // TMEM columns per accumulator
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;      // double-buffered: 64 / 128 / 256 columns
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 1) * 8;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
   static constexpr int CHUNK = BN >= 32 ? 32 : 16;                            // accumulator columns per tcgen05.ld
 };
 
-constexpr int kThreads = 192;  // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: epilogue
+// warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5 / 6-9: epilogue groups 0 / 1
+constexpr int kThreads = 320;
 
 // 16-bit storage helpers: `fp16` selects IEEE half (clamped to the finite range) or bfloat16.
 __device__ __forceinline__ uint32_t pack16(float lo, float hi, int fp16) {
@@ -50,8 +59,139 @@ __device__ __forceinline__ float2 unpack16(uint32_t v, int fp16) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
 
+struct TileCoord {
+  int x0, y0, n0, ntile;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
+  TileCoord t;
+  t.ntile = tile % a.ntiles_n;
+  const int m = tile / a.ntiles_n;
+  t.x0 = (m % a.tiles_x) * a.tw;
+  t.y0 = ((m / a.tiles_x) % a.tiles_y) * a.th;
+  t.n0 = (m / (a.tiles_x * a.tiles_y)) * a.nb;
+  return t;
+}
+
+// One accumulator tile: TMEM -> registers -> fused epilogue -> global memory.
 template <int KC, int BN>
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord& tc, uint32_t taddr, int row) {
+  using Cfg = ConvCfg<KC, BN>;
+  const int per_img = a.th * a.tw;
+  const int n = tc.n0 + row / per_img;
+  const int y = tc.y0 + (row % per_img) / a.tw;
+  const int x = tc.x0 + row % a.tw;
+  const bool valid = (n < a.batch) && (y < a.out_h) && (x < a.out_w);
+
+  if (a.mode == kEpiBf16) {
+    const size_t pix = ((size_t)n * a.out_h + y) * a.out_w + x;
+    const int col0 = tc.ntile * BN;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / Cfg::CHUNK; ++ch) {
+      uint32_t acc[Cfg::CHUNK];
+      if constexpr (Cfg::CHUNK == 32) tmem_ld_32x32(taddr + ch * Cfg::CHUNK, reinterpret_cast<uint32_t(&)[32]>(acc));
+      else tmem_ld_32x16(taddr + ch * Cfg::CHUNK, reinterpret_cast<uint32_t(&)[16]>(acc));
+      tmem_ld_wait();
+      if (valid) {
+        const int c = col0 + ch * Cfg::CHUNK;
+        float v[Cfg::CHUNK];
+#pragma unroll
+        for (int j = 0; j < Cfg::CHUNK; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(a.bias + c + j);
+          v[j] = __uint_as_float(acc[j]) + b.x;
+          v[j + 1] = __uint_as_float(acc[j + 1]) + b.y;
+          v[j + 2] = __uint_as_float(acc[j + 2]) + b.z;
+          v[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
+        }
+        if (a.residual != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.cout + c);
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
+            const uint4 rv = __ldg(rp + j);
+            const float2 r0 = unpack16(rv.x, a.fp16), r1 = unpack16(rv.y, a.fp16);
+            const float2 r2 = unpack16(rv.z, a.fp16), r3 = unpack16(rv.w, a.fp16);
+            v[8 * j + 0] += r0.x; v[8 * j + 1] += r0.y;
+            v[8 * j + 2] += r1.x; v[8 * j + 3] += r1.y;
+            v[8 * j + 4] += r2.x; v[8 * j + 5] += r2.y;
+            v[8 * j + 6] += r3.x; v[8 * j + 7] += r3.y;
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        uint4 pk[Cfg::CHUNK / 8];
+#pragma unroll
+        for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
+          pk[j].x = pack16(v[8 * j + 0], v[8 * j + 1], a.fp16);
+          pk[j].y = pack16(v[8 * j + 2], v[8 * j + 3], a.fp16);
+          pk[j].z = pack16(v[8 * j + 4], v[8 * j + 5], a.fp16);
+          pk[j].w = pack16(v[8 * j + 6], v[8 * j + 7], a.fp16);
+        }
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+        if (!a.up2x) {
+          uint4* dst = reinterpret_cast<uint4*>(outp + pix * a.cout + c);
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK / 8; ++j) dst[j] = pk[j];
+        } else {
+          const int oh = 2 * a.out_h, ow = 2 * a.out_w;
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const size_t up = ((size_t)n * oh + 2 * y + (d >> 1)) * ow + 2 * x + (d & 1);
+            uint4* dst = reinterpret_cast<uint4*>(outp + up * a.cout + c);
+#pragma unroll
+            for (int j = 0; j < Cfg::CHUNK / 8; ++j) dst[j] = pk[j];
+          }
+        }
+      }
+    }
+  } else {
+    // head: logits live in the first num_classes accumulator columns
+    uint32_t acc[16];
+    tmem_ld_32x16(taddr, acc);
+    tmem_ld_wait();
+    if (valid) {
+      const int nc = a.num_classes;
+      float l[16];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        l[j] = (j < nc) ? __uint_as_float(acc[j]) + a.bias[j] : -INFINITY;
+        mx = fmaxf(mx, l[j]);
+      }
+      float sum = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        l[j] = (j < nc) ? expf(l[j] - mx) : 0.0f;
+        sum += l[j];
+      }
+      float* outp = reinterpret_cast<float*>(a.out);
+      if (a.mode == kEpiSoftmaxNHWC) {
+        const size_t rowoff =
+            ((size_t)(y / a.row_block) * a.slice_count + a.slice0 + n) * a.row_block + (y % a.row_block);
+        float* dst = outp + (rowoff * a.out_w + x) * nc;
+        if (nc == 2) {
+          *reinterpret_cast<float2*>(dst) = make_float2(__fdiv_rn(l[0], sum), __fdiv_rn(l[1], sum));
+        } else if (nc == 4) {
+          *reinterpret_cast<float4*>(dst) =
+              make_float4(__fdiv_rn(l[0], sum), __fdiv_rn(l[1], sum), __fdiv_rn(l[2], sum), __fdiv_rn(l[3], sum));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nc) dst[j] = __fdiv_rn(l[j], sum);
+        }
+      } else {
+        const size_t plane = (size_t)a.out_h * a.out_w;
+        float* dst = outp + (size_t)n * nc * plane + (size_t)y * a.out_w + x;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nc) dst[j * plane] = __fdiv_rn(l[j], sum);
+      }
+    }
+  }
+}
+
+template <int KC, int BN>
+__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
   using Cfg = ConvCfg<KC, BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -59,23 +199,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   const uint32_t bar_base = base + Cfg::STAGES * Cfg::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  const uint32_t accum_bar = bar_base + 16u * Cfg::STAGES;
-  const uint32_t tmem_slot = accum_bar + 8u;
+  auto acc_full_bar = [&](int b) { return bar_base + 16u * Cfg::STAGES + 8u * b; };
+  auto acc_empty_bar = [&](int b) { return bar_base + 16u * Cfg::STAGES + 16u + 8u * b; };
+  const uint32_t tmem_slot = bar_base + 16u * Cfg::STAGES + 32u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile -> (image group, row block, column block)
-  const int tile = blockIdx.x;
-  const int tx = tile % a.tiles_x;
-  const int ty = (tile / a.tiles_x) % a.tiles_y;
-  const int tn = tile / (a.tiles_x * a.tiles_y);
-  const int x0 = tx * a.tw, y0 = ty * a.th, n0 = tn * a.nb;
-  const int ntile = blockIdx.y;
-
-  int total_iters = 0;
-  for (int s = 0; s < a.nseg; ++s) total_iters += a.seg[s].ksize * a.seg[s].ksize * (a.seg[s].cin / KC);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.amap[0]);
@@ -85,7 +215,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full_bar(b), 1);
+      mbar_init(acc_empty_bar(b), 4);  // one arrival per warp of the epilogue group that drained it
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -100,23 +233,33 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int it = 0;
-      for (int s = 0; s < a.nseg; ++s) {
-        const ConvSegment sg = a.seg[s];
-        const int chunks = sg.cin / KC;
-        for (int r = 0; r < sg.ksize; ++r) {
-          for (int q = 0; q < sg.ksize; ++q) {
-            for (int cc = 0; cc < chunks; ++cc, ++it) {
-              const int st = it % Cfg::STAGES;
-              const uint32_t ph = (it / Cfg::STAGES) & 1;
-              mbar_wait(empty_bar(st), ph ^ 1u);
-              mbar_arrive_expect_tx(full_bar(st), Cfg::A_BYTES + Cfg::B_BYTES);
-              const uint32_t sa = base + st * Cfg::STAGE_BYTES;
-              tma_load_4d(sa, &a.amap[s], full_bar(st), cc * KC, x0 * sg.stride - sg.pad + q,
-                          y0 * sg.stride - sg.pad + r, n0);
-              tma_load_2d(sa + Cfg::A_BYTES, &a.bmap, full_bar(st), it * KC, ntile * BN);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(a, tile);
+        int kbase = 0;
+        for (int s = 0; s < a.nseg; ++s) {
+          const ConvSegment sg = a.seg[s];
+          const int chunks = sg.cin / KC;
+          const int tps = sg.ksize == 3 ? Cfg::TPS : 1;
+          for (int r = 0; r < sg.ksize; ++r) {
+            for (int q0 = 0; q0 < sg.ksize; q0 += tps) {
+              for (int cc = 0; cc < chunks; ++cc, ++it) {
+                const int st = it % Cfg::STAGES;
+                const uint32_t ph = (it / Cfg::STAGES) & 1;
+                mbar_wait(empty_bar(st), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(st), tps * (Cfg::A_BYTES + Cfg::B_BYTES));
+                for (int j = 0; j < tps; ++j) {
+                  const int q = q0 + j;
+                  const uint32_t sa = base + st * Cfg::STAGE_BYTES + j * Cfg::TAP_BYTES;
+                  tma_load_4d(sa, &a.amap[s], full_bar(st), cc * KC, tc.x0 * sg.stride - sg.pad + q,
+                              tc.y0 * sg.stride - sg.pad + r, tc.n0);
+                  tma_load_2d(sa + Cfg::A_BYTES, &a.bmap, full_bar(st), kbase + (r * sg.ksize + q) * sg.cin + cc * KC,
+                              tc.ntile * BN);
+                }
+              }
             }
           }
+          kbase += sg.ksize * sg.ksize * sg.cin;
         }
       }
     }
@@ -124,135 +267,64 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     // ------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(kTileM, BN, a.fp16);
-      for (int it = 0; it < total_iters; ++it) {
-        const int st = it % Cfg::STAGES;
-        const uint32_t ph = (it / Cfg::STAGES) & 1;
-        mbar_wait(full_bar(st), ph);
-        tc_fence_after();
-        const uint32_t sa = base + st * Cfg::STAGE_BYTES;
-        const uint64_t adesc = umma_smem_desc<Cfg::SW>(sa);
-        const uint64_t bdesc = umma_smem_desc<Cfg::SW>(sa + Cfg::A_BYTES);
-#pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          // advancing K by 16 bf16 = 32 bytes inside the swizzle span = +2 in the (addr >> 4) field
-          umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(empty_bar(st));  // stage reusable once these MMAs have read it
+      int iters_per_tile = 0;
+      for (int s = 0; s < a.nseg; ++s) {
+        const int tps = a.seg[s].ksize == 3 ? Cfg::TPS : 1;
+        iters_per_tile += a.seg[s].ksize * (a.seg[s].ksize / tps) * (a.seg[s].cin / KC);
       }
-      umma_commit(accum_bar);  // accumulator complete
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount & 1u;
+        mbar_wait(acc_empty_bar(buf), ((tcount >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * Cfg::ACC_COLS;
+        uint32_t first = 1;
+        int local = 0;
+        for (int s = 0; s < a.nseg; ++s) {
+          const ConvSegment sg = a.seg[s];
+          const int tps = sg.ksize == 3 ? Cfg::TPS : 1;
+          const int n_it = sg.ksize * (sg.ksize / tps) * (sg.cin / KC);
+          for (int i = 0; i < n_it; ++i, ++it, ++local) {
+            const int st = it % Cfg::STAGES;
+            const uint32_t ph = (it / Cfg::STAGES) & 1;
+            mbar_wait(full_bar(st), ph);
+            tc_fence_after();
+            for (int j = 0; j < tps; ++j) {
+              const uint32_t sa = base + st * Cfg::STAGE_BYTES + j * Cfg::TAP_BYTES;
+              const uint64_t adesc = umma_smem_desc<Cfg::SW>(sa);
+              const uint64_t bdesc = umma_smem_desc<Cfg::SW>(sa + Cfg::A_BYTES);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                // advancing K by 16 elements = 32 bytes inside the swizzle span = +2 in the (addr >> 4) field
+                umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+            umma_commit(empty_bar(st));  // stage reusable once these MMAs have read it
+          }
+        }
+        (void)iters_per_tile;
+        (void)local;
+        umma_commit(acc_full_bar(buf));  // accumulator complete
+      }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue groups (warps 2-5 and 6-9)
+    const int group = (warp - 2) >> 2;
     const int quarter = warp & 3;  // TMEM lanes [32q, 32q+32) are the only ones this warp may read
     const int row = quarter * 32 + lane;
-    const int per_img = a.th * a.tw;
-    const int n = n0 + row / per_img;
-    const int y = y0 + (row % per_img) / a.tw;
-    const int x = x0 + row % a.tw;
-    const bool valid = (n < a.batch) && (y < a.out_h) && (x < a.out_w);
-
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-
-    if (a.mode == kEpiBf16) {
-      const size_t pix = ((size_t)n * a.out_h + y) * a.out_w + x;
-      const int col0 = ntile * BN;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / Cfg::CHUNK; ++ch) {
-        uint32_t acc[Cfg::CHUNK];
-        if constexpr (Cfg::CHUNK == 32) tmem_ld_32x32(taddr + ch * Cfg::CHUNK, reinterpret_cast<uint32_t(&)[32]>(acc));
-        else tmem_ld_32x16(taddr + ch * Cfg::CHUNK, reinterpret_cast<uint32_t(&)[16]>(acc));
-        tmem_ld_wait();
-        if (valid) {
-          const int c = col0 + ch * Cfg::CHUNK;
-          float v[Cfg::CHUNK];
-#pragma unroll
-          for (int j = 0; j < Cfg::CHUNK; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(a.bias + c + j);
-            v[j] = __uint_as_float(acc[j]) + b.x;
-            v[j + 1] = __uint_as_float(acc[j + 1]) + b.y;
-            v[j + 2] = __uint_as_float(acc[j + 2]) + b.z;
-            v[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
-          }
-          if (a.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.cout + c);
-#pragma unroll
-            for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
-              const uint4 rv = __ldg(rp + j);
-              const float2 r0 = unpack16(rv.x, a.fp16), r1 = unpack16(rv.y, a.fp16);
-              const float2 r2 = unpack16(rv.z, a.fp16), r3 = unpack16(rv.w, a.fp16);
-              v[8 * j + 0] += r0.x; v[8 * j + 1] += r0.y;
-              v[8 * j + 2] += r1.x; v[8 * j + 3] += r1.y;
-              v[8 * j + 4] += r2.x; v[8 * j + 5] += r2.y;
-              v[8 * j + 6] += r3.x; v[8 * j + 7] += r3.y;
-            }
-          }
-          if (a.relu) {
-#pragma unroll
-            for (int j = 0; j < Cfg::CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
-          }
-          uint4 pk[Cfg::CHUNK / 8];
-#pragma unroll
-          for (int j = 0; j < Cfg::CHUNK / 8; ++j) {
-            pk[j].x = pack16(v[8 * j + 0], v[8 * j + 1], a.fp16);
-            pk[j].y = pack16(v[8 * j + 2], v[8 * j + 3], a.fp16);
-            pk[j].z = pack16(v[8 * j + 4], v[8 * j + 5], a.fp16);
-            pk[j].w = pack16(v[8 * j + 6], v[8 * j + 7], a.fp16);
-          }
-          __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
-          if (!a.up2x) {
-            uint4* dst = reinterpret_cast<uint4*>(outp + pix * a.cout + c);
-#pragma unroll
-            for (int j = 0; j < Cfg::CHUNK / 8; ++j) dst[j] = pk[j];
-          } else {
-            const int oh = 2 * a.out_h, ow = 2 * a.out_w;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-              const size_t up = ((size_t)n * oh + 2 * y + (d >> 1)) * ow + 2 * x + (d & 1);
-              uint4* dst = reinterpret_cast<uint4*>(outp + up * a.cout + c);
-#pragma unroll
-              for (int j = 0; j < Cfg::CHUNK / 8; ++j) dst[j] = pk[j];
-            }
-          }
-        }
-      }
-    } else {
-      // head: logits live in the first num_classes accumulator columns
-      uint32_t acc[16];
-      tmem_ld_32x16(taddr, acc);
-      tmem_ld_wait();
-      if (valid) {
-        const int nc = a.num_classes;
-        float l[16];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          l[j] = (j < nc) ? __uint_as_float(acc[j]) + a.bias[j] : -INFINITY;
-          mx = fmaxf(mx, l[j]);
-        }
-        float sum = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          l[j] = (j < nc) ? expf(l[j] - mx) : 0.0f;
-          sum += l[j];
-        }
-        float* outp = reinterpret_cast<float*>(a.out);
-        if (a.mode == kEpiSoftmaxNHWC) {
-          const size_t rowoff =
-              ((size_t)(y / a.row_block) * a.slice_count + a.slice0 + n) * a.row_block + (y % a.row_block);
-          float* dst = outp + (rowoff * a.out_w + x) * nc;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nc) dst[j] = __fdiv_rn(l[j], sum);
-        } else {
-          const size_t plane = (size_t)a.out_h * a.out_w;
-          float* dst = outp + (size_t)n * nc * plane + (size_t)y * a.out_w + x;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nc) dst[j * plane] = __fdiv_rn(l[j], sum);
-        }
-      }
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      if ((int)buf != group) continue;
+      const TileCoord tc = decode_tile(a, tile);
+      mbar_wait(acc_full_bar(buf), (tcount >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      epilogue_tile<KC, BN>(a, tc, taddr, row);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty_bar(buf));
     }
   }
 
@@ -262,22 +334,27 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 }
 
 template <int KC, int BN>
-static cudaError_t launch_one(const ConvArgs& args, cudaStream_t stream) {
+static cudaError_t launch_one(const ConvArgs& args_in, cudaStream_t stream) {
   using Cfg = ConvCfg<KC, BN>;
-  static bool configured = false;  // per kernel instantiation; the attribute is per device, set again on any change
-  static int configured_dev = -1;
+  static int configured_dev = -1;  // per kernel instantiation; the attribute is per device
+  static int num_sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!configured || configured_dev != dev) {
+  if (configured_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     configured_dev = dev;
   }
+  for (int s = 0; s < args_in.nseg; ++s)
+    if (Cfg::TPS != 1 && args_in.seg[s].ksize != 3 && args_in.seg[s].ksize != 1) return cudaErrorInvalidValue;
+  ConvArgs args = args_in;
   const int mtiles = args.tiles_x * args.tiles_y * ((args.batch + args.nb - 1) / args.nb);
   const int cout_pad = (args.mode == kEpiBf16) ? args.cout : BN;
-  dim3 grid(mtiles, cout_pad / BN, 1);
+  args.ntiles_n = cout_pad / BN;
+  args.total_tiles = mtiles * args.ntiles_n;
+  const int grid = args.total_tiles < 2 * num_sms ? args.total_tiles : 2 * num_sms;
   conv_tc_kernel<KC, BN><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(args);
   return cudaGetLastError();
 }

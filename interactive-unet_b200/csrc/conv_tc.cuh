@@ -36,6 +36,7 @@ struct alignas(64) ConvArgs {
   int cout;                 // real output channels (bf16 mode: multiple of BN)
   int tw, th, nb;           // tile = nb images x th rows x tw cols = 128 pixels
   int tiles_x, tiles_y;
+  int ntiles_n, total_tiles;  // filled by launch_conv_tc: Cout tiles and (pixel tiles x Cout tiles)
   const float* bias;              // [Cout_pad] folded BatchNorm shift (or conv bias)
   const __nv_bfloat16* residual;  // optional, same geometry as the output
   void* out;
