@@ -140,6 +140,9 @@ int64_t iu_engine_launch_count(const iu_engine* e);
 #define IU_PROF_CONV 3   /* tcgen05 implicit-GEMM convs (incl. head)   */
 #define IU_PROF_REDUCE 4 /* K4 accumulate / blend / quantise / argmax  */
 #define IU_PROF_CLASSES 5
+/* Development aid (engines created with env IU_CONV_DEBUG=1): 16 clock-cycle counters per conv layer written
+ * by the halo kernel's warp roles (layout in csrc/conv_tc.cuh, ConvArgs::debug); n_values <= 1024. */
+int iu_engine_debug_counters(iu_engine* e, unsigned long long* out, int n_values, int reset);
 int iu_engine_profile(iu_engine* e, int enable);
 int iu_engine_profile_read(iu_engine* e, double* ms, int64_t* count, int reset);
 

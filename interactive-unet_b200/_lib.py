@@ -49,6 +49,7 @@ SIGNATURES = {
                                        _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,
                                        _c.c_int, _c.c_int, _c.c_void_p]),
     "iu_engine_launch_count": (_c.c_int64, [_engine_p]),
+    "iu_engine_debug_counters": (_c.c_int, [_engine_p, _c.POINTER(_c.c_uint64), _c.c_int, _c.c_int]),
     "iu_engine_profile": (_c.c_int, [_engine_p, _c.c_int]),
     "iu_engine_profile_read": (_c.c_int, [_engine_p, _c.POINTER(_c.c_double), _c.POINTER(_c.c_int64), _c.c_int]),
 }

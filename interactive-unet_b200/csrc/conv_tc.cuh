@@ -31,6 +31,7 @@ struct alignas(64) ConvArgs {
   CUtensorMap amap[2];  // 4-D maps (C, W, H, N) over the segment sources, box = (KC, tw*stride, th*stride, nb)
   CUtensorMap bmap;     // 2-D map (K, Cout_pad) over the packed weights, box = (KC, BN)
   ConvSegment seg[2];
+  const __nv_bfloat16* src_ptr[2];  // raw pointers of the segment sources (halo kernel: cp.async gathers)
   int nseg;
   int batch, out_h, out_w;  // output geometry (before the optional 2x upsample)
   int cout;                 // real output channels (bf16 mode: multiple of BN)
@@ -48,6 +49,10 @@ struct alignas(64) ConvArgs {
   // softmax NHWC addressing (lets one buffer be laid out destination-major for the multi-GPU exchange):
   //   off(n, y, x) = (((y / row_block) * slice_count + slice0 + n) * row_block + y % row_block) * out_w + x
   int slice0, slice_count, row_block;
+  // optional (nullptr = off): 16 cycle counters per layer filled by the halo kernel's roles (development aid)
+  //   [0] MMA wait accumulator  [1] MMA wait A  [2] MMA wait B  [3] MMA total  [4] gather wait empty
+  //   [5] gather issue  [6] gather wait landing  [7] gather total  [8] epilogue wait  [9] epilogue body  [10] CTAs
+  unsigned long long* debug;
 };
 
 // Launch on `stream`; KC = min(64, cin), BN = min(128, Cout_pad).  Returns cudaGetLastError().
@@ -55,5 +60,12 @@ cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t st
 
 // Shared memory the kernel variant needs (for occupancy planning / tests).
 int conv_tc_smem_bytes(int kc, int bn);
+
+// Halo-tile variant (conv_halo.cu) for stride-1 3x3 convs on images of at least 16x16: every CTA tile is
+// a 16x16 output block whose 18x18 input halo is gathered ONCE per channel chunk into a planar layout,
+// the nine taps being shifted views of it.  Same ConvArgs; tiling fields are overwritten (16x16, nb=1).
+constexpr int kHaloTile = 16;
+bool conv_halo_applicable(const ConvArgs& args);
+cudaError_t launch_conv_halo(const ConvArgs& args, int kc, int bn, cudaStream_t stream);
 
 }  // namespace iu

@@ -100,6 +100,8 @@ struct iu_engine {
   bool loaded = false;
   int max_batch = 0;
   int fp16 = 1;  // 16-bit storage format of weights / activations: 1 = IEEE fp16 (default), 0 = bf16
+  int conv_variant = 0;  // 0 = auto (halo kernel where applicable), 1 = per-tap TMA kernel only (env IU_CONV_VARIANT)
+  unsigned long long* d_debug = nullptr;  // env IU_CONV_DEBUG=1: 16 cycle counters per conv layer (development aid)
   int64_t launches = 0;
   size_t weight_bytes = 0;
 
@@ -550,6 +552,7 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
     a.nseg = L.nseg;
     for (int s = 0; s < L.nseg; ++s) {
       a.seg[s] = L.seg[s];
+      a.src_ptr[s] = p.bufs[L.src[s]];
       const TensorSpec& ts = e->tensors[L.src[s]];
       const int st = L.seg[s].stride;
       int rc = encode_act_map(e, &a.amap[s], p.bufs[L.src[s]], ts.c, w / ts.hdiv, h / ts.hdiv, bp, L.kc, a.tw * st,
@@ -576,6 +579,7 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
     a.slice0 = 0;
     a.slice_count = batch;
     a.row_block = h;
+    a.debug = (e->d_debug && i < 64) ? e->d_debug + 16 * i : nullptr;
   }
   p.batch = batch;
   p.batch_pad = bp;
@@ -590,6 +594,17 @@ int auto_batch(const iu_engine* e, int h, int w, int want) {
   int nb = (int)std::max(1.0, std::min(128.0, std::floor(b)));
   if (e->max_batch > 0) nb = std::min(nb, e->max_batch);
   return std::max(1, std::min(nb, want));
+}
+
+// Kernel choice per conv: the halo-tile kernel for stride-1 3x3 layers on images >= 16x16, else the per-tap TMA kernel.
+// Measured on B200 (profiles/r01_*): the halo kernel wins 2-4x on the <= 32-channel layers (weights resident,
+// activations fetched once instead of nine times in 32/64-byte rows); on 64-channel chunks both kernels are
+// bounded by the tensor pipe's per-MMA operand fetch and the per-tap kernel (2 CTAs/SM) is slightly ahead.
+// IU_CONV_VARIANT: 0 = that rule, 1 = per-tap kernel only, 2 = halo kernel wherever it applies.
+cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
+  const bool halo = e->conv_variant == 2 || (e->conv_variant == 0 && kc <= 32);
+  if (halo && conv_halo_applicable(a)) return launch_conv_halo(a, kc, bn, e->stream);
+  return launch_conv_tc(a, kc, bn, e->stream);
 }
 
 // Run the network on the `batch` slices already in plan.x_in; the head writes according to (mode, out, ...).
@@ -614,7 +629,7 @@ int run_network(iu_engine* e, int batch, int head_mode, float* head_out, int sli
       a.row_block = row_block;
     }
     prof_begin(e, IU_PROF_CONV);
-    cudaError_t ce = launch_conv_tc(a, L.kc, L.bn, e->stream);
+    cudaError_t ce = launch_conv(e, a, L.kc, L.bn);
     prof_end(e);
     if (ce != cudaSuccess) return e->cuda_fail(ce, ("launch " + L.name).c_str());
     e->launches += 1;
@@ -699,6 +714,11 @@ int iu_engine_create(int device, iu_engine** out) {
     return IU_ERR_CUDA;
   }
   e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* v = getenv("IU_CONV_VARIANT")) e->conv_variant = atoi(v);
+  if (const char* v = getenv("IU_CONV_DEBUG")) {
+    if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(e->d_debug, 0, 64 * 16 * sizeof(unsigned long long));
+  }
   *out = e;
   return IU_OK;
 }
@@ -711,6 +731,7 @@ void iu_engine_destroy(iu_engine* e) {
   free_weights(e);
   for (auto& s : e->scratch)
     if (s.ptr) cudaFree(s.ptr);
+  if (e->d_debug) cudaFree(e->d_debug);
   for (auto& s : e->spans) {
     cudaEventDestroy(s.begin);
     cudaEventDestroy(s.end);
@@ -781,6 +802,17 @@ int64_t iu_engine_workspace_bytes(iu_engine* e, int batch, int h, int w) {
 }
 
 int64_t iu_engine_launch_count(const iu_engine* e) { return e ? e->launches : 0; }
+
+int iu_engine_debug_counters(iu_engine* e, unsigned long long* out, int n_values, int reset) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!e->d_debug) return e->fail(IU_ERR_STATE, "debug counters are off (set IU_CONV_DEBUG=1 before creating the engine)");
+  if (!out || n_values < 1 || n_values > 64 * 16) return e->fail(IU_ERR_INVALID, "debug_counters: bad arguments");
+  IU_CUDA(e, cudaStreamSynchronize(e->stream));
+  IU_CUDA(e, cudaMemcpy(out, e->d_debug, (size_t)n_values * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) IU_CUDA(e, cudaMemset(e->d_debug, 0, 64 * 16 * sizeof(unsigned long long)));
+  return IU_OK;
+}
 
 int iu_engine_profile(iu_engine* e, int enable) {
   int rc;
@@ -1076,7 +1108,9 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
     a.fp16 = e->fp16;
     a.up2x = up2x;
     a.mode = kEpiBf16;
-    cudaError_t ce = launch_conv_tc(a, kc, bn, e->stream);
+    a.src_ptr[0] = (const __nv_bfloat16*)src0;
+    a.src_ptr[1] = (const __nv_bfloat16*)src1;
+    cudaError_t ce = launch_conv(e, a, kc, bn);
     e->launches += 1;
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     if (ce != cudaSuccess) rc = e->cuda_fail(ce, "conv_test");

@@ -141,6 +141,12 @@ class Engine:
         self._check(self._lib.iu_engine_profile_read(self._h, ms, cnt, int(bool(reset))))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROF_CLASSES)}
 
+    def debug_counters(self, n_layers=48, reset=True):
+        """Per-layer role cycle counters of the halo kernel (needs env IU_CONV_DEBUG=1 at engine creation)."""
+        buf = (ctypes.c_uint64 * (16 * n_layers))()
+        self._check(self._lib.iu_engine_debug_counters(self._h, buf, 16 * n_layers, int(bool(reset))))
+        return np.array(buf, dtype=np.uint64).reshape(n_layers, 16)
+
     def stream_handle(self):
         return int(self._lib.iu_engine_stream(self._h) or 0)
 

@@ -72,11 +72,15 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", ["pertap", "halo"])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv_matches_fp32_reference(dev, iu, case, precision):
+def test_conv_matches_fp32_reference(dev, iu, case, precision, variant, monkeypatch):
+    """Both tensor-core kernels (per-tap TMA boxes; halo tile with shifted no-swizzle descriptors), forced via
+    IU_CONV_VARIANT; the halo variant falls back to the per-tap kernel where it does not apply."""
     _, b, h, w, c0, c1, cout, k, stride, residual, relu, up2x = case
     act = torch.float16 if precision == "fp16" else torch.bfloat16
+    monkeypatch.setenv("IU_CONV_VARIANT", "1" if variant == "pertap" else "2")
     eng = iu.Engine(0, precision=precision)
     g = torch.Generator().manual_seed(hash(case[0]) % 1000)
     src0 = torch.randn(b, h, w, c0, generator=g).to(dev).to(act)
