@@ -1,4 +1,4 @@
-// HBM-bound kernels around the conv stack: slice gather (K1), stem conv, max-pool, and the fused
+// HBM-bound kernels around the conv stack: slice gather (K1), max-pool, and the fused
 // cross-axis reduce / quantise / argmax (K4).  All arithmetic that the reference does on the host
 // in fp32 (`predict.py:110,237,244-245,255`) is reproduced with round-to-nearest intrinsics so that
 // no FMA contraction or reciprocal substitution can change a bit.
@@ -81,80 +81,6 @@ cudaError_t launch_gather_slices(const void* vol, int vol_is_f32, int n, int axi
     else
       gather_cols_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)vol, n, start, count, out);
   }
-  return cudaGetLastError();
-}
-
-// =========================================================================== stem conv 7x7/s2 + BN + ReLU
-constexpr int kStemTile = 16;                        // output pixels per block edge
-constexpr int kStemPatch = 2 * kStemTile + 5;        // 37 input pixels per block edge
-constexpr int kStemPitch = kStemPatch + 1;
-
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, int h, int w,
-                                                   const float* __restrict__ wt, const float* __restrict__ bias,
-                                                   __nv_bfloat16* __restrict__ out, int fp16) {
-  __shared__ float patch[kStemPatch][kStemPitch];
-  __shared__ float4 wsm[49 * 16];
-  const int n = blockIdx.z;
-  const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
-  const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
-  const float* img = x + (size_t)n * h * w;
-  for (int i = threadIdx.x; i < kStemPatch * kStemPatch; i += 256) {
-    const int py = i / kStemPatch, px = i % kStemPatch;
-    const int iy = iy0 + py, ix = ix0 + px;
-    patch[py][px] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(img + (size_t)iy * w + ix) : 0.0f;
-  }
-  for (int i = threadIdx.x; i < 49 * 16; i += 256) wsm[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
-  __syncthreads();
-
-  const int txl = threadIdx.x & 15, tyl = threadIdx.x >> 4;
-  float acc[64];
-#pragma unroll
-  for (int c = 0; c < 64; ++c) acc[c] = 0.0f;
-#pragma unroll 1
-  for (int r = 0; r < 7; ++r) {
-#pragma unroll
-    for (int s = 0; s < 7; ++s) {
-      const float v = patch[2 * tyl + r][2 * txl + s];
-      const float4* wp = &wsm[(r * 7 + s) * 16];
-#pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        const float4 wv = wp[c4];
-        acc[4 * c4 + 0] = fmaf(v, wv.x, acc[4 * c4 + 0]);
-        acc[4 * c4 + 1] = fmaf(v, wv.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(v, wv.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(v, wv.w, acc[4 * c4 + 3]);
-      }
-    }
-  }
-  const int oh = h / 2, ow = w / 2;
-  const int oy = oy0 + tyl, ox = ox0 + txl;
-  if (oy < oh && ox < ow) {
-    uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)n * oh + oy) * ow + ox) * 64);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = 8 * j + 2 * k;
-        const float a0 = fmaxf(acc[c] + __ldg(bias + c), 0.0f);
-        const float a1 = fmaxf(acc[c + 1] + __ldg(bias + c + 1), 0.0f);
-        if (fp16) {
-          __half2 p = __floats2half2_rn(fminf(a0, 65504.0f), fminf(a1, 65504.0f));
-          pk[k] = *reinterpret_cast<uint32_t*>(&p);
-        } else {
-          __nv_bfloat162 p = __floats2bfloat162_rn(a0, a1);
-          pk[k] = *reinterpret_cast<uint32_t*>(&p);
-        }
-      }
-      dst[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    }
-  }
-}
-
-cudaError_t launch_stem(const float* x, int batch, int h, int w, const float* w_tap_major, const float* bias,
-                        __nv_bfloat16* out, int fp16, cudaStream_t stream) {
-  dim3 grid((w / 2 + kStemTile - 1) / kStemTile, (h / 2 + kStemTile - 1) / kStemTile, batch);
-  stem_kernel<<<grid, 256, 0, stream>>>(x, h, w, w_tap_major, bias, out, fp16);
   return cudaGetLastError();
 }
 

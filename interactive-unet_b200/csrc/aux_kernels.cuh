@@ -13,11 +13,6 @@ namespace iu {
 cudaError_t launch_gather_slices(const void* vol, int vol_is_f32, int n, int axis, int start, int count, float* out,
                                  cudaStream_t stream);
 
-// Stem: 7x7 stride-2 pad-3 conv 1->64 with folded BatchNorm + ReLU, fp32 in, 16-bit (fp16|bf16) NHWC out.
-//   w_tap_major: [49][64] fp32, bias: [64] fp32.
-cudaError_t launch_stem(const float* x, int batch, int h, int w, const float* w_tap_major, const float* bias,
-                        __nv_bfloat16* out, int fp16, cudaStream_t stream);
-
 // 3x3 stride-2 pad-1 max pool on NHWC 16-bit NON-NEGATIVE values (post-ReLU): for those the unsigned
 // integer order of the bit patterns equals the numeric order in both fp16 and bf16.
 cudaError_t launch_maxpool(const __nv_bfloat16* in, int batch, int h, int w, int c, __nv_bfloat16* out,

@@ -21,12 +21,79 @@ __device__ __forceinline__ float2 unpack16(uint32_t v, int fp16) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
 
-// `taddr`: TMEM address of this warp's 32 lanes at the accumulator's first column.
-// Must be called by all 32 lanes of the warp (tcgen05.ld is warp-collective); `valid` masks the stores.
+// Address of class 0 of pixel (n, y, x) in the head's output and the stride between classes.
+__device__ __forceinline__ void softmax_dst(const ConvArgs& a, int n, int y, int x, float** dst, size_t* cstride) {
+  float* outp = reinterpret_cast<float*>(a.out);
+  if (a.mode == kEpiSoftmaxNHWC) {
+    const size_t rowoff = ((size_t)(y / a.row_block) * a.slice_count + a.slice0 + n) * a.row_block + (y % a.row_block);
+    *dst = outp + (rowoff * a.out_w + x) * a.num_classes;
+    *cstride = 1;
+  } else {
+    const size_t plane = (size_t)a.out_h * a.out_w;
+    *dst = outp + (size_t)n * a.num_classes * plane + (size_t)y * a.out_w + x;
+    *cstride = plane;
+  }
+}
+
+// softmax over NC logits (`unet.py:63,67`): exp(l - max) / sum, IEEE division; vector store when NHWC.
+template <int NC>
+__device__ __forceinline__ void softmax_store(const ConvArgs& a, const float* bias, const uint32_t (&acc)[4], int n,
+                                              int y, int x) {
+  float l[NC];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    l[j] = __uint_as_float(acc[j]) + bias[j];
+    mx = fmaxf(mx, l[j]);
+  }
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    l[j] = expf(l[j] - mx);
+    sum += l[j];
+  }
+#pragma unroll
+  for (int j = 0; j < NC; ++j) l[j] = __fdiv_rn(l[j], sum);
+  float* dst;
+  size_t cstride;
+  softmax_dst(a, n, y, x, &dst, &cstride);
+  if (a.mode == kEpiSoftmaxNHWC && NC == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(l[0], l[NC > 1 ? 1 : 0]);
+  } else if (a.mode == kEpiSoftmaxNHWC && NC == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(l[0], l[NC > 1 ? 1 : 0], l[NC > 2 ? 2 : 0], l[NC > 3 ? 3 : 0]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) dst[j * cstride] = l[j];
+  }
+}
+
+// Residual operand of one pixel: CHUNK channels (CHUNK / 8 16-byte vectors) starting at channel `c`.
+template <int BN>
+struct EpiCfg {
+  static constexpr int CHUNK = BN >= 32 ? 32 : 16;  // accumulator columns per tcgen05.ld
+  static constexpr int RV = CHUNK / 8;               // 16-byte vectors per chunk of 16-bit channels
+};
+template <int BN>
+__device__ __forceinline__ void residual_load(const ConvArgs& a, size_t pix, int c, uint4 (&r)[EpiCfg<BN>::RV]) {
+  const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.cout + c);
+#pragma unroll
+  for (int j = 0; j < EpiCfg<BN>::RV; ++j) r[j] = __ldg(rp + j);
+}
+// Issued BEFORE waiting for the accumulator so that the residual's memory latency hides under the MMAs.
+template <int BN>
+__device__ __forceinline__ void residual_prefetch(const ConvArgs& a, int ntile, int n, int y, int x, bool valid,
+                                                  uint4 (&r)[EpiCfg<BN>::RV]) {
+  if (a.mode == kEpiBf16 && a.residual != nullptr && valid)
+    residual_load<BN>(a, ((size_t)n * a.out_h + y) * a.out_w + x, ntile * BN, r);
+}
+
+// `taddr`: TMEM address of this warp's 32 lanes at the accumulator's first column; `res`: residual of the first
+// chunk (residual_prefetch).  Must be called by all 32 lanes of the warp (tcgen05.ld is warp-collective);
+// `valid` masks the loads / stores.
 template <int BN>
 __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* bias, int ntile, uint32_t taddr, int n, int y, int x,
-                                               bool valid) {
-  constexpr int CHUNK = BN >= 32 ? 32 : 16;  // accumulator columns per tcgen05.ld
+                                               bool valid, uint4 (&res)[EpiCfg<BN>::RV]) {
+  constexpr int CHUNK = EpiCfg<BN>::CHUNK;
   if (a.mode == kEpiBf16) {
     const size_t pix = ((size_t)n * a.out_h + y) * a.out_w + x;
     const int col0 = ntile * BN;
@@ -48,10 +115,9 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* b
           v[j + 3] = __uint_as_float(acc[j + 3]) + b.w;
         }
         if (a.residual != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * a.cout + c);
 #pragma unroll
           for (int j = 0; j < CHUNK / 8; ++j) {
-            const uint4 rv = __ldg(rp + j);
+            const uint4 rv = res[j];
             const float2 r0 = unpack16(rv.x, a.fp16), r1 = unpack16(rv.y, a.fp16);
             const float2 r2 = unpack16(rv.z, a.fp16), r3 = unpack16(rv.w, a.fp16);
             v[8 * j + 0] += r0.x; v[8 * j + 1] += r0.y;
@@ -59,6 +125,7 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* b
             v[8 * j + 4] += r2.x; v[8 * j + 5] += r2.y;
             v[8 * j + 6] += r3.x; v[8 * j + 7] += r3.y;
           }
+          if (ch + 1 < BN / CHUNK) residual_load<BN>(a, pix, c + CHUNK, res);  // in flight during this chunk's stores
         }
         if (a.relu) {
 #pragma unroll
@@ -90,46 +157,45 @@ __device__ __forceinline__ void epilogue_pixel(const ConvArgs& a, const float* b
       }
     }
   } else {
-    // head: logits live in the first num_classes accumulator columns
-    uint32_t acc[16];
-    tmem_ld_32x16(taddr, acc);
-    tmem_ld_wait();
-    if (valid) {
-      const int nc = a.num_classes;
-      float l[16];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        l[j] = (j < nc) ? __uint_as_float(acc[j]) + bias[j] : -INFINITY;
-        mx = fmaxf(mx, l[j]);
+    // head: logits live in the first num_classes accumulator columns.  The class count picks a fixed-size
+    // path (2 and 4 are the reference's common settings) so that only num_classes exponentials are evaluated.
+    const int nc = a.num_classes;
+    if (nc <= 4) {
+      uint32_t acc[4];
+      tmem_ld_32x4(taddr, acc);
+      tmem_ld_wait();
+      if (valid) {
+        if (nc == 2) softmax_store<2>(a, bias, acc, n, y, x);
+        else if (nc == 4) softmax_store<4>(a, bias, acc, n, y, x);
+        else if (nc == 3) softmax_store<3>(a, bias, acc, n, y, x);
+        else softmax_store<1>(a, bias, acc, n, y, x);
       }
-      float sum = 0.0f;
+    } else {
+      uint32_t acc[16];
+      tmem_ld_32x16(taddr, acc);
+      tmem_ld_wait();
+      if (valid) {
+        float l[16];
+        float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        l[j] = (j < nc) ? expf(l[j] - mx) : 0.0f;
-        sum += l[j];
-      }
-      float* outp = reinterpret_cast<float*>(a.out);
-      if (a.mode == kEpiSoftmaxNHWC) {
-        const size_t rowoff =
-            ((size_t)(y / a.row_block) * a.slice_count + a.slice0 + n) * a.row_block + (y % a.row_block);
-        float* dst = outp + (rowoff * a.out_w + x) * nc;
-        if (nc == 2) {
-          *reinterpret_cast<float2*>(dst) = make_float2(__fdiv_rn(l[0], sum), __fdiv_rn(l[1], sum));
-        } else if (nc == 4) {
-          *reinterpret_cast<float4*>(dst) =
-              make_float4(__fdiv_rn(l[0], sum), __fdiv_rn(l[1], sum), __fdiv_rn(l[2], sum), __fdiv_rn(l[3], sum));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nc) dst[j] = __fdiv_rn(l[j], sum);
+        for (int j = 0; j < 16; ++j) {
+          l[j] = (j < nc) ? __uint_as_float(acc[j]) + bias[j] : -INFINITY;
+          mx = fmaxf(mx, l[j]);
         }
-      } else {
-        const size_t plane = (size_t)a.out_h * a.out_w;
-        float* dst = outp + (size_t)n * nc * plane + (size_t)y * a.out_w + x;
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j < nc) {
+            l[j] = expf(l[j] - mx);
+            sum += l[j];
+          }
+        }
+        float* dst;
+        size_t cstride;
+        softmax_dst(a, n, y, x, &dst, &cstride);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (j < nc) dst[j * plane] = __fdiv_rn(l[j], sum);
+          if (j < nc) dst[j * cstride] = __fdiv_rn(l[j], sum);
       }
     }
   }

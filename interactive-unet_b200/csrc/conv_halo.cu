@@ -12,7 +12,7 @@
 //     per weight tile, 4 TMEM accumulators (2 tiles x double buffer);
 //   * weights: streamed per tap through a TMA ring (wide layers), or loaded ONCE per CTA and kept resident
 //     (layers with <= 32 input channels: their whole [Cout x 9*Cin] matrix is a few KB);
-//   * warp roles: 1 weight-TMA thread, 1 MMA thread, 8 epilogue warps (one group per M tile), 4 gather warps;
+//   * warp roles: 1 weight-TMA thread, 1 MMA thread, 8 epilogue warps (one group per M tile), 4 or 8 gather warps;
 //     waits are polled by one lane per warp; the folded-BN bias vector lives in shared memory.
 // Everything after the MMA (bias / residual / ReLU / upsampled store / softmax head) is conv_epilogue.cuh.
 #include "conv_epilogue.cuh"
@@ -24,15 +24,18 @@ namespace iu {
 constexpr int kHaloW = kHaloTile + 2;                // 18 halo pixels per edge
 constexpr int kHaloPix = kHaloW * kHaloW;            // 324
 constexpr int kPlaneStride = kHaloPix * 16 + 16;     // 5200 B; (stride / 16) is odd -> conflict-free cp.async stores
-constexpr int kHaloThreads = 448;                    // 14 warps, see roles above
-constexpr int kGatherThreads = 128;
+constexpr int kHaloBaseThreads = 320;                // warps 0-9: weight producer, MMA issuer, 8 epilogue warps
 constexpr int kHaloSmemBudget = 200 * 1024;
 constexpr int kMaxBias = 512;
 
-template <int KC, int BN>
+// STAT: the layer's whole weight matrix stays resident in shared memory (loaded once per CTA) -- every layer with
+// <= 32-channel chunks, and the 64-channel layers whose [BN x K] matrix fits beside the activation ring
+// (64 -> 64 and 64+64 -> 32: 72 KB).  Otherwise weights stream per (chunk, tap) through a TMA ring.
+template <int KC, int BN, bool STAT>
 struct HaloCfg {
-  static constexpr bool STATIONARY = KC <= 32;  // whole weight matrix resident in shared memory
-  static constexpr int CTAS = STATIONARY ? 2 : 1;
+  static constexpr int CTAS = KC <= 32 ? 2 : 1;
+  static constexpr int GATHER_THREADS = KC <= 32 ? 128 : 256;  // 4 gather warps per CTA (two CTAs per SM) or 8
+  static constexpr int THREADS = kHaloBaseThreads + GATHER_THREADS;
   static constexpr int PLANES = KC / 8;
   static constexpr int A_STAGE = (PLANES * kPlaneStride + 1023) / 1024 * 1024;
   static constexpr int A_STAGES = KC == 64 ? 3 : 4;
@@ -40,7 +43,8 @@ struct HaloCfg {
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int B_ALLOC = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int B_RAW = (kHaloSmemBudget - A_STAGES * A_STAGE) / B_ALLOC;
-  static constexpr int B_STAGES = STATIONARY ? 9 : (B_RAW > 9 ? 9 : (B_RAW < 3 ? 3 : B_RAW));
+  // STAT: number of resident [BN x KC] weight tiles; streaming: depth of the weight ring
+  static constexpr int B_STAGES = STAT ? (KC <= 32 ? 9 : (B_RAW > 18 ? 18 : B_RAW)) : (B_RAW > 9 ? 9 : (B_RAW < 3 ? 3 : B_RAW));
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
   static constexpr int TMEM_COLS = 4 * ACC_COLS;  // 2 M tiles x 2 buffers: 128 / 128 / 256 / 512 columns
   static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4;
@@ -69,10 +73,11 @@ __device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity, int lan
   __syncwarp();
 }
 
-template <int KC, int BN>
-__global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
+template <int KC, int BN, bool STAT>
+__global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN, STAT>::CTAS)
     conv_halo_kernel(const __grid_constant__ ConvArgs a) {
-  using Cfg = HaloCfg<KC, BN>;
+  using Cfg = HaloCfg<KC, BN, STAT>;
+  const long long t_cta = (a.debug != nullptr && threadIdx.x == 0) ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -94,11 +99,11 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < a.ntiles_n * BN; i += kHaloThreads) bias_s[i] = a.bias[i];
+  for (int i = threadIdx.x; i < a.ntiles_n * BN; i += Cfg::THREADS) bias_s[i] = a.bias[i];
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.bmap);
     for (int s = 0; s < Cfg::A_STAGES; ++s) {
-      mbar_init(a_full(s), kGatherThreads / 32);  // one arrival per gather warp (after every lane fenced its copies)
+      mbar_init(a_full(s), Cfg::GATHER_THREADS / 32);  // one arrival per gather warp (after every lane fenced its copies)
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < Cfg::B_STAGES; ++s) {
@@ -124,12 +129,20 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
     // ------------------------------------------------------------ weight producer (TMA)
     // The warp stays converged and issues under elect.sync: the compiler then knows exactly one lane is
     // active and emits straight-line UTMALDG instead of a per-lane election loop.
-    if constexpr (Cfg::STATIONARY) {
-      // single source, single channel chunk, single Cout tile: 9 tap tiles, loaded once for all pixel tiles
+    if constexpr (STAT) {
+      // single Cout tile: every (segment, chunk, tap) weight tile is loaded once, for all pixel tiles of this CTA
       if (elect_one()) {
-        mbar_arrive_expect_tx(b_full(0), 9 * Cfg::B_BYTES);
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) tma_load_2d(b_base + tap * Cfg::B_ALLOC, &a.bmap, b_full(0), tap * KC, 0);
+        int ntl = 0;
+        for (int s = 0; s < a.nseg; ++s) ntl += 9 * (a.seg[s].cin / KC);
+        mbar_arrive_expect_tx(b_full(0), ntl * Cfg::B_BYTES);
+        int kbase = 0, idx = 0;
+        for (int s = 0; s < a.nseg; ++s) {
+          const int cin = a.seg[s].cin;
+          for (int cc = 0; cc < cin / KC; ++cc)
+            for (int tap = 0; tap < 9; ++tap, ++idx)
+              tma_load_2d(b_base + idx * Cfg::B_ALLOC, &a.bmap, b_full(0), kbase + tap * cin + cc * KC, 0);
+          kbase += 9 * cin;
+        }
       }
     } else {
       uint32_t it = 0;
@@ -159,7 +172,7 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
     uint32_t ita = 0, itb = 0, tcount = 0;
     const uint64_t bdesc_base = umma_smem_desc<Cfg::SW>(b_base);
     const uint32_t b_lo_base = (uint32_t)bdesc_base, b_hi = (uint32_t)(bdesc_base >> 32);
-    if constexpr (Cfg::STATIONARY) {
+    if constexpr (STAT) {
       warp_wait(b_full(0), 0, lane);
       tc_fence_after();
     }
@@ -174,8 +187,9 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
       const uint32_t tmem_d0 = tmem_base + (buf * 2u) * Cfg::ACC_COLS;
       const uint32_t tmem_d1 = tmem_d0 + Cfg::ACC_COLS;
       uint32_t accumulate = 0;
+      uint32_t chunk = 0;  // (segment, chunk) counter of this tile: index of its 9 resident weight tiles
       for (int s = 0; s < a.nseg; ++s) {
-        for (int cc = 0; cc < a.seg[s].cin / KC; ++cc, ++ita) {
+        for (int cc = 0; cc < a.seg[s].cin / KC; ++cc, ++ita, ++chunk) {
           const int sta = ita % Cfg::A_STAGES;
           if (dbg) t0 = clock64();
           warp_wait(a_full(sta), (ita / Cfg::A_STAGES) & 1, lane);
@@ -185,12 +199,13 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
           // (in 16-byte units), so issuing an MMA costs one integer add instead of a bit-field rebuild.
           const uint64_t adesc_base = umma_smem_desc_planar(a_base + sta * Cfg::A_STAGE, kPlaneStride, kHaloW * 16);
           const uint32_t a_lo = (uint32_t)adesc_base, a_hi = (uint32_t)(adesc_base >> 32);
-          if constexpr (Cfg::STATIONARY) {
+          if constexpr (STAT) {
+            const uint32_t b_lo_chunk = b_lo_base + chunk * 9u * (Cfg::B_ALLOC >> 4);
             if (elect_one()) {
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
                 const int r = tap / 3, q = tap - 3 * r;
-                const uint32_t b_lo = b_lo_base + tap * (Cfg::B_ALLOC >> 4);
+                const uint32_t b_lo = b_lo_chunk + tap * (Cfg::B_ALLOC >> 4);
 #pragma unroll
                 for (int kk = 0; kk < KC / 16; ++kk) {
                   const uint32_t a_off = (uint32_t)(r * kHaloW + q) + (uint32_t)(2 * kk) * (kPlaneStride >> 4);
@@ -248,14 +263,17 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1u;
       const TileCoord tc = decode_tile(a, tile);
+      const int y = tc.y0 + (row >> 3);
+      const int x = tc.x0 + 8 * j + (row & 7);
+      const bool valid = (y < a.out_h) && (x < a.out_w);
+      uint4 res[EpiCfg<BN>::RV];
+      residual_prefetch<BN>(a, tc.ntile, tc.n0, y, x, valid, res);
       if (dbg) t0 = clock64();
       warp_wait(acc_full(buf), (tcount >> 1) & 1u, lane);
       if (dbg) { const long long t1 = clock64(); w_full += t1 - t0; t0 = t1; }
       tc_fence_after();
       const uint32_t taddr = tmem_base + (buf * 2u + j) * Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-      const int y = tc.y0 + (row >> 3);
-      const int x = tc.x0 + 8 * j + (row & 7);
-      epilogue_pixel<BN>(a, bias_s, tc.ntile, taddr, tc.n0, y, x, (y < a.out_h) && (x < a.out_w));
+      epilogue_pixel<BN>(a, bias_s, tc.ntile, taddr, tc.n0, y, x, valid, res);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
@@ -269,10 +287,10 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
     // ------------------------------------------------------------ halo gather (4 warps, cp.async)
     // Thread t copies channel octet kc = t % PLANES of the halo pixels p0, p0 + STEP, ...: a warp reads whole
     // pixel rows (coalesced) and the (row, col) of the next pixel follows incrementally, no divisions.
-    constexpr int STEP = kGatherThreads / Cfg::PLANES;  // halo pixels between two copies of one thread
+    constexpr int STEP = Cfg::GATHER_THREADS / Cfg::PLANES;  // halo pixels between two copies of one thread
     constexpr int DY = STEP / kHaloW, DX = STEP % kHaloW;
     constexpr int DEPTH = Cfg::A_STAGES - 1;            // cp.async groups kept in flight
-    const int t = threadIdx.x - (kHaloThreads - kGatherThreads);
+    const int t = threadIdx.x - kHaloBaseThreads;
     const int kc = t % Cfg::PLANES;
     const int p0 = t / Cfg::PLANES;
     const int hy0 = p0 / kHaloW, hx0 = p0 % kHaloW;
@@ -284,8 +302,10 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
       const TileCoord tc = decode_tile(a, tile);
       for (int s = 0; s < a.nseg; ++s) {
         const int cin = a.seg[s].cin;
+        const int up = a.seg[s].up;  // 1: the source is half resolution and read through a 2x nearest upsample
+        const int src_w = a.out_w >> up;
         const __nv_bfloat16* src = a.src_ptr[s];
-        const __nv_bfloat16* img = src + (size_t)tc.n0 * a.out_h * a.out_w * cin + kc * 8;
+        const __nv_bfloat16* img = src + (size_t)tc.n0 * (a.out_h >> up) * src_w * cin + kc * 8;
         for (int cc = 0; cc < cin / KC; ++cc, ++it) {
           const int st = it % Cfg::A_STAGES;
           if (dbg) t0 = clock64();
@@ -297,7 +317,7 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
           for (int p = p0; p < kHaloPix; p += STEP) {
             const int gy = tc.y0 - 1 + hy, gx = tc.x0 - 1 + hx;
             const bool ok = ((unsigned)gy < (unsigned)a.out_h) && ((unsigned)gx < (unsigned)a.out_w);
-            const __nv_bfloat16* g = ok ? img + ((size_t)gy * a.out_w + gx) * cin + cc * KC : src;
+            const __nv_bfloat16* g = ok ? img + ((size_t)(gy >> up) * src_w + (gx >> up)) * cin + cc * KC : src;
             cp_async_16(dst, g, ok ? 16u : 0u);  // src-size 0 = zero fill (the convolution's padding)
             dst += STEP * 16;
             hx += DX;
@@ -338,35 +358,41 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<KC, BN>::CTAS)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (a.debug != nullptr && threadIdx.x == 0) atomicAdd(a.debug + 11, (unsigned long long)(clock64() - t_cta));
 }
 
-template <int KC, int BN>
+static int halo_weight_tiles(const ConvArgs& a, int kc) {
+  int n = 0;
+  for (int s = 0; s < a.nseg; ++s) n += 9 * (a.seg[s].cin / kc);
+  return n;
+}
+
+template <int KC, int BN, bool STAT>
 static bool halo_variant_ok(const ConvArgs& a) {
-  using Cfg = HaloCfg<KC, BN>;
+  using Cfg = HaloCfg<KC, BN, STAT>;
   const int cout_pad = (a.mode == kEpiBf16) ? a.cout : BN;
   if (cout_pad > kMaxBias) return false;
-  if (Cfg::STATIONARY && (a.nseg != 1 || a.seg[0].cin != KC || cout_pad != BN)) return false;
+  if (STAT && (cout_pad != BN || halo_weight_tiles(a, KC) > Cfg::B_STAGES)) return false;
   return true;
 }
 
 bool conv_halo_applicable(const ConvArgs& a) {
-  if (a.nseg < 1 || a.nseg > 2 || a.out_h < kHaloTile || a.out_w < kHaloTile) return false;
+  if (a.nseg < 1 || a.nseg > 2) return false;
   for (int s = 0; s < a.nseg; ++s)
     if (a.seg[s].ksize != 3 || a.seg[s].stride != 1 || a.seg[s].pad != 1 || a.src_ptr[s] == nullptr) return false;
   return true;
 }
 
-template <int KC, int BN>
+template <int KC, int BN, bool STAT>
 static cudaError_t launch_halo_one(const ConvArgs& args_in, cudaStream_t stream) {
-  using Cfg = HaloCfg<KC, BN>;
+  using Cfg = HaloCfg<KC, BN, STAT>;
   static_assert(Cfg::SMEM_BYTES * Cfg::CTAS <= 227 * 1024, "halo kernel exceeds the shared memory of an SM");
-  if (!halo_variant_ok<KC, BN>(args_in)) return launch_conv_tc(args_in, KC, BN, stream);
   static int configured_dev = -1;
   static int num_sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC, BN, STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -383,12 +409,28 @@ static cudaError_t launch_halo_one(const ConvArgs& args_in, cudaStream_t stream)
   args.total_tiles = args.tiles_x * args.tiles_y * args.batch * args.ntiles_n;
   const int slots = num_sms * Cfg::CTAS;
   const int grid = args.total_tiles < slots ? args.total_tiles : slots;
-  conv_halo_kernel<KC, BN><<<grid, kHaloThreads, Cfg::SMEM_BYTES, stream>>>(args);
+  conv_halo_kernel<KC, BN, STAT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(args);
   return cudaGetLastError();
 }
 
+// Weights resident when the variant allows it, else streamed (64-channel chunks only); layers that fit neither
+// (e.g. <= 32-channel chunks with several Cout tiles -- none in this network) go to the per-tap kernel, which
+// cannot read an upsampled source.
+template <int KC, int BN>
+static cudaError_t launch_halo_pick(const ConvArgs& args, cudaStream_t stream) {
+  if constexpr (BN <= 64) {
+    if (halo_variant_ok<KC, BN, true>(args)) return launch_halo_one<KC, BN, true>(args, stream);
+  }
+  if constexpr (KC == 64) {
+    if (halo_variant_ok<KC, BN, false>(args)) return launch_halo_one<KC, BN, false>(args, stream);
+  }
+  for (int s = 0; s < args.nseg; ++s)
+    if (args.seg[s].up) return cudaErrorInvalidValue;
+  return launch_conv_tc(args, KC, BN, stream);
+}
+
 #define IU_HALO_DISPATCH(KC_, BN_) \
-  if (kc == KC_ && bn == BN_) return launch_halo_one<KC_, BN_>(args, stream);
+  if (kc == KC_ && bn == BN_) return launch_halo_pick<KC_, BN_>(args, stream);
 
 cudaError_t launch_conv_halo(const ConvArgs& args, int kc, int bn, cudaStream_t stream) {
   IU_HALO_DISPATCH(64, 128)

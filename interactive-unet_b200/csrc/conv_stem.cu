@@ -1,0 +1,248 @@
+// Stem of the encoder on the tensor cores: Conv2d(1, 64, 7, stride 2, padding 3) + folded BatchNorm + ReLU
+// (`smp.Unet('resnet34').encoder.conv1/bn1/relu`, reached from `/root/reference/interactive_unet/unet.py:67`).
+//
+// One input channel makes the conv a [pixels x 49] x [49 x 64] GEMM.  K is laid out as 7 filter rows x 8 columns
+// (the 8th column has zero weights) + 8 zero pad = 64, so that the A row of an output pixel is seven 16-byte
+// chunks, each being 8 CONSECUTIVE input pixels of one input row (stride 2 makes every chunk start at an even
+// column).  Per 16x16 block of output pixels a CTA
+//   * stages the 37x38 fp32 input patch as fp16 in shared memory (zero outside the image = the conv's padding),
+//   * 8 builder warps expand it into two 128-row A tiles in the 128B-swizzled K-major layout tcgen05.mma reads
+//     (one thread per output pixel: 7 x (4 LDS.32 + 1 STS.128), both bank-conflict free),
+//   * one thread issues 2 x 4 tcgen05.mma (M=128, N=64, K=16) into double-buffered TMEM accumulators,
+//   * 8 epilogue warps apply bias + ReLU and store 16-bit NHWC (conv_epilogue.cuh).
+// The [64 x 64] weight tile is loaded once per CTA.  Persistent over the tile list like the other conv kernels.
+#include "conv_epilogue.cuh"
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace iu {
+
+constexpr int kStemTileEdge = 16;                          // output pixels per tile edge
+constexpr int kStemPatchRows = 2 * kStemTileEdge + 5;      // 37 input rows per tile
+constexpr int kStemPatchCols = 2 * kStemTileEdge + 6;      // 38 input columns (7 taps + the zero-weight 8th)
+constexpr int kStemPitch = 48;                             // halfs per patch row: rows 2*py apart land 16 banks apart
+constexpr int kStemPatchBytes = (kStemPatchRows * kStemPitch * 2 + 127) / 128 * 128;
+constexpr int kStemAStages = 3;
+constexpr int kStemATile = 128 * 128;                      // one M tile: 128 rows x 64 fp16
+constexpr int kStemAStage = 2 * kStemATile;
+constexpr int kStemBBytes = 64 * 128;
+constexpr int kStemBuilders = 256;
+constexpr int kStemThreads = 320 + kStemBuilders;          // producer warp, MMA warp, 8 epilogue warps, 8 builder warps
+constexpr int kStemSmem = kStemAStages * kStemAStage + kStemBBytes + 2 * kStemPatchBytes + 64 * 4 + 16 * 8 + 16 + 1024;
+
+struct StemArgs {
+  CUtensorMap bmap;  // 2-D map (K = 64, Cout = 64) over the packed weights, box = (64, 64), 128B swizzle
+  const float* x;    // [batch][h][w] fp32 in [0, 1]
+  int batch, h, w;
+  ConvArgs epi;      // epilogue description (mode kEpiBf16, out, relu, fp16, cout = 64, out_h = h / 2, out_w = w / 2)
+};
+
+__global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid_constant__ StemArgs s) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + kStemAStages * kStemAStage;
+  const uint32_t patch_base = b_base + kStemBBytes;
+  const uint32_t bias_base = patch_base + 2 * kStemPatchBytes;
+  const uint32_t bar_base = bias_base + 64 * 4;
+  auto a_full = [&](int st) { return bar_base + 8u * st; };
+  auto a_empty = [&](int st) { return bar_base + 8u * (kStemAStages + st); };
+  const uint32_t b_full = bar_base + 16u * kStemAStages;
+  auto acc_full = [&](int b) { return bar_base + 16u * kStemAStages + 8u + 8u * b; };
+  auto acc_empty = [&](int b) { return bar_base + 16u * kStemAStages + 24u + 8u * b; };
+  const uint32_t tmem_slot = bar_base + 16u * kStemAStages + 40u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
+  uint8_t* a_ptr = smem_raw + (a_base - raw);
+  uint16_t* patch_ptr = reinterpret_cast<uint16_t*>(smem_raw + (patch_base - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const ConvArgs& a = s.epi;
+  const int tiles_x = (a.out_w + kStemTileEdge - 1) / kStemTileEdge;
+  const int tiles_y = (a.out_h + kStemTileEdge - 1) / kStemTileEdge;
+  const int total_tiles = tiles_x * tiles_y * s.batch;
+
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = a.bias[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&s.bmap);
+    for (int st = 0; st < kStemAStages; ++st) {
+      mbar_init(a_full(st), kStemBuilders / 32);
+      mbar_init(a_empty(st), 1);
+    }
+    mbar_init(b_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weights: one TMA load for the whole kernel
+    if (elect_one()) {
+      mbar_arrive_expect_tx(b_full, kStemBBytes);
+      tma_load_2d(b_base, &s.bmap, b_full, 0, 0);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_f16(kTileM, 64, a.fp16);
+    const uint64_t bdesc = umma_smem_desc<128>(b_base);
+    const uint32_t b_lo = (uint32_t)bdesc, b_hi = (uint32_t)(bdesc >> 32);
+    if (lane == 0) mbar_wait(b_full, 0);
+    __syncwarp();
+    tc_fence_after();
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      const int st = it % kStemAStages;
+      if (lane == 0) {
+        mbar_wait(acc_empty(buf), ((it >> 1) & 1u) ^ 1u);
+        mbar_wait(a_full(st), (it / kStemAStages) & 1);
+      }
+      __syncwarp();
+      tc_fence_after();
+      const uint64_t adesc = umma_smem_desc<128>(a_base + st * kStemAStage);
+      const uint32_t a_lo = (uint32_t)adesc, a_hi = (uint32_t)(adesc >> 32);
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16_lohi(tmem_base + (buf * 2u + j) * 64u, a_lo + j * (kStemATile >> 4) + 2u * kk, a_hi, b_lo + 2u * kk,
+                          b_hi, idesc, kk ? 1u : 0u);
+        }
+        umma_commit(a_empty(st));
+        umma_commit(acc_full(buf));
+      }
+      __syncwarp();
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------ epilogue: group j owns M tile j (columns 8j..8j+7)
+    const int j = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+      const int y = ty * kStemTileEdge + (row >> 3);
+      const int x = tx * kStemTileEdge + 8 * j + (row & 7);
+      if (lane == 0) mbar_wait(acc_full(buf), (it >> 1) & 1u);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (buf * 2u + j) * 64u + ((uint32_t)(quarter * 32) << 16);
+      uint4 res[EpiCfg<64>::RV];
+      epilogue_pixel<64>(a, bias_s, 0, taddr, n, y, x, (y < a.out_h) && (x < a.out_w), res);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+    }
+  } else {
+    // ------------------------------------------------------------ A builders (8 warps, one thread per output pixel)
+    const int t = threadIdx.x - 320;
+    const int py = t >> 4, px = t & 15;
+    const int m = py * 8 + (px & 7);  // row inside the M tile; the tile's two halves are columns 0-7 / 8-15
+    const uint32_t row_off = (uint32_t)(px >> 3) * kStemATile + (uint32_t)m * 128u;
+    // the zero K columns 56..63 (chunk 7) never change: write them once in every stage
+#pragma unroll
+    for (int st = 0; st < kStemAStages; ++st)
+      *reinterpret_cast<uint4*>(a_ptr + st * kStemAStage + row_off + ((7 ^ (m & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+    constexpr int kPatchElems = kStemPatchRows * kStemPatchCols;
+    constexpr int kPerThread = (kPatchElems + kStemBuilders - 1) / kStemBuilders;
+    float pre[kPerThread];
+    auto load_patch = [&](int tile) {
+      const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+      const int iy0 = 2 * ty * kStemTileEdge - 3, ix0 = 2 * tx * kStemTileEdge - 3;
+      const float* img = s.x + (size_t)n * s.h * s.w;
+#pragma unroll
+      for (int i = 0; i < kPerThread; ++i) {
+        const int e = t + i * kStemBuilders;
+        const int r = e / kStemPatchCols, c = e - r * kStemPatchCols;
+        const int iy = iy0 + r, ix = ix0 + c;
+        const bool ok = e < kPatchElems && (unsigned)iy < (unsigned)s.h && (unsigned)ix < (unsigned)s.w;
+        pre[i] = ok ? __ldg(img + (size_t)iy * s.w + ix) : 0.0f;
+      }
+    };
+    auto store_patch = [&](int which) {
+      uint16_t* p = patch_ptr + which * (kStemPatchBytes / 2);
+#pragma unroll
+      for (int i = 0; i < kPerThread; ++i) {
+        const int e = t + i * kStemBuilders;
+        const int r = e / kStemPatchCols, c = e - r * kStemPatchCols;
+        if (e < kPatchElems)
+          p[r * kStemPitch + c] = a.fp16 ? __half_as_ushort(__float2half_rn(pre[i]))
+                                         : __bfloat16_as_ushort(__float2bfloat16_rn(pre[i]));
+      }
+    };
+    auto builders_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kStemBuilders) : "memory"); };
+    uint32_t it = 0;
+    int tile = blockIdx.x;
+    if (tile < total_tiles) {
+      load_patch(tile);
+      store_patch(0);
+    }
+    builders_sync();
+    for (; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int st = it % kStemAStages;
+      const int next = tile + gridDim.x;
+      if (next < total_tiles) load_patch(next);  // global latency hides under this tile's expansion
+      if (lane == 0) mbar_wait(a_empty(st), ((it / kStemAStages) & 1) ^ 1u);
+      __syncwarp();
+      const uint32_t* prow =
+          reinterpret_cast<const uint32_t*>(patch_ptr + (it & 1u) * (kStemPatchBytes / 2) + (2 * py) * kStemPitch + 2 * px);
+      uint8_t* arow = a_ptr + st * kStemAStage + row_off;
+#pragma unroll
+      for (int r = 0; r < 7; ++r) {
+        const uint32_t* q = prow + r * (kStemPitch / 2);
+        *reinterpret_cast<uint4*>(arow + ((r ^ (m & 7)) << 4)) = make_uint4(q[0], q[1], q[2], q[3]);
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(st));
+      if (next < total_tiles) store_patch((it + 1) & 1u);
+      builders_sync();  // next patch complete; everyone is done reading the current one
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+cudaError_t launch_conv_stem(const CUtensorMap& bmap, const float* x, int batch, int h, int w, const ConvArgs& epi,
+                             cudaStream_t stream) {
+  static_assert(kStemSmem <= 227 * 1024, "stem kernel exceeds the shared memory of an SM");
+  static int configured_dev = -1;
+  static int num_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(conv_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured_dev = dev;
+  }
+  StemArgs s;
+  s.bmap = bmap;
+  s.x = x;
+  s.batch = batch;
+  s.h = h;
+  s.w = w;
+  s.epi = epi;
+  const int tiles = ((h / 2 + kStemTileEdge - 1) / kStemTileEdge) * ((w / 2 + kStemTileEdge - 1) / kStemTileEdge) * batch;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  conv_stem_kernel<<<grid, kStemThreads, kStemSmem, stream>>>(s);
+  return cudaGetLastError();
+}
+
+}  // namespace iu

@@ -174,14 +174,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
       const uint32_t buf = tcount & 1u;
       if ((int)buf != group) continue;
       const TileCoord tc = decode_tile(a, tile);
-      mbar_wait(acc_full_bar(buf), (tcount >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
       const int per_img = a.th * a.tw;
       const int n = tc.n0 + row / per_img;
       const int y = tc.y0 + (row % per_img) / a.tw;
       const int x = tc.x0 + row % a.tw;
-      epilogue_pixel<BN>(a, a.bias, tc.ntile, taddr, n, y, x, (n < a.batch) && (y < a.out_h) && (x < a.out_w));
+      const bool valid = (n < a.batch) && (y < a.out_h) && (x < a.out_w);
+      uint4 res[EpiCfg<BN>::RV];
+      residual_prefetch<BN>(a, tc.ntile, n, y, x, valid, res);
+      mbar_wait(acc_full_bar(buf), (tcount >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      epilogue_pixel<BN>(a, a.bias, tc.ntile, taddr, n, y, x, valid, res);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty_bar(buf));

@@ -25,6 +25,8 @@ struct ConvSegment {
   int ksize;   // 1 or 3
   int stride;  // 1 or 2
   int pad;     // 0 or 1
+  int up;      // 1: the source is stored at half the output resolution and read through a 2x nearest upsample
+               //    (decoder `F.interpolate(x, scale_factor=2)` fused into the consumer; halo kernel only)
 };
 
 struct alignas(64) ConvArgs {
@@ -52,6 +54,7 @@ struct alignas(64) ConvArgs {
   // optional (nullptr = off): 16 cycle counters per layer filled by the halo kernel's roles (development aid)
   //   [0] MMA wait accumulator  [1] MMA wait A  [2] MMA wait B  [3] MMA total  [4] gather wait empty
   //   [5] gather issue  [6] gather wait landing  [7] gather total  [8] epilogue wait  [9] epilogue body  [10] CTAs
+  //   [11] CTA lifetime (first instruction to after the TMEM dealloc)
   unsigned long long* debug;
 };
 
@@ -67,5 +70,12 @@ int conv_tc_smem_bytes(int kc, int bn);
 constexpr int kHaloTile = 16;
 bool conv_halo_applicable(const ConvArgs& args);
 cudaError_t launch_conv_halo(const ConvArgs& args, int kc, int bn, cudaStream_t stream);
+
+// Stem (conv_stem.cu): Conv2d(1, 64, 7, stride 2, padding 3) + bias + ReLU on the tensor cores.
+//   bmap: 2-D map over the packed 16-bit weights [64 cout][64 k], k = filter_row * 8 + filter_col (col 7 and
+//         k >= 56 are zero), box (64, 64), 128-byte swizzle;  x: fp32 [batch][h][w];
+//   epi:  epilogue description (mode kEpiBf16, out = [batch][h/2][w/2][64], bias, relu, fp16, cout = 64, out_h, out_w).
+cudaError_t launch_conv_stem(const CUtensorMap& bmap, const float* x, int batch, int h, int w, const ConvArgs& epi,
+                             cudaStream_t stream);
 
 }  // namespace iu

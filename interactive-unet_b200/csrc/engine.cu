@@ -51,6 +51,7 @@ struct Plan {
   std::vector<__nv_bfloat16*> bufs;
   float* x_in = nullptr;
   std::vector<ConvArgs> args;
+  ConvArgs stem_epi;
   size_t bytes = 0;
 };
 
@@ -100,13 +101,15 @@ struct iu_engine {
   bool loaded = false;
   int max_batch = 0;
   int fp16 = 1;  // 16-bit storage format of weights / activations: 1 = IEEE fp16 (default), 0 = bf16
+  int auto_batch_override = 0;  // env IU_AUTO_BATCH: slices per internal batch instead of the automatic choice
   int conv_variant = 0;  // 0 = auto (halo kernel where applicable), 1 = per-tap TMA kernel only (env IU_CONV_VARIANT)
   unsigned long long* d_debug = nullptr;  // env IU_CONV_DEBUG=1: 16 cycle counters per conv layer (development aid)
   int64_t launches = 0;
   size_t weight_bytes = 0;
 
-  float* d_stem_w = nullptr;
+  __nv_bfloat16* d_stem_w = nullptr;  // [64][64] 16-bit, k = filter_row * 8 + filter_col (conv_stem.cu)
   float* d_stem_b = nullptr;
+  CUtensorMap stem_bmap;
   std::vector<TensorSpec> tensors;
   std::vector<ConvLayer> convs;
   int t_f1 = -1, t_p1 = -1;
@@ -290,7 +293,8 @@ void free_weights(iu_engine* e) {
   e->tensors.clear();
   if (e->d_stem_w) cudaFree(e->d_stem_w);
   if (e->d_stem_b) cudaFree(e->d_stem_b);
-  e->d_stem_w = e->d_stem_b = nullptr;
+  e->d_stem_w = nullptr;
+  e->d_stem_b = nullptr;
   e->loaded = false;
   e->weight_bytes = 0;
 }
@@ -307,11 +311,13 @@ int new_tensor(iu_engine* e, int c, int hdiv) {
   return (int)e->tensors.size() - 1;
 }
 
+int encode_weight_map(iu_engine* e, CUtensorMap* m, const void* base, int ktot, int cout_pad, int kc, int bn);
+
 // Build one folded conv layer (+ optional fused 1x1/s2 downsample as a second K segment).
 int add_conv(iu_engine* e, const HostTensors& ht, const std::string& name, const std::string& conv_key,
              const std::string& bn_key, int nsrc, const int* src, const int* src_cin, int ksize, int stride,
              int cout, int out_tensor, int out_hdiv, int residual, int relu, int up2x, const std::string& ds_conv,
-             const std::string& ds_bn, int ds_src, int ds_cin) {
+             const std::string& ds_bn, int ds_src, int ds_cin, int src_up_mask = 0) {
   ConvLayer L;
   L.name = name;
   L.cout = cout;
@@ -333,7 +339,7 @@ int add_conv(iu_engine* e, const HostTensors& ht, const std::string& name, const
   L.nseg = nsrc;
   int k = 0;
   for (int s = 0; s < nsrc; ++s) {
-    L.seg[s] = {src_cin[s], ksize, stride, ksize / 2};
+    L.seg[s] = {src_cin[s], ksize, stride, ksize / 2, (src_up_mask >> s) & 1};
     L.src[s] = src[s];
     k += ksize * ksize * src_cin[s];
   }
@@ -342,7 +348,7 @@ int add_conv(iu_engine* e, const HostTensors& ht, const std::string& name, const
     if (nsrc != 1) return e->fail(IU_ERR_INVALID, "downsample fusion needs a single main source");
     if (!fold_bn(ht, ds_conv, ds_bn, cout, ds_cin, &wd, &bd, &err)) return e->fail(IU_ERR_INVALID, err);
     L.nseg = 2;
-    L.seg[1] = {ds_cin, 1, 2, 0};
+    L.seg[1] = {ds_cin, 1, 2, 0, 0};
     L.src[1] = ds_src;
     k += ds_cin;
     cin_min = std::min(cin_min, ds_cin);
@@ -369,18 +375,21 @@ int add_conv(iu_engine* e, const HostTensors& ht, const std::string& name, const
 
 int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
   std::string err;
-  // ---- stem: encoder.conv1 + bn1 (+ReLU), CUDA-core kernel, fp32 weights tap-major [49][64]
+  // ---- stem: encoder.conv1 + bn1 (+ReLU) as a K=64 GEMM on the tensor cores (conv_stem.cu)
   {
     std::vector<float> w, b;
     if (!fold_bn(ht, "encoder.conv1.weight", "encoder.bn1", 64, 49, &w, &b, &err)) return e->fail(IU_ERR_INVALID, err);
-    std::vector<float> wt(49 * 64);
+    std::vector<uint16_t> wk(64 * 64, 0);
     for (int co = 0; co < 64; ++co)
-      for (int tap = 0; tap < 49; ++tap) wt[tap * 64 + co] = w[co * 49 + tap];
-    IU_CUDA(e, cudaMalloc(&e->d_stem_w, wt.size() * 4));
+      for (int r = 0; r < 7; ++r)
+        for (int q = 0; q < 7; ++q) wk[co * 64 + r * 8 + q] = to16(w[co * 49 + r * 7 + q], e->fp16);
+    IU_CUDA(e, cudaMalloc(&e->d_stem_w, wk.size() * 2));
     IU_CUDA(e, cudaMalloc(&e->d_stem_b, 64 * 4));
-    IU_CUDA(e, cudaMemcpy(e->d_stem_w, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+    IU_CUDA(e, cudaMemcpy(e->d_stem_w, wk.data(), wk.size() * 2, cudaMemcpyHostToDevice));
     IU_CUDA(e, cudaMemcpy(e->d_stem_b, b.data(), 64 * 4, cudaMemcpyHostToDevice));
-    e->weight_bytes += wt.size() * 4 + 256;
+    e->weight_bytes += wk.size() * 2 + 256;
+    int rc = encode_weight_map(e, &e->stem_bmap, e->d_stem_w, 64, 64, 64, 64);
+    if (rc != IU_OK) return rc;
   }
   e->t_f1 = new_tensor(e, 64, 2);
   e->t_p1 = new_tensor(e, 64, 4);
@@ -397,20 +406,17 @@ int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
       const bool down = (li > 0 && b == 0);
       const int stride = down ? 2 : 1;
       const int hdiv = cur_hdiv * stride;
-      const bool last = (li == 3 && b == nblocks[li] - 1);
       const int t = new_tensor(e, cout, hdiv);
       int rc = add_conv(e, ht, base + ".conv1", base + ".conv1.weight", base + ".bn1", 1, &cur, &cur_c, 3, stride,
                         cout, t, hdiv, -1, 1, 0, "", "", -1, 0);
       if (rc != IU_OK) return rc;
-      // the last encoder feature is consumed only through the decoder's 2x nearest upsample: write it upsampled
-      const int o = new_tensor(e, cout, last ? hdiv / 2 : hdiv);
+      const int o = new_tensor(e, cout, hdiv);
       if (down)
         rc = add_conv(e, ht, base + ".conv2+downsample", base + ".conv2.weight", base + ".bn2", 1, &t, &cout, 3, 1,
-                      cout, o, hdiv, -1, 1, last ? 1 : 0, base + ".downsample.0.weight", base + ".downsample.1", cur,
-                      cur_c);
+                      cout, o, hdiv, -1, 1, 0, base + ".downsample.0.weight", base + ".downsample.1", cur, cur_c);
       else
         rc = add_conv(e, ht, base + ".conv2", base + ".conv2.weight", base + ".bn2", 1, &t, &cout, 3, 1, cout, o,
-                      hdiv, cur, 1, last ? 1 : 0, "", "", -1, 0);
+                      hdiv, cur, 1, 0, "", "", -1, 0);
       if (rc != IU_OK) return rc;
       cur = o;
       cur_c = cout;
@@ -418,12 +424,12 @@ int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
     }
     feat[li + 2] = cur;
   }
-  // ---- decoder (smp UnetDecoder): x = cat([up2x(x), skip]) -> conv1 -> conv2; the 2x nearest upsample of
-  //      every block output is produced by its conv2 epilogue (up2x store), so conv1 reads plain tensors.
+  // ---- decoder (smp UnetDecoder): x = cat([up2x(x), skip]) -> conv1 -> conv2; x stays at its own resolution in
+  //      memory and conv1's operand gather reads it through the 2x nearest upsample (ConvSegment::up).
   const int dec_out[5] = {256, 128, 64, 32, 16};
   const int skip_t[5] = {feat[4], feat[3], feat[2], feat[1], -1};
   const int skip_c[5] = {256, 128, 64, 64, 0};
-  int x = cur, x_c = 512;  // already upsampled to 1/16
+  int x = cur, x_c = 512;
   for (int i = 0; i < 5; ++i) {
     const int hdiv = 16 >> i;
     const std::string base = "decoder.blocks." + std::to_string(i);
@@ -431,12 +437,11 @@ int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
     int srcs[2] = {x, skip_t[i]};
     int cins[2] = {x_c, skip_c[i]};
     int rc = add_conv(e, ht, base + ".conv1", base + ".conv1.0.weight", base + ".conv1.1", skip_t[i] >= 0 ? 2 : 1,
-                      srcs, cins, 3, 1, dec_out[i], t, hdiv, -1, 1, 0, "", "", -1, 0);
+                      srcs, cins, 3, 1, dec_out[i], t, hdiv, -1, 1, 0, "", "", -1, 0, /*src_up_mask=*/1);
     if (rc != IU_OK) return rc;
-    const bool up = i < 4;
-    const int o = new_tensor(e, dec_out[i], up ? hdiv / 2 : hdiv);
+    const int o = new_tensor(e, dec_out[i], hdiv);
     rc = add_conv(e, ht, base + ".conv2", base + ".conv2.0.weight", base + ".conv2.1", 1, &t, &dec_out[i], 3, 1,
-                  dec_out[i], o, hdiv, -1, 1, up ? 1 : 0, "", "", -1, 0);
+                  dec_out[i], o, hdiv, -1, 1, 0, "", "", -1, 0);
     if (rc != IU_OK) return rc;
     x = o;
     x_c = dec_out[i];
@@ -448,7 +453,7 @@ int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
     L.cout = num_classes;
     L.cout_pad = 16;
     L.nseg = 1;
-    L.seg[0] = {16, 3, 1, 1};
+    L.seg[0] = {16, 3, 1, 1, 0};
     L.src[0] = x;
     L.out = -1;
     L.out_hdiv = 1;
@@ -555,6 +560,7 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
       a.src_ptr[s] = p.bufs[L.src[s]];
       const TensorSpec& ts = e->tensors[L.src[s]];
       const int st = L.seg[s].stride;
+      if (L.seg[s].up) continue;  // read by the halo kernel's gather only (raw pointer)
       int rc = encode_act_map(e, &a.amap[s], p.bufs[L.src[s]], ts.c, w / ts.hdiv, h / ts.hdiv, bp, L.kc, a.tw * st,
                               a.th * st, a.nb, st);
       if (rc != IU_OK) {
@@ -581,6 +587,19 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
     a.row_block = h;
     a.debug = (e->d_debug && i < 64) ? e->d_debug + 16 * i : nullptr;
   }
+  {
+    ConvArgs& a = p.stem_epi;
+    memset(&a, 0, sizeof(a));
+    a.batch = batch;
+    a.out_h = h / 2;
+    a.out_w = w / 2;
+    a.cout = 64;
+    a.bias = e->d_stem_b;
+    a.out = p.bufs[e->t_f1];
+    a.relu = 1;
+    a.fp16 = e->fp16;
+    a.mode = kEpiBf16;
+  }
   p.batch = batch;
   p.batch_pad = bp;
   p.h = h;
@@ -588,22 +607,34 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
   return IU_OK;
 }
 
+// Slices per internal batch.  Every conv tiles its output in 128- or 256-pixel blocks whose count per slice is a
+// power of two (>= 4 with the Cout tiles at 512^2 and above), and a B200 has 148 = 4 x 37 SMs: a multiple of 37
+// slices makes every layer's tile count a multiple of the SM count (no partial last wave).  74 slices at 512^2
+// also halve the per-layer launch overhead relative to 37; larger images use 37 to bound the workspace.
 int auto_batch(const iu_engine* e, int h, int w, int want) {
-  // enough slices that the deepest layers (1/32 resolution) still fill the 148 SMs, bounded for memory
-  double b = 32.0 * (512.0 / h) * (512.0 / w);
-  int nb = (int)std::max(1.0, std::min(128.0, std::floor(b)));
+  const double rel = ((double)h * w) / (512.0 * 512.0);
+  int mult = (int)std::floor(2.0 / rel + 0.5);
+  mult = std::max(1, std::min(4, mult));
+  int nb = e->auto_batch_override > 0 ? e->auto_batch_override : 37 * mult;
   if (e->max_batch > 0) nb = std::min(nb, e->max_batch);
   return std::max(1, std::min(nb, want));
 }
 
-// Kernel choice per conv: the halo-tile kernel for stride-1 3x3 layers on images >= 16x16, else the per-tap TMA kernel.
-// Measured on B200 (profiles/r01_*): the halo kernel wins 2-4x on the <= 32-channel layers (weights resident,
-// activations fetched once instead of nine times in 32/64-byte rows); on 64-channel chunks both kernels are
-// bounded by the tensor pipe's per-MMA operand fetch and the per-tap kernel (2 CTAs/SM) is slightly ahead.
-// IU_CONV_VARIANT: 0 = that rule, 1 = per-tap kernel only, 2 = halo kernel wherever it applies.
+// Kernel choice per conv.  The halo-tile kernel fetches every activation once per channel chunk instead of once
+// per tap and keeps small weight matrices resident; the per-tap TMA kernel covers strided / 1x1 segments.
+// Measured on B200 (profiles/): the per-tap kernel is L2->SM bandwidth bound on every layer (24-32 KB of operands
+// per four MMAs); the halo kernel is ahead wherever the weights are resident or the source is upsampled.
+// IU_CONV_VARIANT: 0 = automatic, 1 = per-tap kernel wherever it can run, 2 = halo kernel wherever it applies.
 cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
-  const bool halo = e->conv_variant == 2 || (e->conv_variant == 0 && kc <= 32);
-  if (halo && conv_halo_applicable(a)) return launch_conv_halo(a, kc, bn, e->stream);
+  bool has_up = false;
+  for (int s = 0; s < a.nseg; ++s) has_up |= a.seg[s].up != 0;
+  const bool applicable = conv_halo_applicable(a);
+  if (has_up && !applicable) return cudaErrorInvalidValue;
+  bool halo;
+  if (e->conv_variant == 1) halo = has_up;
+  else if (e->conv_variant == 2) halo = applicable;
+  else halo = has_up || (applicable && (kc <= 32 || bn <= 64) && a.out_h >= kHaloTile && a.out_w >= kHaloTile);
+  if (halo) return launch_conv_halo(a, kc, bn, e->stream);
   return launch_conv_tc(a, kc, bn, e->stream);
 }
 
@@ -611,7 +642,7 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
 int run_network(iu_engine* e, int batch, int head_mode, float* head_out, int slice0, int slice_count, int row_block) {
   Plan& p = e->plan;
   prof_begin(e, IU_PROF_STEM);
-  IU_CUDA(e, launch_stem(p.x_in, batch, p.h, p.w, e->d_stem_w, e->d_stem_b, p.bufs[e->t_f1], e->fp16, e->stream));
+  IU_CUDA(e, launch_conv_stem(e->stem_bmap, p.x_in, batch, p.h, p.w, p.stem_epi, e->stream));
   prof_end(e);
   prof_begin(e, IU_PROF_POOL);
   IU_CUDA(e, launch_maxpool(p.bufs[e->t_f1], batch, p.h / 2, p.w / 2, 64, p.bufs[e->t_p1], e->stream));
@@ -715,6 +746,7 @@ int iu_engine_create(int device, iu_engine** out) {
   }
   e->encode = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* v = getenv("IU_CONV_VARIANT")) e->conv_variant = atoi(v);
+  if (const char* v = getenv("IU_AUTO_BATCH")) e->auto_batch_override = atoi(v);
   if (const char* v = getenv("IU_CONV_DEBUG")) {
     if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(e->d_debug, 0, 64 * 16 * sizeof(unsigned long long));
@@ -1088,14 +1120,23 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
   cudaMemcpyAsync(d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, e->stream);
   cudaMemcpyAsync(d_b, bias, (size_t)cout * 4, cudaMemcpyHostToDevice, e->stream);
   const int pad = ksize / 2;
+  const int src0_up = (up2x >> 1) & 1;  // bit 1: src0 is [batch][h_in/2][w_in/2][cin0], read through a 2x nearest upsample
+  up2x &= 1;
+  if (src0_up && (ksize != 3 || stride != 1 || (h_in | w_in) % 2)) {
+    scratch_put(e, d_w);
+    scratch_put(e, d_b);
+    return e->fail(IU_ERR_INVALID, "conv_test: an upsampled source needs a 3x3 stride-1 conv and even h_in, w_in");
+  }
   const int out_h = (h_in + 2 * pad - ksize) / stride + 1, out_w = (w_in + 2 * pad - ksize) / stride + 1;
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   set_tiling(&a, batch, out_h, out_w);
   a.nseg = nseg;
-  a.seg[0] = {cin0, ksize, stride, pad};
-  a.seg[1] = {cin1, ksize, stride, pad};
-  rc = encode_act_map(e, &a.amap[0], src0, cin0, w_in, h_in, batch, kc, a.tw * stride, a.th * stride, a.nb, stride);
+  a.seg[0] = {cin0, ksize, stride, pad, src0_up};
+  a.seg[1] = {cin1, ksize, stride, pad, 0};
+  rc = src0_up ? IU_OK
+               : encode_act_map(e, &a.amap[0], src0, cin0, w_in, h_in, batch, kc, a.tw * stride, a.th * stride, a.nb,
+                                stride);
   if (rc == IU_OK && src1)
     rc = encode_act_map(e, &a.amap[1], src1, cin1, w_in, h_in, batch, kc, a.tw * stride, a.th * stride, a.nb, stride);
   if (rc == IU_OK) rc = encode_weight_map(e, &a.bmap, d_w, ktot, cout, kc, bn);

@@ -237,9 +237,13 @@ class Engine:
                 _ptr(out_u8)[0], _ptr(out_labels)[0], _ptr(out_mean)[0], 0))
 
     # ------------------------------------------------------------------ test hook
-    def conv_test(self, src0, src1, weight, bias, ksize, stride, residual=None, relu=True, up2x=False):
-        """One tensor-core conv on bf16 NHWC CUDA tensors, exactly as the engine runs its layers."""
+    def conv_test(self, src0, src1, weight, bias, ksize, stride, residual=None, relu=True, up2x=False,
+                  src0_up=False):
+        """One tensor-core conv on 16-bit NHWC CUDA tensors, exactly as the engine runs its layers.
+        `src0_up`: src0 is stored at half resolution and read through a 2x nearest upsample (decoder conv1)."""
         b, h, w, c0 = src0.shape
+        if src0_up:
+            h, w = 2 * h, 2 * w
         c1 = 0 if src1 is None else src1.shape[3]
         cout = weight.shape[0]
         pad = ksize // 2
@@ -254,5 +258,5 @@ class Engine:
             self._sync_torch(src0)
             self._check(self._lib.iu_engine_conv_test(
                 self._h, _ptr(src0)[0], c0, _ptr(src1)[0], c1, b, h, w, ksize, stride, _ptr(wt)[0], _ptr(bs)[0],
-                cout, _ptr(residual)[0], int(relu), int(up2x), _ptr(out)[0]))
+                cout, _ptr(residual)[0], int(relu), int(bool(up2x)) | (2 if src0_up else 0), _ptr(out)[0]))
         return out

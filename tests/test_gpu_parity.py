@@ -69,6 +69,14 @@ CONV_CASES = [
     ("tiny_4x4", 8, 4, 4, 512, 0, 512, 3, 1, True, True, True),
     ("ragged_24x24", 8, 24, 24, 64, 0, 64, 3, 1, False, True, False),
     ("ragged_3x3", 8, 3, 3, 256, 0, 256, 3, 1, False, True, False),
+    # decoder conv1: source 0 stored at half resolution, read through the fused 2x nearest upsample (up2x = "src")
+    ("upsrc_cat_k64n128", 8, 32, 32, 256, 128, 128, 3, 1, False, True, "src"),
+    ("upsrc_cat_k64n64", 8, 32, 32, 128, 64, 64, 3, 1, False, True, "src"),
+    ("upsrc_cat_k64n32", 8, 64, 64, 64, 64, 32, 3, 1, False, True, "src"),
+    ("upsrc_k32n16", 8, 64, 64, 32, 0, 16, 3, 1, False, True, "src"),
+    ("upsrc_tiny_8x8", 8, 8, 8, 512, 256, 256, 3, 1, False, True, "src"),
+    ("upsrc_ragged_40x24", 8, 40, 24, 64, 64, 32, 3, 1, False, True, "src"),
+    ("stat_k64n64_big", 8, 64, 64, 64, 0, 64, 3, 1, True, True, False),
 ]
 
 
@@ -83,16 +91,19 @@ def test_conv_matches_fp32_reference(dev, iu, case, precision, variant, monkeypa
     monkeypatch.setenv("IU_CONV_VARIANT", "1" if variant == "pertap" else "2")
     eng = iu.Engine(0, precision=precision)
     g = torch.Generator().manual_seed(hash(case[0]) % 1000)
-    src0 = torch.randn(b, h, w, c0, generator=g).to(dev).to(act)
+    src_up = up2x == "src"
+    up2x = up2x is True
+    src0 = torch.randn(b, h // 2 if src_up else h, w // 2 if src_up else w, c0, generator=g).to(dev).to(act)
     src1 = torch.randn(b, h, w, c1, generator=g).to(dev).to(act) if c1 else None
     cin = c0 + c1
     wt = (torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)).numpy()
     bias = (0.1 * torch.randn(cout, generator=g)).numpy()
     oh, ow = (h + 2 * (k // 2) - k) // stride + 1, (w + 2 * (k // 2) - k) // stride + 1
     res = torch.randn(b, oh, ow, cout, generator=g).to(dev).to(act) if residual else None
-    got = eng.conv_test(src0, src1, wt, bias, k, stride, residual=res, relu=relu, up2x=up2x).float()
+    got = eng.conv_test(src0, src1, wt, bias, k, stride, residual=res, relu=relu, up2x=up2x, src0_up=src_up).float()
 
-    x = (src0 if src1 is None else torch.cat([src0, src1], 3)).float().permute(0, 3, 1, 2)
+    x0 = src0.repeat_interleave(2, 1).repeat_interleave(2, 2) if src_up else src0      # nearest 2x: src = dst // 2
+    x = (x0 if src1 is None else torch.cat([x0, src1], 3)).float().permute(0, 3, 1, 2)
     y = F.conv2d(x, torch.from_numpy(wt).to(dev).to(act).float(), torch.from_numpy(bias).to(dev), stride=stride,
                  padding=k // 2)
     if res is not None:

@@ -43,7 +43,7 @@ def main():
         eng.debug_counters(reset=True)
         model(x)
         c = eng.debug_counters(reset=True).astype(float)
-        print("layer ctas | MMA: total  w_acc  w_A  w_B  issue | gather: total w_empty issue w_land | epi: wait body   (kcycles per CTA)")
+        print("layer ctas | MMA: total  w_acc  w_A  w_B  issue | gather: total w_empty issue w_land | epi: wait body | CTA life  (kcycles per CTA)")
         for i, r in enumerate(c):
             n = r[10]
             if n == 0:
@@ -51,7 +51,7 @@ def main():
             k = 1e-3 / n
             issue = r[3] - r[0] - r[1] - r[2]
             print(f"{i:3d} {int(n):4d} | {r[3]*k:8.1f} {r[0]*k:7.1f} {r[1]*k:7.1f} {r[2]*k:7.1f} {issue*k:7.1f} | "
-                  f"{r[7]*k:8.1f} {r[4]*k:7.1f} {r[5]*k:7.1f} {r[6]*k:7.1f} | {r[8]*k:7.1f} {r[9]*k:7.1f}")
+                  f"{r[7]*k:8.1f} {r[4]*k:7.1f} {r[5]*k:7.1f} {r[6]*k:7.1f} | {r[8]*k:7.1f} {r[9]*k:7.1f} | {r[11]*k:8.1f}")
 
 
 if __name__ == "__main__":
