@@ -361,6 +361,331 @@ __global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN
   if (a.debug != nullptr && threadIdx.x == 0) atomicAdd(a.debug + 11, (unsigned long long)(clock64() - t_cta));
 }
 
+// =====================================================================================================
+// CTA-pair variant for the wide layers (64-channel chunks, Cout a multiple of 128): two CTAs of a cluster sit
+// on the two SMs of a TPC and run ONE tcgen05.mma.cta_group::2 stream (M = 256, N = 128).  Each CTA owns a
+// 16x16 pixel block (its two 128-row A tiles, gathered exactly as above) and HALF of every [128 x 64] weight
+// tile: the tensor cores exchange the B halves, so the weight traffic L2 -> SM and the B share of the
+// shared-memory reads are halved -- the two limits the single-CTA kernel runs into on these layers
+// (profiles/r01_mma_probe.txt).  Barrier protocol:
+//   a_full / b_full / acc_empty : waited by the leader's MMA thread; arrivals come from both CTAs
+//                                 (remote mbarrier.arrive, TMA complete_tx addressed to the leader);
+//   a_empty / b_empty / acc_full: signalled in both CTAs at once by the leader's multicast tcgen05.commit.
+struct PairCfg {
+  static constexpr int KC = 64, BN = 128;
+  static constexpr int GATHER_THREADS = 256;
+  static constexpr int THREADS = kHaloBaseThreads + GATHER_THREADS;
+  static constexpr int PLANES = KC / 8;
+  static constexpr int A_STAGE = (PLANES * kPlaneStride + 1023) / 1024 * 1024;
+  static constexpr int A_STAGES = 3;
+  static constexpr int B_HALF_BYTES = (BN / 2) * KC * 2;  // 8 KB: this CTA's 64 weight rows of one (chunk, tap)
+  static constexpr int B_STAGES = 8;
+  static constexpr int TMEM_COLS = 4 * BN;                // 2 M tiles x 2 buffers
+  static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_HALF_BYTES + kMaxBias * 4 + NBAR * 8 + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(PairCfg::THREADS, 1) conv_pair_kernel(const __grid_constant__ ConvArgs a) {
+  using Cfg = PairCfg;
+  constexpr int KC = Cfg::KC, BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + Cfg::A_STAGES * Cfg::A_STAGE;
+  const uint32_t bias_base = b_base + Cfg::B_STAGES * Cfg::B_HALF_BYTES;
+  const uint32_t bar_base = bias_base + kMaxBias * 4;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::A_STAGES + s); };
+  auto b_full = [&](int s) { return bar_base + 16u * Cfg::A_STAGES + 8u * s; };
+  auto b_empty = [&](int s) { return bar_base + 16u * Cfg::A_STAGES + 8u * (Cfg::B_STAGES + s); };
+  const uint32_t acc_bars = bar_base + 16u * (Cfg::A_STAGES + Cfg::B_STAGES);
+  auto acc_full = [&](int b) { return acc_bars + 8u * b; };
+  auto acc_empty = [&](int b) { return acc_bars + 16u + 8u * b; };
+  const uint32_t tmem_slot = acc_bars + 32u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  // super tile s -> (Cout tile, pair of pixel blocks); this CTA's block is 2 * (s / ntiles_n) + rank
+  const int n_blocks = a.tiles_x * a.tiles_y * a.batch;
+  const int n_super = ((n_blocks + 1) >> 1) * a.ntiles_n;
+
+  for (int i = threadIdx.x; i < a.ntiles_n * BN; i += Cfg::THREADS) bias_s[i] = a.bias[i];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.bmap2);
+    for (int s = 0; s < Cfg::A_STAGES; ++s) {
+      mbar_init(a_full(s), 2 * Cfg::GATHER_THREADS / 32);  // the gather warps of both CTAs
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::B_STAGES; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 16);  // the epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before anyone signals across
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weight producer: this CTA's 64 rows of every tile
+    uint32_t it = 0;
+    for (int st_ = pair_id; st_ < n_super; st_ += n_pairs) {
+      const int ntile = st_ % a.ntiles_n;
+      int kbase = 0;
+      for (int s = 0; s < a.nseg; ++s) {
+        const int cin = a.seg[s].cin;
+        for (int cc = 0; cc < cin / KC; ++cc) {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap, ++it) {
+            const int st = it % Cfg::B_STAGES;
+            warp_wait(b_empty(st), ((it / Cfg::B_STAGES) & 1) ^ 1u, lane);
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(b_full(st), 2 * Cfg::B_HALF_BYTES);
+              tma_load_2d_pair(b_base + st * Cfg::B_HALF_BYTES, &a.bmap2, mapa_shared(b_full(st), 0),
+                               kbase + tap * cin + cc * KC, ntile * BN + (int)rank * (BN / 2));
+            }
+          }
+        }
+        kbase += 9 * cin;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(2 * kTileM, BN, a.fp16);
+      uint32_t ita = 0, itb = 0, tcount = 0;
+      const uint64_t bdesc_base = umma_smem_desc<128>(b_base);
+      const uint32_t b_lo_base = (uint32_t)bdesc_base, b_hi = (uint32_t)(bdesc_base >> 32);
+      const bool dbg = a.debug != nullptr;
+      long long w_acc = 0, w_a = 0, w_b = 0, t_begin = dbg ? clock64() : 0, t0 = 0;
+      for (int st_ = pair_id; st_ < n_super; st_ += n_pairs, ++tcount) {
+        const uint32_t buf = tcount & 1u;
+        if (dbg) t0 = clock64();
+        if (lane == 0) mbar_wait_cluster(acc_empty(buf), ((tcount >> 1) & 1u) ^ 1u);
+        __syncwarp();
+        if (dbg) w_acc += clock64() - t0;
+        tc_fence_after();
+        const uint32_t tmem_d0 = tmem_base + (buf * 2u) * BN;
+        const uint32_t tmem_d1 = tmem_d0 + BN;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < a.nseg; ++s) {
+          for (int cc = 0; cc < a.seg[s].cin / KC; ++cc, ++ita) {
+            const int sta = ita % Cfg::A_STAGES;
+            if (dbg) t0 = clock64();
+            if (lane == 0) mbar_wait_cluster(a_full(sta), (ita / Cfg::A_STAGES) & 1);
+            __syncwarp();
+            if (dbg) w_a += clock64() - t0;
+            tc_fence_after();
+            const uint64_t adesc_base = umma_smem_desc_planar(a_base + sta * Cfg::A_STAGE, kPlaneStride, kHaloW * 16);
+            const uint32_t a_lo = (uint32_t)adesc_base, a_hi = (uint32_t)(adesc_base >> 32);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap, ++itb) {
+              const int stb = itb % Cfg::B_STAGES;
+              if (dbg) t0 = clock64();
+              if (lane == 0) mbar_wait_cluster(b_full(stb), (itb / Cfg::B_STAGES) & 1);
+              __syncwarp();
+              if (dbg) w_b += clock64() - t0;
+              tc_fence_after();
+              const int r = tap / 3, q = tap - 3 * r;
+              const uint32_t b_lo = b_lo_base + stb * (Cfg::B_HALF_BYTES >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  const uint32_t a_off = (uint32_t)(r * kHaloW + q) + (uint32_t)(2 * kk) * (kPlaneStride >> 4);
+                  umma_f16_pair_lohi(tmem_d0, a_lo + a_off, a_hi, b_lo + 2u * kk, b_hi, idesc, accumulate);
+                  umma_f16_pair_lohi(tmem_d1, a_lo + a_off + 8u, a_hi, b_lo + 2u * kk, b_hi, idesc, accumulate);
+                  accumulate = 1;
+                }
+                umma_commit_pair(b_empty(stb));
+                if (tap == 8) umma_commit_pair(a_empty(sta));
+              }
+              accumulate = 1;
+            }
+          }
+        }
+        if (elect_one()) umma_commit_pair(acc_full(buf));
+      }
+      if (dbg && lane == 0) {
+        atomicAdd(a.debug + 0, (unsigned long long)w_acc);
+        atomicAdd(a.debug + 1, (unsigned long long)w_a);
+        atomicAdd(a.debug + 2, (unsigned long long)w_b);
+        atomicAdd(a.debug + 3, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(a.debug + 10, 1ull);
+      }
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------ epilogue: group j owns this CTA's M tile j
+    const int j = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t acc_empty_leader = mapa_shared(acc_empty(0), 0);
+    uint32_t tcount = 0;
+    const bool dbg = a.debug != nullptr && rank == 0 && warp == 2 && lane == 0;
+    long long w_full = 0, t_body = 0, t0 = 0;
+    for (int st_ = pair_id; st_ < n_super; st_ += n_pairs, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      const int block = 2 * (st_ / a.ntiles_n) + (int)rank;
+      const TileCoord tc = decode_tile(a, block * a.ntiles_n + st_ % a.ntiles_n);
+      const int y = tc.y0 + (row >> 3);
+      const int x = tc.x0 + 8 * j + (row & 7);
+      const bool valid = (block < n_blocks) && (y < a.out_h) && (x < a.out_w);
+      uint4 res[EpiCfg<BN>::RV];
+      residual_prefetch<BN>(a, tc.ntile, tc.n0, y, x, valid, res);
+      if (dbg) t0 = clock64();
+      warp_wait(acc_full(buf), (tcount >> 1) & 1u, lane);
+      if (dbg) { const long long t1 = clock64(); w_full += t1 - t0; t0 = t1; }
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (buf * 2u + j) * BN + ((uint32_t)(quarter * 32) << 16);
+      epilogue_pixel<BN>(a, bias_s, tc.ntile, taddr, tc.n0, y, x, valid, res);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * buf);
+      if (dbg) t_body += clock64() - t0;
+    }
+    if (dbg) {
+      atomicAdd(a.debug + 8, (unsigned long long)w_full);
+      atomicAdd(a.debug + 9, (unsigned long long)t_body);
+    }
+  } else {
+    // ------------------------------------------------------------ halo gather of this CTA's block (8 warps, cp.async)
+    constexpr int STEP = Cfg::GATHER_THREADS / Cfg::PLANES;
+    constexpr int DY = STEP / kHaloW, DX = STEP % kHaloW;
+    constexpr int DEPTH = Cfg::A_STAGES - 1;
+    const int t = threadIdx.x - kHaloBaseThreads;
+    const int kc = t % Cfg::PLANES;
+    const int p0 = t / Cfg::PLANES;
+    const int hy0 = p0 / kHaloW, hx0 = p0 % kHaloW;
+    const uint32_t dst_off = kc * kPlaneStride + p0 * 16;
+    const uint32_t a_full_leader = mapa_shared(a_full(0), 0);
+    uint32_t it = 0;
+    const bool dbg = a.debug != nullptr && rank == 0 && t == 0;
+    long long g_empty = 0, g_issue = 0, g_land = 0, t0 = 0, t_begin = dbg ? clock64() : 0;
+    for (int st_ = pair_id; st_ < n_super; st_ += n_pairs) {
+      const int block = 2 * (st_ / a.ntiles_n) + (int)rank;
+      const TileCoord tc = decode_tile(a, block * a.ntiles_n);
+      const bool live = block < n_blocks;  // an odd block count leaves the last pair's second CTA with zeros
+      for (int s = 0; s < a.nseg; ++s) {
+        const int cin = a.seg[s].cin;
+        const int up = a.seg[s].up;
+        const int src_w = a.out_w >> up;
+        const __nv_bfloat16* src = a.src_ptr[s];
+        const __nv_bfloat16* img = src + (size_t)tc.n0 * (a.out_h >> up) * src_w * cin + kc * 8;
+        for (int cc = 0; cc < cin / KC; ++cc, ++it) {
+          const int st = it % Cfg::A_STAGES;
+          if (dbg) t0 = clock64();
+          warp_wait(a_empty(st), ((it / Cfg::A_STAGES) & 1) ^ 1u, lane);
+          if (dbg) { const long long t1 = clock64(); g_empty += t1 - t0; t0 = t1; }
+          uint32_t dst = a_base + st * Cfg::A_STAGE + dst_off;
+          int hy = hy0, hx = hx0;
+#pragma unroll 4
+          for (int p = p0; p < kHaloPix; p += STEP) {
+            const int gy = tc.y0 - 1 + hy, gx = tc.x0 - 1 + hx;
+            const bool ok = live && ((unsigned)gy < (unsigned)a.out_h) && ((unsigned)gx < (unsigned)a.out_w);
+            const __nv_bfloat16* g = ok ? img + ((size_t)(gy >> up) * src_w + (gx >> up)) * cin + cc * KC : src;
+            cp_async_16(dst, g, ok ? 16u : 0u);
+            dst += STEP * 16;
+            hx += DX;
+            hy += DY;
+            if (hx >= kHaloW) {
+              hx -= kHaloW;
+              hy += 1;
+            }
+          }
+          cp_async_commit();
+          if (dbg) { const long long t1 = clock64(); g_issue += t1 - t0; t0 = t1; }
+          if (it >= (uint32_t)(DEPTH - 1)) {
+            cp_async_wait<DEPTH - 1>();
+            if (dbg) g_land += clock64() - t0;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(a_full_leader + 8u * ((it - (DEPTH - 1)) % Cfg::A_STAGES));
+          }
+        }
+      }
+    }
+    if (dbg) {
+      atomicAdd(a.debug + 4, (unsigned long long)g_empty);
+      atomicAdd(a.debug + 5, (unsigned long long)g_issue);
+      atomicAdd(a.debug + 6, (unsigned long long)g_land);
+      atomicAdd(a.debug + 7, (unsigned long long)(clock64() - t_begin));
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t first = it >= (uint32_t)(DEPTH - 1) ? it - (DEPTH - 1) : 0u;
+      for (uint32_t k = first; k < it; ++k) mbar_arrive_cluster(a_full_leader + 8u * (k % Cfg::A_STAGES));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still signal this CTA's barriers / read its weight half until here
+  if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+}
+
+bool conv_pair_applicable(const ConvArgs& a) {
+  if (!conv_halo_applicable(a)) return false;
+  const int cout_pad = (a.mode == kEpiBf16) ? a.cout : 0;
+  if (cout_pad == 0 || cout_pad % PairCfg::BN || cout_pad > kMaxBias) return false;
+  for (int s = 0; s < a.nseg; ++s)
+    if (a.seg[s].cin % PairCfg::KC) return false;
+  return true;
+}
+
+cudaError_t launch_conv_pair(const ConvArgs& args_in, cudaStream_t stream) {
+  using Cfg = PairCfg;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "pair kernel exceeds the shared memory of an SM");
+  static int configured_dev = -1;
+  static int num_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured_dev = dev;
+  }
+  ConvArgs args = args_in;
+  args.tw = kHaloTile;
+  args.th = kHaloTile;
+  args.nb = 1;
+  args.tiles_x = (args.out_w + kHaloTile - 1) / kHaloTile;
+  args.tiles_y = (args.out_h + kHaloTile - 1) / kHaloTile;
+  args.ntiles_n = args.cout / Cfg::BN;
+  args.total_tiles = args.tiles_x * args.tiles_y * args.batch * args.ntiles_n;
+  const int n_blocks = args.tiles_x * args.tiles_y * args.batch;
+  const int n_super = ((n_blocks + 1) / 2) * args.ntiles_n;
+  const int max_pairs = num_sms / 2;
+  const int pairs = n_super < max_pairs ? n_super : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_pair_kernel, args);
+}
+
 static int halo_weight_tiles(const ConvArgs& a, int kc) {
   int n = 0;
   for (int s = 0; s < a.nseg; ++s) n += 9 * (a.seg[s].cin / kc);

@@ -32,6 +32,7 @@ struct ConvSegment {
 struct alignas(64) ConvArgs {
   CUtensorMap amap[2];  // 4-D maps (C, W, H, N) over the segment sources, box = (KC, tw*stride, th*stride, nb)
   CUtensorMap bmap;     // 2-D map (K, Cout_pad) over the packed weights, box = (KC, BN)
+  CUtensorMap bmap2;    // the same weights with box = (64, 64): one CTA's half tile in the CTA-pair kernel
   ConvSegment seg[2];
   const __nv_bfloat16* src_ptr[2];  // raw pointers of the segment sources (halo kernel: cp.async gathers)
   int nseg;
@@ -70,6 +71,11 @@ int conv_tc_smem_bytes(int kc, int bn);
 constexpr int kHaloTile = 16;
 bool conv_halo_applicable(const ConvArgs& args);
 cudaError_t launch_conv_halo(const ConvArgs& args, int kc, int bn, cudaStream_t stream);
+
+// CTA-pair variant (tcgen05 cta_group::2, M = 256, N = 128) for stride-1 3x3 convs with 64-channel chunks and
+// Cout a multiple of 128; needs `bmap2`.
+bool conv_pair_applicable(const ConvArgs& args);
+cudaError_t launch_conv_pair(const ConvArgs& args, cudaStream_t stream);
 
 // Stem (conv_stem.cu): Conv2d(1, 64, 7, stride 2, padding 3) + bias + ReLU on the tensor cores.
 //   bmap: 2-D map over the packed 16-bit weights [64 cout][64 k], k = filter_row * 8 + filter_col (col 7 and

@@ -102,6 +102,7 @@ struct iu_engine {
   int max_batch = 0;
   int fp16 = 1;  // 16-bit storage format of weights / activations: 1 = IEEE fp16 (default), 0 = bf16
   int auto_batch_override = 0;  // env IU_AUTO_BATCH: slices per internal batch instead of the automatic choice
+  int conv_pair = 0;  // env IU_CONV_PAIR=1 routes the wide layers to the CTA-pair kernel (opt-in: not yet faster end to end)
   int conv_variant = 0;  // 0 = auto (halo kernel where applicable), 1 = per-tap TMA kernel only (env IU_CONV_VARIANT)
   unsigned long long* d_debug = nullptr;  // env IU_CONV_DEBUG=1: 16 cycle counters per conv layer (development aid)
   int64_t launches = 0;
@@ -569,6 +570,8 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
       }
     }
     int rc = encode_weight_map(e, &a.bmap, L.d_w, L.ktot, L.cout_pad, L.kc, L.bn);
+    if (rc == IU_OK && L.kc == 64 && L.cout_pad % 128 == 0)
+      rc = encode_weight_map(e, &a.bmap2, L.d_w, L.ktot, L.cout_pad, 64, 64);
     if (rc != IU_OK) {
       free_plan(e);
       return rc;
@@ -630,6 +633,9 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
   for (int s = 0; s < a.nseg; ++s) has_up |= a.seg[s].up != 0;
   const bool applicable = conv_halo_applicable(a);
   if (has_up && !applicable) return cudaErrorInvalidValue;
+  if (e->conv_pair && e->conv_variant != 1 && kc == 64 && bn == 128 && conv_pair_applicable(a) &&
+      (e->conv_variant == 2 || (a.out_h >= kHaloTile && a.out_w >= kHaloTile)))
+    return launch_conv_pair(a, e->stream);
   bool halo;
   if (e->conv_variant == 1) halo = has_up;
   else if (e->conv_variant == 2) halo = applicable;
@@ -747,6 +753,7 @@ int iu_engine_create(int device, iu_engine** out) {
   e->encode = reinterpret_cast<EncodeTiledFn>(fn);
   if (const char* v = getenv("IU_CONV_VARIANT")) e->conv_variant = atoi(v);
   if (const char* v = getenv("IU_AUTO_BATCH")) e->auto_batch_override = atoi(v);
+  if (const char* v = getenv("IU_CONV_PAIR")) e->conv_pair = atoi(v);
   if (const char* v = getenv("IU_CONV_DEBUG")) {
     if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(e->d_debug, 0, 64 * 16 * sizeof(unsigned long long));
@@ -1140,6 +1147,7 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
   if (rc == IU_OK && src1)
     rc = encode_act_map(e, &a.amap[1], src1, cin1, w_in, h_in, batch, kc, a.tw * stride, a.th * stride, a.nb, stride);
   if (rc == IU_OK) rc = encode_weight_map(e, &a.bmap, d_w, ktot, cout, kc, bn);
+  if (rc == IU_OK && kc == 64 && cout % 128 == 0) rc = encode_weight_map(e, &a.bmap2, d_w, ktot, cout, 64, 64);
   if (rc == IU_OK) {
     a.cout = cout;
     a.bias = d_b;

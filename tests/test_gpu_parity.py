@@ -80,15 +80,17 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", ["pertap", "halo"])
+@pytest.mark.parametrize("variant", ["pertap", "halo", "pair"])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_matches_fp32_reference(dev, iu, case, precision, variant, monkeypatch):
-    """Both tensor-core kernels (per-tap TMA boxes; halo tile with shifted no-swizzle descriptors), forced via
-    IU_CONV_VARIANT; the halo variant falls back to the per-tap kernel where it does not apply."""
+    """The tensor-core kernels (per-tap TMA boxes; halo tile with shifted no-swizzle descriptors; CTA-pair halo
+    kernel with tcgen05 cta_group::2 on the Cout >= 128 cases), forced via IU_CONV_VARIANT / IU_CONV_PAIR; each
+    variant falls back to the next one where it does not apply."""
     _, b, h, w, c0, c1, cout, k, stride, residual, relu, up2x = case
     act = torch.float16 if precision == "fp16" else torch.bfloat16
     monkeypatch.setenv("IU_CONV_VARIANT", "1" if variant == "pertap" else "2")
+    monkeypatch.setenv("IU_CONV_PAIR", "1" if variant == "pair" else "0")
     eng = iu.Engine(0, precision=precision)
     g = torch.Generator().manual_seed(hash(case[0]) % 1000)
     src_up = up2x == "src"

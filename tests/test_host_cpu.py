@@ -35,6 +35,22 @@ def test_python_binding_mirrors_header(built_library):
     _lib.load()
 
 
+def test_product_package_never_touches_the_oracle():
+    """`oracle/` is test infrastructure: no file of the shipped package (Python or CUDA) may import or name it,
+    and none may read the reference tree."""
+    pkg = os.path.join(ROOT, "interactive-unet_b200")
+    for base, _, files in os.walk(pkg):
+        if os.path.basename(base) in ("build", "__pycache__"):
+            continue
+        for name in files:
+            if not name.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            text = open(os.path.join(base, name)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{name} imports oracle/"
+            assert "/root/reference" not in text.replace("`/root/reference", "").replace("(`/root/reference", ""), \
+                f"{name} reads the reference tree"
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback(built_library):
     import interactive_unet_b200 as iu
