@@ -332,9 +332,14 @@ __global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN
           if (it >= (uint32_t)(DEPTH - 1)) {
             cp_async_wait<DEPTH - 1>();  // the group issued DEPTH-1 stages ago has landed
             if (dbg) g_land += clock64() - t0;
-            fence_proxy_async();         // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            // every lane's copies have landed; ONE proxy fence per warp (after the warp-level sync that orders the
+            // lanes' writes before it) makes them visible to the tensor core's async-proxy reads: a fence per thread
+            // serialises ~10 cycles x 256 threads per stage
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_full((it - (DEPTH - 1)) % Cfg::A_STAGES));
+            if (lane == 0) {
+              fence_proxy_async();
+              mbar_arrive(a_full((it - (DEPTH - 1)) % Cfg::A_STAGES));
+            }
           }
         }
       }
@@ -347,9 +352,9 @@ __global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN
     }
     // drain: signal the last DEPTH-1 stages
     cp_async_wait<0>();
-    fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
+      fence_proxy_async();
       const uint32_t first = it >= (uint32_t)(DEPTH - 1) ? it - (DEPTH - 1) : 0u;
       for (uint32_t k = first; k < it; ++k) mbar_arrive(a_full(k % Cfg::A_STAGES));
     }
@@ -610,9 +615,11 @@ __global__ void __launch_bounds__(PairCfg::THREADS, 1) conv_pair_kernel(const __
           if (it >= (uint32_t)(DEPTH - 1)) {
             cp_async_wait<DEPTH - 1>();
             if (dbg) g_land += clock64() - t0;
-            fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(a_full_leader + 8u * ((it - (DEPTH - 1)) % Cfg::A_STAGES));
+            if (lane == 0) {
+              fence_proxy_async();
+              mbar_arrive_cluster(a_full_leader + 8u * ((it - (DEPTH - 1)) % Cfg::A_STAGES));
+            }
           }
         }
       }
@@ -624,9 +631,9 @@ __global__ void __launch_bounds__(PairCfg::THREADS, 1) conv_pair_kernel(const __
       atomicAdd(a.debug + 7, (unsigned long long)(clock64() - t_begin));
     }
     cp_async_wait<0>();
-    fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
+      fence_proxy_async();
       const uint32_t first = it >= (uint32_t)(DEPTH - 1) ? it - (DEPTH - 1) : 0u;
       for (uint32_t k = first; k < it; ++k) mbar_arrive_cluster(a_full_leader + 8u * (k % Cfg::A_STAGES));
     }

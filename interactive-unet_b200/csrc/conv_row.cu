@@ -1,0 +1,558 @@
+// Row-folded implicit-GEMM 3x3 convolution for the narrow layers (Cout = 16 / 32 / 64, image width % 128 == 0).
+//
+// Why: a tcgen05.mma with M = 128 and both operands in shared memory costs ~42 cycles however small N is (it has
+// to read the 4 KB A tile), so an N = 16 / 32 / 64 MMA runs at 19 / 38 / 66 % of the tensor rate
+// (profiles/r01_pipe_probe.txt).  The narrow layers -- layer1, decoder blocks 2-4 and the head, 31 % of the
+// network's FLOPs -- were therefore issue bound at a fraction of peak.  This kernel makes every MMA three filter
+// taps wide:
+//   * an M tile is 128 CONSECUTIVE PIXELS OF ONE IMAGE ROW; a CTA block is R output rows x 128 columns;
+//   * the accumulators of the block's R output rows sit side by side in TMEM: row r owns columns [r*CO, (r+1)*CO);
+//   * the weights of one filter column kx are packed [W(ky=2) | W(ky=1) | W(ky=0)] (3*CO rows of B), so ONE MMA of
+//     input row i against that tile adds, in a single N = 3*CO instruction, input row i's contribution to output
+//     rows i-1, i and i+1 -- the three vertical taps land in three neighbouring accumulators because those are
+//     contiguous TMEM columns.  The block's first / last input rows use the matching 1- or 2-slot sub-tiles.
+//     Per (kx, 16 channels): R+2 MMAs of N <= 3*CO instead of 3*R MMAs of N = CO.
+//   * the A operand is the planar halo layout of conv_halo.cu (plane = 8 channels, 16 B per pixel) with a row pitch
+//     of 130 pixels: input row i, filter column kx is the same buffer through a descriptor shifted by
+//     i * pitch + kx * 16 bytes (SBO = 128 B: the eight-pixel core matrices of a row are contiguous).  The 2x nearest
+//     upsample of the decoder (`src = dst >> 1`) and the channel concat are folded into the gather as before;
+//   * a residual (ResNet shortcut) is one more K segment against an identity weight tile: the tensor core adds it,
+//     the epilogue never touches global memory for it;
+//   * epilogue: TMEM -> registers -> bias / ReLU / 16-bit pack -> swizzled shared-memory staging -> ONE TMA store
+//     of the 128-pixel row (a contiguous 128*CO*2-byte run of the NHWC tensor).  The per-lane 16-byte global
+//     stores of the generic epilogue cost 32 L1 wavefronts per instruction and were the bottleneck of layer1.
+//   * all weight tiles of the layer stay resident in shared memory (loaded once per CTA by TMA).
+// Warp roles (576 threads, one persistent CTA per SM): warp 0 weight TMA, warp 1 MMA issue, warps 2-9 epilogue
+// (two groups of four, alternating output rows), warps 10-17 gather (cp.async).
+//
+// Replaces the same cuDNN conv2d / batch_norm / relu / add / cat / upsample / softmax launches as conv_tc.cu
+// (`smp.Unet.forward` under `/root/reference/interactive_unet/unet.py:67`).
+#include "conv_epilogue.cuh"
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace iu {
+
+constexpr int kRowSeg = 128;               // output pixels per M tile (one image-row segment)
+constexpr int kRowHaloPx = kRowSeg + 2;    // gathered pixels per row: x0-1 .. x0+128
+constexpr int kRowPitch = kRowHaloPx * 16;  // bytes per gathered row inside a plane
+constexpr int kRowBaseThreads = 320;       // warps 0-9
+constexpr int kRowGatherThreads = 256;     // warps 10-17
+constexpr int kRowThreads = kRowBaseThreads + kRowGatherThreads;
+constexpr int kRowSmemMax = 227 * 1024;
+
+// KC : channels per gathered A stage          KCB: channels per weight tile (its TMA / UMMA swizzle span is KCB*2 bytes;
+//      a 64-byte span is read by the tensor core with 2-way bank conflicts, so the 64-output layers use 128-byte tiles)
+// CO : output channels (= cout_pad)           R  : output rows per block         STAGES: A ring depth
+// RB : output rows per TMA store (one staging buffer per epilogue group holds RB rows)
+template <int KC, int KCB, int CO, int R, int STAGES, int RB>
+struct RowCfg {
+  static constexpr int PLANES = KC / 8;
+  static constexpr int ROWS = R + 2;
+  static constexpr int PLANE_STRIDE = ROWS * kRowPitch + 16;  // (stride / 16) odd: planes start 16 B apart mod 32 banks
+  static constexpr int A_STAGE = (PLANES * PLANE_STRIDE + 1023) / 1024 * 1024;
+  static constexpr int A_STAGES = STAGES;
+  static constexpr int NF = 3 * CO;         // N of a full-width (three-slot) MMA
+  static constexpr int SWB = KCB * 2;       // bytes per weight row = TMA / UMMA swizzle span
+  static constexpr int B_TILE = NF * SWB;   // one (segment, KCB chunk, kx) weight tile
+  static constexpr int I_TILE = CO * SWB;   // one identity tile (residual segment)
+  static constexpr int STG = RB * kRowSeg * CO * 2;  // staging of RB output row segments
+  static constexpr int ACC_COLS = R * CO;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;  // double buffered: 512 / 512 / 256
+  static constexpr int MISC = 1024;  // bias (<= 256 B) + barriers + TMEM slot
+  static constexpr int W_MAX = (kRowSmemMax - 1024 - A_STAGES * A_STAGE - 2 * STG - MISC) / 1024 * 1024;
+  static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + W_MAX + 2 * STG + MISC;
+  static constexpr int CH = CO >= 32 ? 32 : 16;  // accumulator columns per tcgen05.ld
+  static_assert(KCB % KC == 0 && (KCB == 64 || KCB == 32 || KCB == 16), "weight tile width");
+  static_assert((PLANE_STRIDE / 16) % 2 == 1, "plane stride must be an odd number of 16-byte units");
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+  static_assert(W_MAX > 0 && SMEM_BYTES <= kRowSmemMax, "shared memory budget");
+  static_assert((R / 2) % RB == 0, "each epilogue group stores whole RB-row boxes");
+  static_assert((kRowSeg * PLANES) % kRowGatherThreads == 0, "gather columns per thread");
+};
+
+// 16-bit pack with saturation to the finite range (one cvt per pair) and ReLU on the packed pair.
+__device__ __forceinline__ uint32_t pack16_sat(float lo, float hi, int fp16) {
+  uint32_t r;
+  if (fp16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t relu16x2(uint32_t v, int fp16) {
+  uint32_t r;
+  const uint32_t zero = 0u;
+  if (fp16) asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(zero));
+  else asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(zero));
+  return r;
+}
+
+__device__ __forceinline__ void rcp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void rcp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void rcp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint64_t row_desc_planar(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (uint64_t)(lbo >> 4) << 16 | (uint64_t)(sbo >> 4) << 32 |
+         (uint64_t)1 << 46;
+}
+__device__ __forceinline__ void row_warp_wait(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+struct RowTile {
+  int n, y0, x0;
+};
+__device__ __forceinline__ RowTile row_decode(const ConvArgs& a, int tile, int rows_per_block) {
+  RowTile t;
+  t.x0 = (tile % a.tiles_x) * kRowSeg;
+  const int m = tile / a.tiles_x;
+  t.y0 = (m % a.tiles_y) * rows_per_block;
+  t.n = m / a.tiles_y;
+  return t;
+}
+
+template <int KC, int KCB, int CO, int R, int STAGES, int RB>
+__global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_constant__ ConvArgs a) {
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB>;
+  const long long t_cta = (a.debug != nullptr && threadIdx.x == 0) ? clock64() : 0;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t w_base = a_base + Cfg::A_STAGES * Cfg::A_STAGE;
+  const uint32_t stg_base = w_base + Cfg::W_MAX;
+  const uint32_t bias_base = stg_base + 2 * Cfg::STG;
+  const uint32_t bar_base = bias_base + 256;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::A_STAGES + s); };
+  const uint32_t b_full = bar_base + 16u * Cfg::A_STAGES;
+  auto acc_full = [&](int b) { return b_full + 8u + 8u * b; };
+  auto acc_empty = [&](int b) { return b_full + 24u + 8u * b; };
+  const uint32_t tmem_slot = b_full + 40u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool has_res = a.residual != nullptr;
+  constexpr int RES_CHUNKS = CO / KC;    // A stages of the identity (residual) segment
+  constexpr int RES_BTILES = CO / KCB;   // its weight tiles
+  constexpr int CPB = KCB / KC;          // A chunks per weight tile
+
+  if (threadIdx.x < CO) bias_s[threadIdx.x] = a.bias[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.bmapf);
+    if (has_res) tma_prefetch_desc(&a.bmapi);
+    if (a.mode == kEpiBf16) tma_prefetch_desc(&a.omap);
+    for (int s = 0; s < Cfg::A_STAGES; ++s) {
+      mbar_init(a_full(s), kRowGatherThreads / 32);
+      mbar_init(a_empty(s), 1);
+    }
+    mbar_init(b_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weights: every tile once, resident for the CTA's life
+    if (elect_one()) {
+      int ntl = 0;
+      for (int s = 0; s < a.nseg; ++s) ntl += 3 * (a.seg[s].cin / KCB);
+      mbar_arrive_expect_tx(b_full, ntl * Cfg::B_TILE + (has_res ? RES_BTILES * Cfg::I_TILE : 0));
+      int kbase = 0, idx = 0;
+      for (int s = 0; s < a.nseg; ++s) {
+        const int cin = a.seg[s].cin;
+        for (int cb = 0; cb < cin / KCB; ++cb)
+          for (int kx = 0; kx < 3; ++kx, ++idx)
+            tma_load_2d(w_base + idx * Cfg::B_TILE, &a.bmapf, b_full, kbase + kx * cin + cb * KCB, 0);
+        kbase += 3 * cin;
+      }
+      if (has_res)
+        for (int cb = 0; cb < RES_BTILES; ++cb)
+          tma_load_2d(w_base + ntl * Cfg::B_TILE + cb * Cfg::I_TILE, &a.bmapi, b_full, cb * KCB, 0);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    const uint32_t idesc1 = umma_idesc_f16(kTileM, CO, a.fp16);
+    const uint32_t idesc2 = umma_idesc_f16(kTileM, 2 * CO, a.fp16);
+    const uint32_t idesc3 = umma_idesc_f16(kTileM, 3 * CO, a.fp16);
+    const uint64_t bdesc_base = umma_smem_desc<Cfg::SWB>(w_base);
+    const uint32_t b_lo_base = (uint32_t)bdesc_base, b_hi = (uint32_t)(bdesc_base >> 32);
+    int ntl = 0;
+    for (int s = 0; s < a.nseg; ++s) ntl += 3 * (a.seg[s].cin / KCB);
+    const bool dbg = a.debug != nullptr;
+    long long w_acc = 0, w_a = 0, w_b = 0, t_begin = dbg ? clock64() : 0, t0 = 0;
+    row_warp_wait(b_full, 0, lane);
+    if (dbg) w_b = clock64() - t_begin;
+    tc_fence_after();
+    uint32_t ita = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      if (dbg) t0 = clock64();
+      row_warp_wait(acc_empty(buf), ((tcount >> 1) & 1u) ^ 1u, lane);
+      if (dbg) w_acc += clock64() - t0;
+      tc_fence_after();
+      const uint32_t dbase = tmem_base + buf * Cfg::ACC_COLS;
+      // input row j (0 .. R+1) of the block against the kx tile at b_lo: the slots of [W2|W1|W0] whose output row
+      // (j - 2 + slot) lies inside the block
+      auto issue_row = [&](int j, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t accumulate) {
+        const int lo_slot = j >= 2 ? 0 : 2 - j;
+        const int hi_slot = j <= R - 1 ? 2 : R + 1 - j;
+        const int nslots = hi_slot - lo_slot + 1;
+        const uint32_t idesc = nslots == 3 ? idesc3 : (nslots == 2 ? idesc2 : idesc1);
+        umma_f16_lohi(dbase + (uint32_t)((j - 2 + lo_slot) * CO), a_lo + (uint32_t)((j * kRowPitch) >> 4), a_hi,
+                      b_lo + (uint32_t)((lo_slot * CO * Cfg::SWB) >> 4), b_hi, idesc, accumulate);
+      };
+      uint32_t chunk = 0;
+      for (int s = 0; s < a.nseg; ++s) {
+        for (int cc = 0; cc < a.seg[s].cin / KC; ++cc, ++ita, ++chunk) {
+          const int sta = ita % Cfg::A_STAGES;
+          if (dbg) t0 = clock64();
+          row_warp_wait(a_full(sta), (ita / Cfg::A_STAGES) & 1, lane);
+          if (dbg) w_a += clock64() - t0;
+          tc_fence_after();
+          const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::A_STAGE, Cfg::PLANE_STRIDE, 128);
+          const uint32_t a_lo = (uint32_t)adesc, a_hi = (uint32_t)(adesc >> 32);
+          // weight tile of this chunk: tiles are KCB wide, chunk `chunk` sits (chunk % CPB) * KC channels into its tile
+          const uint32_t b_chunk = b_lo_base + (chunk / CPB) * 3u * (Cfg::B_TILE >> 4) + (chunk % CPB) * (KC / 8u);
+          if (elect_one()) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+              for (int kk = 0; kk < KC / 16; ++kk) {
+                const uint32_t a_k = a_lo + (uint32_t)kx + (uint32_t)(2 * kk) * (Cfg::PLANE_STRIDE >> 4);
+                const uint32_t b_k = b_chunk + (uint32_t)kx * (Cfg::B_TILE >> 4) + 2u * kk;
+                if (kx == 0 && kk == 0 && chunk == 0) {
+                  // first touch of this accumulator buffer: the input rows j = 2, 5, 8, ... cover every output row
+                  // exactly once, so they overwrite (accumulate = 0); everything after accumulates
+#pragma unroll
+                  for (int j = 2; j < R + 2; j += 3) issue_row(j, a_k, a_hi, b_k, 0u);
+#pragma unroll
+                  for (int j = 0; j < R + 2; ++j)
+                    if (j % 3 != 2) issue_row(j, a_k, a_hi, b_k, 1u);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < R + 2; ++j) issue_row(j, a_k, a_hi, b_k, 1u);
+                }
+              }
+            }
+            umma_commit(a_empty(sta));
+          }
+          __syncwarp();
+        }
+      }
+      if (has_res) {
+        // residual: out row r += I * residual row r (gathered like any other source: block row r+1, centre column)
+        for (int cc = 0; cc < RES_CHUNKS; ++cc, ++ita) {
+          const int sta = ita % Cfg::A_STAGES;
+          if (dbg) t0 = clock64();
+          row_warp_wait(a_full(sta), (ita / Cfg::A_STAGES) & 1, lane);
+          if (dbg) w_a += clock64() - t0;
+          tc_fence_after();
+          const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::A_STAGE, Cfg::PLANE_STRIDE, 128);
+          const uint32_t a_lo = (uint32_t)adesc, a_hi = (uint32_t)(adesc >> 32);
+          const uint32_t b_i = b_lo_base + (uint32_t)((ntl * Cfg::B_TILE + (cc / CPB) * Cfg::I_TILE) >> 4) +
+                               (uint32_t)(cc % CPB) * (KC / 8u);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < KC / 16; ++kk) {
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+                umma_f16_lohi(dbase + (uint32_t)(r * CO),
+                              a_lo + (uint32_t)(((r + 1) * kRowPitch) >> 4) + 1u +
+                                  (uint32_t)(2 * kk) * (Cfg::PLANE_STRIDE >> 4),
+                              a_hi, b_i + 2u * kk, b_hi, idesc1, 1u);
+            }
+            umma_commit(a_empty(sta));
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) umma_commit(acc_full(buf));
+      __syncwarp();
+    }
+    if (dbg && lane == 0) {
+      atomicAdd(a.debug + 0, (unsigned long long)w_acc);
+      atomicAdd(a.debug + 1, (unsigned long long)w_a);
+      atomicAdd(a.debug + 2, (unsigned long long)w_b);
+      atomicAdd(a.debug + 3, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(a.debug + 10, 1ull);
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------ epilogue: group g owns rows [g*R/2, (g+1)*R/2)
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;           // TMEM lanes [32q, 32q+32) = pixels [32q, 32q+32) of the row segment
+    const int px = quarter * 32 + lane;
+    const bool leader = (warp - 2) % 4 == 0 && lane == 0;
+    const uint32_t stg = stg_base + g * Cfg::STG;
+    // 16-byte chunk c of pixel px lives at chunk (c ^ swz) of its row: the TMA swizzle of a CO*2-byte wide box
+    const uint32_t swz = CO == 64 ? (uint32_t)(px & 7) : (CO == 32 ? (uint32_t)((px >> 1) & 3) : (uint32_t)((px >> 2) & 1));
+    const uint32_t stg_px = stg + (uint32_t)px * (CO * 2);
+    uint32_t tcount = 0;
+    const bool dbg = a.debug != nullptr && warp == 2 && lane == 0;
+    long long w_full = 0, t_body = 0, t0 = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1u;
+      const RowTile tc = row_decode(a, tile, R);
+      if (dbg) t0 = clock64();
+      row_warp_wait(acc_full(buf), (tcount >> 1) & 1u, lane);
+      if (dbg) { const long long t1 = clock64(); w_full += t1 - t0; t0 = t1; }
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      if (a.mode == kEpiBf16) {
+#pragma unroll 1
+        for (int rb = 0; rb < R / 2; rb += RB) {
+          const int r0 = g * (R / 2) + rb;             // first row of this store box
+          if (tc.y0 + r0 >= a.out_h) break;            // ragged last block (uniform over the group)
+          if (leader) bulk_wait_read_all();            // the previous store has finished reading the staging buffer
+          group_bar(1 + g);
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const uint32_t taddr = tacc + (uint32_t)((r0 + i) * CO);
+#pragma unroll
+            for (int ch = 0; ch < CO / Cfg::CH; ++ch) {
+              uint32_t acc[Cfg::CH];
+              if constexpr (Cfg::CH == 32) tmem_ld_32x32(taddr + ch * 32, reinterpret_cast<uint32_t(&)[32]>(acc));
+              else tmem_ld_32x16(taddr + ch * 16, reinterpret_cast<uint32_t(&)[16]>(acc));
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < Cfg::CH; j += 8) {
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 b2 = *reinterpret_cast<const float2*>(bias_s + ch * Cfg::CH + j + 2 * k);
+                  o[k] = pack16_sat(__uint_as_float(acc[j + 2 * k]) + b2.x, __uint_as_float(acc[j + 2 * k + 1]) + b2.y,
+                                    a.fp16);
+                  if (a.relu) o[k] = relu16x2(o[k], a.fp16);
+                }
+                const uint32_t c = (uint32_t)((ch * Cfg::CH + j) / 8);
+                const uint32_t dst = stg_px + (uint32_t)i * (kRowSeg * CO * 2) + ((c ^ swz) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                             "r"(o[3])
+                             : "memory");
+              }
+            }
+          }
+          group_bar(1 + g);
+          if (leader) {
+            fence_proxy_async();  // the group's staging writes (ordered by the barrier) -> visible to the TMA store
+            tma_store_4d(&a.omap, stg, 0, tc.x0, tc.y0 + r0, tc.n);  // rows beyond the image are clipped by the TMA unit
+            bulk_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int r = g * (R / 2); r < (g + 1) * (R / 2); ++r) {
+          const int y = tc.y0 + r;
+          if (y >= a.out_h) break;
+          uint4 unused[EpiCfg<16>::RV];
+          epilogue_pixel<16>(a, bias_s, 0, tacc + (uint32_t)(r * CO), tc.n, y, tc.x0 + px, true, unused);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
+      if (dbg) t_body += clock64() - t0;
+    }
+    if (dbg) {
+      atomicAdd(a.debug + 8, (unsigned long long)w_full);
+      atomicAdd(a.debug + 9, (unsigned long long)t_body);
+    }
+    if (leader) bulk_wait_all();
+  } else {
+    // ------------------------------------------------------------ gather: (R+2) rows x 130 pixels x KC channels per stage
+    // Thread t owns fixed (plane, pixel) columns of the stage and walks the rows: per copy one bounds test and one
+    // pointer add.  Lanes run over the planes of consecutive pixels, so a warp reads contiguous global memory.
+    // The 128 interior pixels (always inside the image: width % 128 == 0) take (128 * PLANES) / 256 columns per
+    // thread; the two halo pixels (x0-1, x0+128) are 2 * PLANES * ROWS single copies spread over the first threads.
+    constexpr int P = Cfg::PLANES;
+    constexpr int ROWS = Cfg::ROWS;
+    constexpr int COLS_PER_THREAD = (kRowSeg * P) / kRowGatherThreads;  // 2 (KC = 32) or 1 (KC = 16)
+    constexpr int PX_STEP = kRowGatherThreads / P;
+    constexpr int NHALO = 2 * P * ROWS;
+    constexpr int DEPTH = Cfg::A_STAGES - 1;  // cp.async groups kept in flight
+    const int t = threadIdx.x - kRowBaseThreads;
+    const int plane = t % P;
+    const int pxm = t / P;                                    // interior pixel 1 + pxm (+ k * PX_STEP)
+    const uint32_t dst_col = plane * Cfg::PLANE_STRIDE + (1 + pxm) * 16;
+    const bool halo_thread = t < NHALO;
+    const int h_plane = t % P, h_row = (t / P) % ROWS, h_side = t / (P * ROWS);  // side 0: x0-1, side 1: x0+128
+    const uint32_t dst_halo = h_plane * Cfg::PLANE_STRIDE + (h_row * kRowHaloPx + h_side * (kRowHaloPx - 1)) * 16;
+    const int nsrc = a.nseg + (has_res ? 1 : 0);
+    uint32_t it = 0;
+    const bool dbg = a.debug != nullptr && t == 0;
+    long long g_empty = 0, g_issue = 0, g_land = 0, t0 = 0, t_begin = dbg ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const RowTile tc = row_decode(a, tile, R);
+      for (int s = 0; s < nsrc; ++s) {
+        const bool is_res = s >= a.nseg;
+        const int cin = is_res ? CO : a.seg[s].cin;
+        const int up = is_res ? 0 : a.seg[s].up;
+        const int src_w = a.out_w >> up;
+        const size_t row_stride = (size_t)src_w * cin;
+        const __nv_bfloat16* src = is_res ? a.residual : a.src_ptr[s];
+        const __nv_bfloat16* img = src + (size_t)tc.n * (a.out_h >> up) * row_stride;
+        for (int cc = 0; cc < cin / KC; ++cc, ++it) {
+          const int st = it % Cfg::A_STAGES;
+          if (dbg) t0 = clock64();
+          row_warp_wait(a_empty(st), ((it / Cfg::A_STAGES) & 1) ^ 1u, lane);
+          if (dbg) { const long long t1 = clock64(); g_empty += t1 - t0; t0 = t1; }
+          const uint32_t stage = a_base + st * Cfg::A_STAGE;
+          // the residual (identity) segment only reads block rows 1..R and the interior pixels
+          const int j_lo = is_res ? 1 : 0, j_hi = is_res ? ROWS - 1 : ROWS;
+#pragma unroll
+          for (int k = 0; k < COLS_PER_THREAD; ++k) {
+            const int gx = tc.x0 + pxm + k * PX_STEP;
+            const __nv_bfloat16* col = img + (size_t)(gx >> up) * cin + cc * KC + plane * 8;
+            const uint32_t dst = stage + dst_col + k * (PX_STEP * 16);
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+              if (j >= j_lo && j < j_hi) {
+                const int gy = tc.y0 - 1 + j;
+                const bool ok = (unsigned)gy < (unsigned)a.out_h;
+                rcp_async_16(dst + j * kRowPitch, ok ? col + (size_t)(gy >> up) * row_stride : src, ok ? 16u : 0u);
+              }
+            }
+          }
+          if (halo_thread && !is_res) {
+            const int gy = tc.y0 - 1 + h_row, gx = tc.x0 - 1 + h_side * (kRowSeg + 1);
+            const bool ok = ((unsigned)gy < (unsigned)a.out_h) && ((unsigned)gx < (unsigned)a.out_w);
+            const __nv_bfloat16* gp = ok ? img + (size_t)(gy >> up) * row_stride + (size_t)(gx >> up) * cin + cc * KC + h_plane * 8 : src;
+            rcp_async_16(stage + dst_halo, gp, ok ? 16u : 0u);
+          }
+          rcp_async_commit();
+          if (dbg) { const long long t1 = clock64(); g_issue += t1 - t0; t0 = t1; }
+          if (DEPTH == 1 || it >= (uint32_t)(DEPTH - 1)) {
+            rcp_async_wait<DEPTH - 1>();
+            if (dbg) g_land += clock64() - t0;
+            __syncwarp();
+            if (lane == 0) {
+              fence_proxy_async();  // one per warp, after the sync that orders the lanes' writes before it
+              mbar_arrive(a_full((it - (DEPTH - 1)) % Cfg::A_STAGES));
+            }
+          }
+        }
+      }
+    }
+    if (dbg) {
+      atomicAdd(a.debug + 4, (unsigned long long)g_empty);
+      atomicAdd(a.debug + 5, (unsigned long long)g_issue);
+      atomicAdd(a.debug + 6, (unsigned long long)g_land);
+      atomicAdd(a.debug + 7, (unsigned long long)(clock64() - t_begin));
+    }
+    rcp_async_wait<0>();
+    __syncwarp();
+    if (lane == 0) {
+      fence_proxy_async();
+      const uint32_t first = (DEPTH == 1 || it >= (uint32_t)(DEPTH - 1)) ? it - (DEPTH - 1) : 0u;
+      for (uint32_t k = first; k < it; ++k) mbar_arrive(a_full(k % Cfg::A_STAGES));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (a.debug != nullptr && threadIdx.x == 0) atomicAdd(a.debug + 11, (unsigned long long)(clock64() - t_cta));
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+// The three instantiations: <KC, KCB, CO, R, STAGES, RB>
+//   Cout 64 (layer1, decoder block 2 conv2): 32-channel A stages x 2, 128-byte weight tiles, 4-row blocks
+//   Cout 32 (decoder block 3):               16-channel A stages x 3, 8-row blocks
+//   Cout 16 (decoder block 4, head):         16-channel A stages x 4, 8-row blocks, 4 rows per TMA store
+#define IU_ROW_CFG64 32, 64, 64, 4, 2, 1
+#define IU_ROW_CFG32 16, 16, 32, 8, 3, 1
+#define IU_ROW_CFG16 16, 16, 16, 8, 4, 4
+
+template <int KC, int KCB, int CO, int R, int STAGES, int RB>
+static bool row_fits(const ConvArgs& a) {
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB>;
+  int bytes = 0;
+  for (int s = 0; s < a.nseg; ++s) {
+    if (a.seg[s].cin % KCB) return false;
+    bytes += 3 * (a.seg[s].cin / KCB) * Cfg::B_TILE;
+  }
+  if (a.residual != nullptr) bytes += (CO / KCB) * Cfg::I_TILE;
+  return bytes <= Cfg::W_MAX;
+}
+
+int conv_row_kc(int cout_pad) { return cout_pad == 64 ? 64 : 16; }
+int conv_row_store_rows(int cout_pad) { return cout_pad == 16 ? 4 : 1; }
+
+bool conv_row_applicable(const ConvArgs& a) {
+  if (a.nseg < 1 || a.nseg > 2 || a.up2x) return false;
+  for (int s = 0; s < a.nseg; ++s)
+    if (a.seg[s].ksize != 3 || a.seg[s].stride != 1 || a.seg[s].pad != 1 || a.src_ptr[s] == nullptr) return false;
+  if (a.out_w % kRowSeg != 0 || a.out_h < 1) return false;
+  if (a.mode == kEpiBf16) {
+    if (a.cout == 64) return row_fits<IU_ROW_CFG64>(a);
+    if (a.cout == 32) return row_fits<IU_ROW_CFG32>(a);
+    if (a.cout == 16) return row_fits<IU_ROW_CFG16>(a);
+    return false;
+  }
+  // softmax head: the logits occupy the first num_classes of 16 padded output channels
+  return a.residual == nullptr && a.num_classes <= 16 && row_fits<IU_ROW_CFG16>(a);
+}
+
+template <int KC, int KCB, int CO, int R, int STAGES, int RB>
+static cudaError_t launch_row_one(const ConvArgs& args_in, cudaStream_t stream) {
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB>;
+  static int configured_dev = -1;
+  static int num_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_dev != dev) {
+    cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<KC, KCB, CO, R, STAGES, RB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured_dev = dev;
+  }
+  ConvArgs args = args_in;
+  args.tiles_x = args.out_w / kRowSeg;
+  args.tiles_y = (args.out_h + R - 1) / R;
+  args.ntiles_n = 1;
+  args.total_tiles = args.tiles_x * args.tiles_y * args.batch;
+  const int grid = args.total_tiles < num_sms ? args.total_tiles : num_sms;
+  conv_row_kernel<KC, KCB, CO, R, STAGES, RB><<<grid, kRowThreads, Cfg::SMEM_BYTES, stream>>>(args);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_row(const ConvArgs& args, cudaStream_t stream) {
+  if (!conv_row_applicable(args)) return cudaErrorInvalidValue;
+  const int co = args.mode == kEpiBf16 ? args.cout : 16;
+  if (co == 64) return launch_row_one<IU_ROW_CFG64>(args, stream);
+  if (co == 32) return launch_row_one<IU_ROW_CFG32>(args, stream);
+  return launch_row_one<IU_ROW_CFG16>(args, stream);
+}
+
+}  // namespace iu

@@ -206,9 +206,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
         const uint32_t* q = prow + r * (kStemPitch / 2);
         *reinterpret_cast<uint4*>(arow + ((r ^ (m & 7)) << 4)) = make_uint4(q[0], q[1], q[2], q[3]);
       }
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full(st));
+      if (lane == 0) {
+        fence_proxy_async();  // generic-proxy writes (ordered by the warp sync) -> visible to the tensor core's reads
+        mbar_arrive(a_full(st));
+      }
       if (next < total_tiles) store_patch((it + 1) & 1u);
       builders_sync();  // next patch complete; everyone is done reading the current one
     }

@@ -33,6 +33,11 @@ struct alignas(64) ConvArgs {
   CUtensorMap amap[2];  // 4-D maps (C, W, H, N) over the segment sources, box = (KC, tw*stride, th*stride, nb)
   CUtensorMap bmap;     // 2-D map (K, Cout_pad) over the packed weights, box = (KC, BN)
   CUtensorMap bmap2;    // the same weights with box = (64, 64): one CTA's half tile in the CTA-pair kernel
+  // row-folded kernel (conv_row.cu), valid when use_row != 0:
+  CUtensorMap bmapf;    // 2-D map (3*sum(cin), 3*Cout_pad) over the fold-packed weights, box = (row KC, 3*Cout_pad)
+  CUtensorMap bmapi;    // 2-D map over the [Cout][Cout] identity (residual segment), box = (row KC, Cout)
+  CUtensorMap omap;     // 4-D map (Cout, W, H, N) over the output tensor, box = (Cout, 128, store rows, 1): TMA store
+  int use_row;
   ConvSegment seg[2];
   const __nv_bfloat16* src_ptr[2];  // raw pointers of the segment sources (halo kernel: cp.async gathers)
   int nseg;
@@ -76,6 +81,14 @@ cudaError_t launch_conv_halo(const ConvArgs& args, int kc, int bn, cudaStream_t 
 // Cout a multiple of 128; needs `bmap2`.
 bool conv_pair_applicable(const ConvArgs& args);
 cudaError_t launch_conv_pair(const ConvArgs& args, cudaStream_t stream);
+
+// Row-folded variant (conv_row.cu) for stride-1 3x3 convs with Cout_pad in {16, 32, 64} on images whose width is a
+// multiple of 128: vertical taps folded into the MMA's N, residual as an identity K segment, TMA-store epilogue.
+// Needs `bmapf` / `omap` (and `bmapi` with a residual).  conv_row_kc: the K chunk its weight maps are boxed with.
+bool conv_row_applicable(const ConvArgs& args);
+int conv_row_kc(int cout_pad);
+int conv_row_store_rows(int cout_pad);  // output rows per TMA store box (the `omap` box height)
+cudaError_t launch_conv_row(const ConvArgs& args, cudaStream_t stream);
 
 // Stem (conv_stem.cu): Conv2d(1, 64, 7, stride 2, padding 3) + bias + ReLU on the tensor cores.
 //   bmap: 2-D map over the packed 16-bit weights [64 cout][64 k], k = filter_row * 8 + filter_col (col 7 and

@@ -44,6 +44,9 @@ struct ConvLayer {
   int out_hdiv = 1;  // output geometry BEFORE the optional 2x upsample
   __nv_bfloat16* d_w = nullptr;
   float* d_b = nullptr;
+  // row-folded packing (conv_row.cu) for the stride-1 3x3 layers with cout_pad <= 64; nullptr otherwise
+  __nv_bfloat16* d_wf = nullptr;
+  int ktot_f = 0;
 };
 
 struct Plan {
@@ -104,6 +107,8 @@ struct iu_engine {
   int auto_batch_override = 0;  // env IU_AUTO_BATCH: slices per internal batch instead of the automatic choice
   int conv_pair = 0;  // env IU_CONV_PAIR=1 routes the wide layers to the CTA-pair kernel (opt-in: not yet faster end to end)
   int conv_variant = 0;  // 0 = auto (halo kernel where applicable), 1 = per-tap TMA kernel only (env IU_CONV_VARIANT)
+  int conv_row = 1;  // env IU_CONV_ROW=0 keeps the narrow layers off the row-folded kernel
+  __nv_bfloat16* d_ident = nullptr;  // [64][64] identity in the storage format: the residual segment of conv_row.cu
   unsigned long long* d_debug = nullptr;  // env IU_CONV_DEBUG=1: 16 cycle counters per conv layer (development aid)
   int64_t launches = 0;
   size_t weight_bytes = 0;
@@ -274,6 +279,42 @@ void pack_segment(std::vector<uint16_t>& dst, int fp16, int ktot, int kbase, con
               to16(w[(((size_t)co * cin_total + coff + c) * ks + r) * ks + q], fp16);
 }
 
+// Row-folded packing (conv_row.cu): rows = (2 - ky) * cout_pad + co, K = segment -> kx -> channel, so that the
+// [3*cout_pad x KC] tile of one (chunk, kx) holds the three vertical taps side by side in N.
+void pack_fold_segment(std::vector<uint16_t>& dst, int fp16, int ktot_f, int kbase, const float* w, int cout,
+                       int cout_pad, int cin_total, int coff, int cin_s) {
+  for (int co = 0; co < cout; ++co)
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx)
+        for (int c = 0; c < cin_s; ++c)
+          dst[(size_t)((2 - ky) * cout_pad + co) * ktot_f + kbase + kx * cin_s + c] =
+              to16(w[(((size_t)co * cin_total + coff + c) * 3 + ky) * 3 + kx], fp16);
+}
+
+int upload_fold(iu_engine* e, ConvLayer& L, const float* w, int cout, int cin_total, int nsrc, const int* src_cin) {
+  L.ktot_f = 3 * cin_total;
+  std::vector<uint16_t> packed((size_t)3 * L.cout_pad * L.ktot_f, 0);
+  int kbase = 0, coff = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    pack_fold_segment(packed, e->fp16, L.ktot_f, kbase, w, cout, L.cout_pad, cin_total, coff, src_cin[s]);
+    kbase += 3 * src_cin[s];
+    coff += src_cin[s];
+  }
+  IU_CUDA(e, cudaMalloc(&L.d_wf, packed.size() * 2));
+  IU_CUDA(e, cudaMemcpy(L.d_wf, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+  e->weight_bytes += packed.size() * 2;
+  return IU_OK;
+}
+
+int ensure_identity(iu_engine* e) {
+  if (e->d_ident) return IU_OK;
+  std::vector<uint16_t> id(64 * 64, 0);
+  for (int i = 0; i < 64; ++i) id[i * 64 + i] = to16(1.0f, e->fp16);
+  IU_CUDA(e, cudaMalloc(&e->d_ident, id.size() * 2));
+  IU_CUDA(e, cudaMemcpy(e->d_ident, id.data(), id.size() * 2, cudaMemcpyHostToDevice));
+  return IU_OK;
+}
+
 int upload_conv(iu_engine* e, ConvLayer& L, const std::vector<uint16_t>& packed, const std::vector<float>& bias) {
   IU_CUDA(e, cudaMalloc(&L.d_w, packed.size() * 2));
   IU_CUDA(e, cudaMalloc(&L.d_b, (size_t)L.cout_pad * 4));
@@ -289,7 +330,10 @@ void free_weights(iu_engine* e) {
   for (auto& L : e->convs) {
     if (L.d_w) cudaFree(L.d_w);
     if (L.d_b) cudaFree(L.d_b);
+    if (L.d_wf) cudaFree(L.d_wf);
   }
+  if (e->d_ident) cudaFree(e->d_ident);
+  e->d_ident = nullptr;
   e->convs.clear();
   e->tensors.clear();
   if (e->d_stem_w) cudaFree(e->d_stem_w);
@@ -370,12 +414,20 @@ int add_conv(iu_engine* e, const HostTensors& ht, const std::string& name, const
   if (!ds_conv.empty()) pack_segment(packed, e->fp16, L.ktot, kbase, wd.data(), cout, ds_cin, 0, ds_cin, 1);
   int rc = upload_conv(e, L, packed, b);
   if (rc != IU_OK) return rc;
+  if (ds_conv.empty() && ksize == 3 && stride == 1 && !up2x && L.cout_pad <= 64 && L.cout_pad == cout) {
+    rc = upload_fold(e, L, w.data(), cout, cin_total, nsrc, src_cin);
+    if (rc != IU_OK) return rc;
+  }
   e->convs.push_back(L);
   return IU_OK;
 }
 
 int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
   std::string err;
+  {
+    int rc = ensure_identity(e);
+    if (rc != IU_OK) return rc;
+  }
   // ---- stem: encoder.conv1 + bn1 (+ReLU) as a K=64 GEMM on the tensor cores (conv_stem.cu)
   {
     std::vector<float> w, b;
@@ -469,6 +521,9 @@ int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
     std::vector<uint16_t> packed((size_t)16 * L.ktot, 0);
     pack_segment(packed, e->fp16, L.ktot, 0, w, num_classes, 16, 0, 16, 3);
     int rc = upload_conv(e, L, packed, std::vector<float>(b, b + num_classes));
+    if (rc != IU_OK) return rc;
+    const int head_cin = 16;
+    rc = upload_fold(e, L, w, num_classes, 16, 1, &head_cin);
     if (rc != IU_OK) return rc;
     e->convs.push_back(L);
   }
@@ -589,6 +644,22 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
     a.slice_count = batch;
     a.row_block = h;
     a.debug = (e->d_debug && i < 64) ? e->d_debug + 16 * i : nullptr;
+    a.use_row = 0;
+    if (L.d_wf && e->conv_row && conv_row_applicable(a)) {
+      const int kcr = conv_row_kc(L.cout_pad);
+      rc = encode_weight_map(e, &a.bmapf, L.d_wf, L.ktot_f, 3 * L.cout_pad, kcr, 3 * L.cout_pad);
+      if (rc == IU_OK && L.residual >= 0) rc = encode_weight_map(e, &a.bmapi, e->d_ident, 64, 64, kcr, L.cout_pad);
+      if (rc == IU_OK && L.mode == kEpiBf16) {
+        const TensorSpec& to = e->tensors[L.out];
+        rc = encode_act_map(e, &a.omap, p.bufs[L.out], L.cout_pad, w / to.hdiv, h / to.hdiv, bp, L.cout_pad, 128,
+                            conv_row_store_rows(L.cout_pad), 1, 1);
+      }
+      if (rc == IU_OK) a.use_row = 1;
+      else if (rc > 0) {
+        free_plan(e);
+        return rc;
+      }
+    }
   }
   {
     ConvArgs& a = p.stem_epi;
@@ -631,6 +702,7 @@ int auto_batch(const iu_engine* e, int h, int w, int want) {
 cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
   bool has_up = false;
   for (int s = 0; s < a.nseg; ++s) has_up |= a.seg[s].up != 0;
+  if (a.use_row && e->conv_row && e->conv_variant != 1) return launch_conv_row(a, e->stream);
   const bool applicable = conv_halo_applicable(a);
   if (has_up && !applicable) return cudaErrorInvalidValue;
   if (e->conv_pair && e->conv_variant != 1 && kc == 64 && bn == 128 && conv_pair_applicable(a) &&
@@ -754,6 +826,7 @@ int iu_engine_create(int device, iu_engine** out) {
   if (const char* v = getenv("IU_CONV_VARIANT")) e->conv_variant = atoi(v);
   if (const char* v = getenv("IU_AUTO_BATCH")) e->auto_batch_override = atoi(v);
   if (const char* v = getenv("IU_CONV_PAIR")) e->conv_pair = atoi(v);
+  if (const char* v = getenv("IU_CONV_ROW")) e->conv_row = atoi(v);
   if (const char* v = getenv("IU_CONV_DEBUG")) {
     if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(e->d_debug, 0, 64 * 16 * sizeof(unsigned long long));
@@ -1148,6 +1221,7 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
     rc = encode_act_map(e, &a.amap[1], src1, cin1, w_in, h_in, batch, kc, a.tw * stride, a.th * stride, a.nb, stride);
   if (rc == IU_OK) rc = encode_weight_map(e, &a.bmap, d_w, ktot, cout, kc, bn);
   if (rc == IU_OK && kc == 64 && cout % 128 == 0) rc = encode_weight_map(e, &a.bmap2, d_w, ktot, cout, 64, 64);
+  void* d_wf = nullptr;
   if (rc == IU_OK) {
     a.cout = cout;
     a.bias = d_b;
@@ -1159,6 +1233,23 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
     a.mode = kEpiBf16;
     a.src_ptr[0] = (const __nv_bfloat16*)src0;
     a.src_ptr[1] = (const __nv_bfloat16*)src1;
+    if (e->conv_row && ksize == 3 && conv_row_applicable(a) && (rc = ensure_identity(e)) == IU_OK) {
+      const int ktot_f = 3 * cin_total, kcr = conv_row_kc(cout);
+      std::vector<uint16_t> pf((size_t)3 * cout * ktot_f, 0);
+      pack_fold_segment(pf, e->fp16, ktot_f, 0, weight, cout, cout, cin_total, 0, cin0);
+      if (src1) pack_fold_segment(pf, e->fp16, ktot_f, 3 * cin0, weight, cout, cout, cin_total, cin0, cin1);
+      if ((rc = scratch_get(e, pf.size() * 2, &d_wf)) == IU_OK) {
+        cudaMemcpyAsync(d_wf, pf.data(), pf.size() * 2, cudaMemcpyHostToDevice, e->stream);
+        cudaStreamSynchronize(e->stream);  // `pf` is a local
+        rc = encode_weight_map(e, &a.bmapf, d_wf, ktot_f, 3 * cout, kcr, 3 * cout);
+        if (rc == IU_OK && residual) rc = encode_weight_map(e, &a.bmapi, e->d_ident, 64, 64, kcr, cout);
+        if (rc == IU_OK)
+          rc = encode_act_map(e, &a.omap, out, cout, out_w, out_h, batch, cout, 128, conv_row_store_rows(cout), 1, 1);
+        if (rc == IU_OK) a.use_row = 1;
+      }
+    }
+  }
+  if (rc == IU_OK) {
     cudaError_t ce = launch_conv(e, a, kc, bn);
     e->launches += 1;
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
@@ -1167,6 +1258,7 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
   cudaStreamSynchronize(e->stream);
   scratch_put(e, d_w);
   scratch_put(e, d_b);
+  scratch_put(e, d_wf);
   return rc;
 }
 
