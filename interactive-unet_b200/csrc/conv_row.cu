@@ -44,24 +44,26 @@ constexpr int kRowSmemMax = 227 * 1024;
 // KC : channels per gathered A stage          KCB: channels per weight tile (its TMA / UMMA swizzle span is KCB*2 bytes;
 //      a 64-byte span is read by the tensor core with 2-way bank conflicts, so the 64-output layers use 128-byte tiles)
 // CO : output channels (= cout_pad)           R  : output rows per block         STAGES: A ring depth
-// RB : output rows per TMA store (one staging buffer per epilogue group holds RB rows)
-template <int KC, int KCB, int CO, int R, int STAGES, int RB>
+// RB : output rows per TMA store            NSTG: staging buffers (of RB rows) per epilogue group (1 or 2)
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
 struct RowCfg {
   static constexpr int PLANES = KC / 8;
   static constexpr int ROWS = R + 2;
   static constexpr int PLANE_STRIDE = ROWS * kRowPitch + 16;  // (stride / 16) odd: planes start 16 B apart mod 32 banks
-  static constexpr int A_STAGE = (PLANES * PLANE_STRIDE + 1023) / 1024 * 1024;
+  static constexpr int A_STAGE = PLANES * PLANE_STRIDE;  // no-swizzle operand: 16-byte alignment is enough
   static constexpr int A_STAGES = STAGES;
   static constexpr int NF = 3 * CO;         // N of a full-width (three-slot) MMA
   static constexpr int SWB = KCB * 2;       // bytes per weight row = TMA / UMMA swizzle span
   static constexpr int B_TILE = NF * SWB;   // one (segment, KCB chunk, kx) weight tile
   static constexpr int I_TILE = CO * SWB;   // one identity tile (residual segment)
-  static constexpr int STG = RB * kRowSeg * CO * 2;  // staging of RB output row segments
+  static constexpr int STG = RB * kRowSeg * CO * 2;  // one staging buffer: RB output row segments
+  static constexpr int STG_TOTAL = 2 * NSTG * STG;   // two epilogue groups x NSTG buffers
   static constexpr int ACC_COLS = R * CO;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;  // double buffered: 512 / 512 / 256
-  static constexpr int MISC = 1024;  // bias (<= 256 B) + barriers + TMEM slot
-  static constexpr int W_MAX = (kRowSmemMax - 1024 - A_STAGES * A_STAGE - 2 * STG - MISC) / 1024 * 1024;
-  static constexpr int SMEM_BYTES = 1024 + A_STAGES * A_STAGE + W_MAX + 2 * STG + MISC;
+  static constexpr int MISC = 512;  // bias (<= 256 B) + barriers + TMEM slot
+  // layout: [weights W_MAX][staging][A ring][bias, barriers]; the swizzled regions come first (1024-aligned base)
+  static constexpr int W_MAX = (kRowSmemMax - STG_TOTAL - A_STAGES * A_STAGE - MISC) / 1024 * 1024;
+  static constexpr int SMEM_BYTES = W_MAX + STG_TOTAL + A_STAGES * A_STAGE + MISC;
   static constexpr int CH = CO >= 32 ? 32 : 16;  // accumulator columns per tcgen05.ld
   static_assert(KCB % KC == 0 && (KCB == 64 || KCB == 32 || KCB == 16), "weight tile width");
   static_assert((PLANE_STRIDE / 16) % 2 == 1, "plane stride must be an odd number of 16-byte units");
@@ -113,7 +115,8 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
@@ -129,17 +132,17 @@ __device__ __forceinline__ RowTile row_decode(const ConvArgs& a, int tile, int r
   return t;
 }
 
-template <int KC, int KCB, int CO, int R, int STAGES, int RB>
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
 __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_constant__ ConvArgs a) {
-  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB>;
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG>;
   const long long t_cta = (a.debug != nullptr && threadIdx.x == 0) ? clock64() : 0;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t a_base = base;
-  const uint32_t w_base = a_base + Cfg::A_STAGES * Cfg::A_STAGE;
+  if ((raw & 1023u) != 0u) __trap();  // the swizzled regions rely on the 1024-byte alignment of the dynamic window
+  const uint32_t w_base = raw;
   const uint32_t stg_base = w_base + Cfg::W_MAX;
-  const uint32_t bias_base = stg_base + 2 * Cfg::STG;
+  const uint32_t a_base = stg_base + Cfg::STG_TOTAL;
+  const uint32_t bias_base = a_base + Cfg::A_STAGES * Cfg::A_STAGE;
   const uint32_t bar_base = bias_base + 256;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::A_STAGES + s); };
@@ -313,10 +316,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     const int quarter = warp & 3;           // TMEM lanes [32q, 32q+32) = pixels [32q, 32q+32) of the row segment
     const int px = quarter * 32 + lane;
     const bool leader = (warp - 2) % 4 == 0 && lane == 0;
-    const uint32_t stg = stg_base + g * Cfg::STG;
+    const uint32_t stg_g = stg_base + g * NSTG * Cfg::STG;  // this group's staging buffer(s)
+    uint32_t nstore = 0;
     // 16-byte chunk c of pixel px lives at chunk (c ^ swz) of its row: the TMA swizzle of a CO*2-byte wide box
     const uint32_t swz = CO == 64 ? (uint32_t)(px & 7) : (CO == 32 ? (uint32_t)((px >> 1) & 3) : (uint32_t)((px >> 2) & 1));
-    const uint32_t stg_px = stg + (uint32_t)px * (CO * 2);
+    const uint32_t px_off = (uint32_t)px * (CO * 2);
     uint32_t tcount = 0;
     const bool dbg = a.debug != nullptr && warp == 2 && lane == 0;
     long long w_full = 0, t_body = 0, t0 = 0;
@@ -333,7 +337,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         for (int rb = 0; rb < R / 2; rb += RB) {
           const int r0 = g * (R / 2) + rb;             // first row of this store box
           if (tc.y0 + r0 >= a.out_h) break;            // ragged last block (uniform over the group)
-          if (leader) bulk_wait_read_all();            // the previous store has finished reading the staging buffer
+          const uint32_t stg = stg_g + (NSTG == 2 ? (nstore & 1u) * Cfg::STG : 0u);
+          const uint32_t stg_px = stg + px_off;
+          ++nstore;
+          if (leader) {                                // the last store out of this buffer has finished reading it
+            if constexpr (NSTG == 2) bulk_wait_read_1();
+            else bulk_wait_read_0();
+          }
           group_bar(1 + g);
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
@@ -410,7 +420,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     const int nsrc = a.nseg + (has_res ? 1 : 0);
     uint32_t it = 0;
     const bool dbg = a.debug != nullptr && t == 0;
-    long long g_empty = 0, g_issue = 0, g_land = 0, t0 = 0, t_begin = dbg ? clock64() : 0;
+    long long g_empty = 0, g_issue = 0, g_land = 0, g_rest = 0, t0 = 0, t_begin = dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const RowTile tc = row_decode(a, tile, R);
       for (int s = 0; s < nsrc; ++s) {
@@ -453,12 +463,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           if (dbg) { const long long t1 = clock64(); g_issue += t1 - t0; t0 = t1; }
           if (DEPTH == 1 || it >= (uint32_t)(DEPTH - 1)) {
             rcp_async_wait<DEPTH - 1>();
-            if (dbg) g_land += clock64() - t0;
+            if (dbg) { const long long t1 = clock64(); g_land += t1 - t0; t0 = t1; }
             __syncwarp();
             if (lane == 0) {
               fence_proxy_async();  // one per warp, after the sync that orders the lanes' writes before it
               mbar_arrive(a_full((it - (DEPTH - 1)) % Cfg::A_STAGES));
             }
+            if (dbg) g_rest += clock64() - t0;
           }
         }
       }
@@ -468,6 +479,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
       atomicAdd(a.debug + 5, (unsigned long long)g_issue);
       atomicAdd(a.debug + 6, (unsigned long long)g_land);
       atomicAdd(a.debug + 7, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(a.debug + 12, (unsigned long long)g_rest);
     }
     rcp_async_wait<0>();
     __syncwarp();
@@ -485,17 +497,18 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------- host side
-// The three instantiations: <KC, KCB, CO, R, STAGES, RB>
-//   Cout 64 (layer1, decoder block 2 conv2): 32-channel A stages x 2, 128-byte weight tiles, 4-row blocks
+// The three instantiations: <KC, KCB, CO, R, STAGES, RB, NSTG>
+//   Cout 64 (layer1, decoder block 2 conv2): 32-channel A stages x 2, 128-byte weight tiles, 4-row blocks, one
+//                                            staging buffer per group (72-80 KB of resident weights leave no more)
 //   Cout 32 (decoder block 3):               16-channel A stages x 3, 8-row blocks
-//   Cout 16 (decoder block 4, head):         16-channel A stages x 4, 8-row blocks, 4 rows per TMA store
-#define IU_ROW_CFG64 32, 64, 64, 4, 2, 1
-#define IU_ROW_CFG32 16, 16, 32, 8, 3, 1
-#define IU_ROW_CFG16 16, 16, 16, 8, 4, 4
+//   Cout 16 (decoder block 4, head):         16-channel A stages x 4, 8-row blocks, 2 rows per TMA store
+#define IU_ROW_CFG64 32, 64, 64, 4, 2, 1, 1
+#define IU_ROW_CFG32 16, 16, 32, 8, 3, 1, 2
+#define IU_ROW_CFG16 16, 16, 16, 8, 4, 2, 2
 
-template <int KC, int KCB, int CO, int R, int STAGES, int RB>
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
 static bool row_fits(const ConvArgs& a) {
-  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB>;
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG>;
   int bytes = 0;
   for (int s = 0; s < a.nseg; ++s) {
     if (a.seg[s].cin % KCB) return false;
@@ -506,7 +519,7 @@ static bool row_fits(const ConvArgs& a) {
 }
 
 int conv_row_kc(int cout_pad) { return cout_pad == 64 ? 64 : 16; }
-int conv_row_store_rows(int cout_pad) { return cout_pad == 16 ? 4 : 1; }
+int conv_row_store_rows(int cout_pad) { return cout_pad == 16 ? 2 : 1; }
 
 bool conv_row_applicable(const ConvArgs& a) {
   if (a.nseg < 1 || a.nseg > 2 || a.up2x) return false;
@@ -523,15 +536,15 @@ bool conv_row_applicable(const ConvArgs& a) {
   return a.residual == nullptr && a.num_classes <= 16 && row_fits<IU_ROW_CFG16>(a);
 }
 
-template <int KC, int KCB, int CO, int R, int STAGES, int RB>
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
 static cudaError_t launch_row_one(const ConvArgs& args_in, cudaStream_t stream) {
-  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB>;
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG>;
   static int configured_dev = -1;
   static int num_sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<KC, KCB, CO, R, STAGES, RB>,
+    cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -543,7 +556,7 @@ static cudaError_t launch_row_one(const ConvArgs& args_in, cudaStream_t stream) 
   args.ntiles_n = 1;
   args.total_tiles = args.tiles_x * args.tiles_y * args.batch;
   const int grid = args.total_tiles < num_sms ? args.total_tiles : num_sms;
-  conv_row_kernel<KC, KCB, CO, R, STAGES, RB><<<grid, kRowThreads, Cfg::SMEM_BYTES, stream>>>(args);
+  conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG><<<grid, kRowThreads, Cfg::SMEM_BYTES, stream>>>(args);
   return cudaGetLastError();
 }
 

@@ -51,7 +51,7 @@ def main():
             k = 1e-3 / n
             issue = r[3] - r[0] - r[1] - r[2]
             print(f"{i:3d} {int(n):4d} | {r[3]*k:8.1f} {r[0]*k:7.1f} {r[1]*k:7.1f} {r[2]*k:7.1f} {issue*k:7.1f} | "
-                  f"{r[7]*k:8.1f} {r[4]*k:7.1f} {r[5]*k:7.1f} {r[6]*k:7.1f} | {r[8]*k:7.1f} {r[9]*k:7.1f} | {r[11]*k:8.1f}")
+                  f"{r[7]*k:8.1f} {r[4]*k:7.1f} {r[5]*k:7.1f} {r[6]*k:7.1f} | {r[8]*k:7.1f} {r[9]*k:7.1f} | {r[11]*k:8.1f}  rest {r[12]*k:6.1f}")
 
 
 if __name__ == "__main__":
