@@ -328,6 +328,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # exactly ONE line may reach stdout (the driver parses it): libraries that print there (NCCL's version banner,
+    # ...) are sent to stderr for the whole run, and the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved_stdout, "w")
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return

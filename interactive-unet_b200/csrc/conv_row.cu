@@ -1,4 +1,4 @@
-// Row-folded implicit-GEMM 3x3 convolution for the narrow layers (Cout = 16 / 32 / 64, image width % 128 == 0).
+// Row-folded implicit-GEMM 3x3 convolution for the narrow layers (Cout = 16 / 32 / 64, image width >= 128).
 //
 // Why: a tcgen05.mma with M = 128 and both operands in shared memory costs ~42 cycles however small N is (it has
 // to read the 4 KB A tile), so an N = 16 / 32 / 64 MMA runs at 19 / 38 / 66 % of the tensor rate
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           const int y = tc.y0 + r;
           if (y >= a.out_h) break;
           uint4 unused[EpiCfg<16>::RV];
-          epilogue_pixel<16>(a, bias_s, 0, tacc + (uint32_t)(r * CO), tc.n, y, tc.x0 + px, true, unused);
+          epilogue_pixel<16>(a, bias_s, 0, tacc + (uint32_t)(r * CO), tc.n, y, tc.x0 + px, tc.x0 + px < a.out_w, unused);
         }
       }
       tc_fence_before();
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     // ------------------------------------------------------------ gather: (R+2) rows x 130 pixels x KC channels per stage
     // Thread t owns fixed (plane, pixel) columns of the stage and walks the rows: per copy one bounds test and one
     // pointer add.  Lanes run over the planes of consecutive pixels, so a warp reads contiguous global memory.
-    // The 128 interior pixels (always inside the image: width % 128 == 0) take (128 * PLANES) / 256 columns per
+    // The 128 interior pixels take (128 * PLANES) / 256 columns per
     // thread; the two halo pixels (x0-1, x0+128) are 2 * PLANES * ROWS single copies spread over the first threads.
     constexpr int P = Cfg::PLANES;
     constexpr int ROWS = Cfg::ROWS;
@@ -442,13 +442,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < COLS_PER_THREAD; ++k) {
             const int gx = tc.x0 + pxm + k * PX_STEP;
+            const bool xok = gx < a.out_w;  // only the last segment of a row can be ragged (width % 128 != 0)
             const __nv_bfloat16* col = img + (size_t)(gx >> up) * cin + cc * KC + plane * 8;
             const uint32_t dst = stage + dst_col + k * (PX_STEP * 16);
 #pragma unroll
             for (int j = 0; j < ROWS; ++j) {
               if (j >= j_lo && j < j_hi) {
                 const int gy = tc.y0 - 1 + j;
-                const bool ok = (unsigned)gy < (unsigned)a.out_h;
+                const bool ok = xok && (unsigned)gy < (unsigned)a.out_h;
                 rcp_async_16(dst + j * kRowPitch, ok ? col + (size_t)(gy >> up) * row_stride : src, ok ? 16u : 0u);
               }
             }
@@ -525,7 +526,10 @@ bool conv_row_applicable(const ConvArgs& a) {
   if (a.nseg < 1 || a.nseg > 2 || a.up2x) return false;
   for (int s = 0; s < a.nseg; ++s)
     if (a.seg[s].ksize != 3 || a.seg[s].stride != 1 || a.seg[s].pad != 1 || a.src_ptr[s] == nullptr) return false;
-  if (a.out_w % kRowSeg != 0 || a.out_h < 1) return false;
+  // any width >= 128: a ragged last segment is zero-filled by the gather and clipped by the TMA store; below 60 %
+  // column utilisation the 16x16-block kernels are the better fit
+  const int segs = (a.out_w + kRowSeg - 1) / kRowSeg;
+  if (a.out_w < kRowSeg || a.out_w * 5 < 3 * kRowSeg * segs || a.out_h < 1) return false;
   if (a.mode == kEpiBf16) {
     if (a.cout == 64) return row_fits<IU_ROW_CFG64>(a);
     if (a.cout == 32) return row_fits<IU_ROW_CFG32>(a);
@@ -551,7 +555,7 @@ static cudaError_t launch_row_one(const ConvArgs& args_in, cudaStream_t stream) 
     configured_dev = dev;
   }
   ConvArgs args = args_in;
-  args.tiles_x = args.out_w / kRowSeg;
+  args.tiles_x = (args.out_w + kRowSeg - 1) / kRowSeg;
   args.tiles_y = (args.out_h + R - 1) / R;
   args.ntiles_n = 1;
   args.total_tiles = args.tiles_x * args.tiles_y * args.batch;

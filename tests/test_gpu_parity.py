@@ -77,7 +77,7 @@ CONV_CASES = [
     ("upsrc_tiny_8x8", 8, 8, 8, 512, 256, 256, 3, 1, False, True, "src"),
     ("upsrc_ragged_40x24", 8, 40, 24, 64, 64, 32, 3, 1, False, True, "src"),
     ("stat_k64n64_big", 8, 64, 64, 64, 0, 64, 3, 1, True, True, False),
-    # image width % 128 == 0 and Cout <= 64: the row-folded kernel (vertical taps folded into N, identity-segment
+    # image width >= 128 and Cout <= 64: the row-folded kernel (vertical taps folded into N, identity-segment
     # residual, TMA-store epilogue) in the "row" variant; ragged heights against its 4- / 8-row blocks
     ("row_k64n64", 8, 12, 128, 64, 0, 64, 3, 1, False, True, False),
     ("row_k64n64_res", 8, 10, 128, 64, 0, 64, 3, 1, True, True, False),
@@ -87,6 +87,10 @@ CONV_CASES = [
     ("row_upsrc_k32n16", 8, 12, 256, 32, 0, 16, 3, 1, False, True, "src"),
     ("row_k16n16", 8, 9, 256, 16, 0, 16, 3, 1, False, True, False),
     ("row_k16n16_tall", 8, 40, 128, 16, 0, 16, 3, 1, False, True, False),
+    # ragged last row segment (width % 128 != 0)
+    ("row_ragged_w160_k64n64", 8, 8, 160, 64, 0, 64, 3, 1, True, True, False),
+    ("row_ragged_w320_upsrc_cat_n32", 8, 12, 320, 64, 64, 32, 3, 1, False, True, "src"),
+    ("row_ragged_w200_k16n16", 8, 10, 200, 16, 0, 16, 3, 1, False, True, False),
 ]
 
 
@@ -252,7 +256,7 @@ def _check_probs(got, want):
 
 
 @pytest.mark.parametrize("c", [2, 4])
-@pytest.mark.parametrize("size", [64, 128, 256, 512])
+@pytest.mark.parametrize("size", [64, 128, 256, 320, 512])
 def test_forward_matches_fp32_oracle(dev, fitted, c, size):
     from oracle import synth
     ref, model = fitted[c]

@@ -1,0 +1,52 @@
+"""Multi-GPU check (torchrun, one rank per GPU): the z-slab sharded prediction over NCCL must equal the
+single-GPU prediction of the same volume bit for bit.  Rank 0 prints the verdict."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import interactive_unet_b200 as iu  # noqa: E402
+from interactive_unet_b200 import distributed as iud  # noqa: E402
+from oracle import synth  # noqa: E402  (seeded synthetic weights / volume only)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for n, c in ((128, 2), (256, 4)):
+        if n % world or (n // world) % 1:
+            continue
+        ref = synth.make_model(c)
+        model = iu.UNet(num_classes=c)
+        model.load_state_dict(ref.state_dict())
+        model = model.to(dev).eval()
+        eng = model.engine()
+        vol = torch.from_numpy(synth.blob_volume(n, 21)[0]).to(dev)
+        window = iu.gaussian_window_1d(n)
+        res = iud.predict_volume_sharded(eng, vol, axes=(0, 1, 2), window=window)
+        t, z0 = res["t"], res["z0"]
+        want_u8 = torch.empty((n, n, n, c), dtype=torch.uint8, device=dev)
+        want_lab = torch.empty((n, n, n), dtype=torch.uint8, device=dev)
+        eng.predict_volume(vol, axes=(0, 1, 2), window=window, out_u8=want_u8, out_labels=want_lab)
+        same = torch.equal(res["u8"], want_u8[z0:z0 + t]) and torch.equal(res["labels"], want_lab[z0:z0 + t])
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        full = iud.gather_slabs(res["u8"], dst=0)
+        if rank == 0:
+            whole = torch.equal(full, want_u8)
+            print(f"edge {n} classes {c} world {world}: slabs bit-identical on every rank = {bool(flag.item())}, "
+                  f"gathered volume identical = {whole}")
+            ok = ok and bool(flag.item()) and whole
+    if rank == 0:
+        print("SHARDED_CHECK", "PASS" if ok else "FAIL")
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
