@@ -8,7 +8,8 @@ import os
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libiunet_b200.so")
+# IU_LIB: development override (kernel-variant A/B runs built by tools/build_variant.py)
+LIB_PATH = os.environ.get("IU_LIB") or os.path.join(_PKG_DIR, "libiunet_b200.so")
 
 ABI_VERSION = 1
 IU_OK, IU_ERR_INVALID, IU_ERR_CUDA, IU_ERR_OOM, IU_ERR_STATE = 0, 1, 2, 3, 4

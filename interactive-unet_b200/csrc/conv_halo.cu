@@ -25,7 +25,19 @@ constexpr int kHaloW = kHaloTile + 2;                // 18 halo pixels per edge
 constexpr int kHaloPix = kHaloW * kHaloW;            // 324
 constexpr int kPlaneStride = kHaloPix * 16 + 16;     // 5200 B; (stride / 16) is odd -> conflict-free cp.async stores
 constexpr int kHaloBaseThreads = 320;                // warps 0-9: weight producer, MMA issuer, 8 epilogue warps
-constexpr int kHaloSmemBudget = 200 * 1024;
+#ifndef IU_HALO_BUDGET_KB
+#define IU_HALO_BUDGET_KB 200
+#endif
+#ifndef IU_HALO_A64_STAGES
+#define IU_HALO_A64_STAGES 3
+#endif
+#ifndef IU_PAIR_A_STAGES
+#define IU_PAIR_A_STAGES 3
+#endif
+#ifndef IU_PAIR_B_STAGES
+#define IU_PAIR_B_STAGES 8
+#endif
+constexpr int kHaloSmemBudget = IU_HALO_BUDGET_KB * 1024;
 constexpr int kMaxBias = 512;
 
 // STAT: the layer's whole weight matrix stays resident in shared memory (loaded once per CTA) -- every layer with
@@ -38,7 +50,7 @@ struct HaloCfg {
   static constexpr int THREADS = kHaloBaseThreads + GATHER_THREADS;
   static constexpr int PLANES = KC / 8;
   static constexpr int A_STAGE = (PLANES * kPlaneStride + 1023) / 1024 * 1024;
-  static constexpr int A_STAGES = KC == 64 ? 3 : 4;
+  static constexpr int A_STAGES = KC == 64 ? (STAT ? 3 : IU_HALO_A64_STAGES) : 4;
   static constexpr int SW = KC * 2;
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int B_ALLOC = (B_BYTES + 1023) / 1024 * 1024;
@@ -194,7 +206,7 @@ __global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN
           if (dbg) t0 = clock64();
           warp_wait(a_full(sta), (ita / Cfg::A_STAGES) & 1, lane);
           if (dbg) w_a += clock64() - t0;
-          tc_fence_after();
+          operand_ready_fence();
           // Descriptors: one base per stage; every (tap, k-step, M tile) is base.lo + a compile-time constant
           // (in 16-byte units), so issuing an MMA costs one integer add instead of a bit-field rebuild.
           const uint64_t adesc_base = umma_smem_desc_planar(a_base + sta * Cfg::A_STAGE, kPlaneStride, kHaloW * 16);
@@ -224,15 +236,16 @@ __global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN
               if (dbg) t0 = clock64();
               warp_wait(b_full(stb), (itb / Cfg::B_STAGES) & 1, lane);
               if (dbg) w_b += clock64() - t0;
-              tc_fence_after();
+              operand_ready_fence();
               const int r = tap / 3, q = tap - 3 * r;
               const uint32_t b_lo = b_lo_base + stb * (Cfg::B_ALLOC >> 4);
+              const uint32_t a_tap = a_lo + (uint32_t)(r * kHaloW + q);
               if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < KC / 16; ++kk) {
-                  const uint32_t a_off = (uint32_t)(r * kHaloW + q) + (uint32_t)(2 * kk) * (kPlaneStride >> 4);
-                  umma_f16_lohi(tmem_d0, a_lo + a_off, a_hi, b_lo + 2u * kk, b_hi, idesc, accumulate);
-                  umma_f16_lohi(tmem_d1, a_lo + a_off + 8u, a_hi, b_lo + 2u * kk, b_hi, idesc, accumulate);
+                  const uint32_t a_off = (uint32_t)(2 * kk) * (kPlaneStride >> 4);
+                  umma_f16_lohi(tmem_d0, a_tap + a_off, a_hi, b_lo + 2u * kk, b_hi, idesc, accumulate);
+                  umma_f16_lohi(tmem_d1, a_tap + a_off + 8u, a_hi, b_lo + 2u * kk, b_hi, idesc, accumulate);
                   accumulate = 1;
                 }
                 umma_commit(b_empty(stb));
@@ -382,9 +395,9 @@ struct PairCfg {
   static constexpr int THREADS = kHaloBaseThreads + GATHER_THREADS;
   static constexpr int PLANES = KC / 8;
   static constexpr int A_STAGE = (PLANES * kPlaneStride + 1023) / 1024 * 1024;
-  static constexpr int A_STAGES = 3;
+  static constexpr int A_STAGES = IU_PAIR_A_STAGES;
   static constexpr int B_HALF_BYTES = (BN / 2) * KC * 2;  // 8 KB: this CTA's 64 weight rows of one (chunk, tap)
-  static constexpr int B_STAGES = 8;
+  static constexpr int B_STAGES = IU_PAIR_B_STAGES;
   static constexpr int TMEM_COLS = 4 * BN;                // 2 M tiles x 2 buffers
   static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4;
   static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_HALF_BYTES + kMaxBias * 4 + NBAR * 8 + 16 + 1024;
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(PairCfg::THREADS, 1) conv_pair_kernel(const __
             if (lane == 0) mbar_wait_cluster(a_full(sta), (ita / Cfg::A_STAGES) & 1);
             __syncwarp();
             if (dbg) w_a += clock64() - t0;
-            tc_fence_after();
+            operand_ready_fence();
             const uint64_t adesc_base = umma_smem_desc_planar(a_base + sta * Cfg::A_STAGE, kPlaneStride, kHaloW * 16);
             const uint32_t a_lo = (uint32_t)adesc_base, a_hi = (uint32_t)(adesc_base >> 32);
 #pragma unroll
@@ -504,7 +517,7 @@ __global__ void __launch_bounds__(PairCfg::THREADS, 1) conv_pair_kernel(const __
               if (lane == 0) mbar_wait_cluster(b_full(stb), (itb / Cfg::B_STAGES) & 1);
               __syncwarp();
               if (dbg) w_b += clock64() - t0;
-              tc_fence_after();
+              operand_ready_fence();
               const int r = tap / 3, q = tap - 3 * r;
               const uint32_t b_lo = b_lo_base + stb * (Cfg::B_HALF_BYTES >> 4);
               if (elect_one()) {

@@ -22,8 +22,8 @@
 //     of the 128-pixel row (a contiguous 128*CO*2-byte run of the NHWC tensor).  The per-lane 16-byte global
 //     stores of the generic epilogue cost 32 L1 wavefronts per instruction and were the bottleneck of layer1.
 //   * all weight tiles of the layer stay resident in shared memory (loaded once per CTA by TMA).
-// Warp roles (576 threads, one persistent CTA per SM): warp 0 weight TMA, warp 1 MMA issue, warps 2-9 epilogue
-// (two groups of four, alternating output rows), warps 10-17 gather (cp.async).
+// Warp roles (640 threads, one persistent CTA per SM): warp 0 weight TMA, warp 1 MMA issue, warps 2-9 epilogue
+// (two groups of four, each owning half of the block's rows), eight of the warps 10-19 gather (cp.async).
 //
 // Replaces the same cuDNN conv2d / batch_norm / relu / add / cat / upsample / softmax launches as conv_tc.cu
 // (`smp.Unet.forward` under `/root/reference/interactive_unet/unet.py:67`).
@@ -36,15 +36,21 @@ namespace iu {
 constexpr int kRowSeg = 128;               // output pixels per M tile (one image-row segment)
 constexpr int kRowHaloPx = kRowSeg + 2;    // gathered pixels per row: x0-1 .. x0+128
 constexpr int kRowPitch = kRowHaloPx * 16;  // bytes per gathered row inside a plane
-constexpr int kRowBaseThreads = 320;       // warps 0-9
-constexpr int kRowGatherThreads = 256;     // warps 10-17
-constexpr int kRowThreads = kRowBaseThreads + kRowGatherThreads;
+constexpr int kRowGatherThreads = 256;     // 8 gather warps
+// Warps are bound to the SM's four schedulers by (warp id % 4).  The MMA issuer is warp 1; the gather warps are the
+// ids >= 10 with id % 4 != 1 (10,11,12,14,15,16,18,19), ids 13 and 17 idle, so that the issuer's scheduler hosts only
+// itself and two epilogue warps (TMEM lane quarter 1 needs them there): tools/contention_probe.cu shows ALU-busy
+// warps on the issuer's scheduler slowing a small-N MMA stream by 25 %.
+constexpr int kRowThreads = 640;
 constexpr int kRowSmemMax = 227 * 1024;
 
 // KC : channels per gathered A stage          KCB: channels per weight tile (its TMA / UMMA swizzle span is KCB*2 bytes;
 //      a 64-byte span is read by the tensor core with 2-way bank conflicts, so the 64-output layers use 128-byte tiles)
 // CO : output channels (= cout_pad)           R  : output rows per block         STAGES: A ring depth
-// RB : output rows per TMA store            NSTG: staging buffers (of RB rows) per epilogue group (1 or 2)
+// RB : output rows per TMA store            NSTG: staging buffers (of RB rows) per epilogue group (1 or 2).
+//      Direct 16-byte global stores from the epilogue lanes were measured SLOWER even for 32 / 64 bytes per pixel
+//      (dec3/dec4 layers +7..14 %): they share the LSU / L1 wavefront queue with the gather's cp.async traffic,
+//      which is the scarcer resource; the TMA store bypasses it.
 template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
 struct RowCfg {
   static constexpr int PLANES = KC / 8;
@@ -65,6 +71,7 @@ struct RowCfg {
   static constexpr int W_MAX = (kRowSmemMax - STG_TOTAL - A_STAGES * A_STAGE - MISC) / 1024 * 1024;
   static constexpr int SMEM_BYTES = W_MAX + STG_TOTAL + A_STAGES * A_STAGE + MISC;
   static constexpr int CH = CO >= 32 ? 32 : 16;  // accumulator columns per tcgen05.ld
+  static_assert(NSTG == 1 || NSTG == 2, "one or two staging buffers per epilogue group");
   static_assert(KCB % KC == 0 && (KCB == 64 || KCB == 32 || KCB == 16), "weight tile width");
   static_assert((PLANE_STRIDE / 16) % 2 == 1, "plane stride must be an odd number of 16-byte units");
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     long long w_acc = 0, w_a = 0, w_b = 0, t_begin = dbg ? clock64() : 0, t0 = 0;
     row_warp_wait(b_full, 0, lane);
     if (dbg) w_b = clock64() - t_begin;
-    tc_fence_after();
+    operand_ready_fence();
     uint32_t ita = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1u;
@@ -232,7 +239,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         const int hi_slot = j <= R - 1 ? 2 : R + 1 - j;
         const int nslots = hi_slot - lo_slot + 1;
         const uint32_t idesc = nslots == 3 ? idesc3 : (nslots == 2 ? idesc2 : idesc1);
+#ifdef IU_EXP_A_ALIGNED  // timing experiment only (wrong results): 128-byte aligned A rows
+        umma_f16_lohi(dbase + (uint32_t)((j - 2 + lo_slot) * CO), (a_lo & ~7u) + (uint32_t)((j * 2048) >> 4), a_hi,
+#else
         umma_f16_lohi(dbase + (uint32_t)((j - 2 + lo_slot) * CO), a_lo + (uint32_t)((j * kRowPitch) >> 4), a_hi,
+#endif
                       b_lo + (uint32_t)((lo_slot * CO * Cfg::SWB) >> 4), b_hi, idesc, accumulate);
       };
       uint32_t chunk = 0;
@@ -242,7 +253,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           if (dbg) t0 = clock64();
           row_warp_wait(a_full(sta), (ita / Cfg::A_STAGES) & 1, lane);
           if (dbg) w_a += clock64() - t0;
-          tc_fence_after();
+          operand_ready_fence();
           const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::A_STAGE, Cfg::PLANE_STRIDE, 128);
           const uint32_t a_lo = (uint32_t)adesc, a_hi = (uint32_t)(adesc >> 32);
           // weight tile of this chunk: tiles are KCB wide, chunk `chunk` sits (chunk % CPB) * KC channels into its tile
@@ -280,7 +291,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           if (dbg) t0 = clock64();
           row_warp_wait(a_full(sta), (ita / Cfg::A_STAGES) & 1, lane);
           if (dbg) w_a += clock64() - t0;
-          tc_fence_after();
+          operand_ready_fence();
           const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::A_STAGE, Cfg::PLANE_STRIDE, 128);
           const uint32_t a_lo = (uint32_t)adesc, a_hi = (uint32_t)(adesc >> 32);
           const uint32_t b_i = b_lo_base + (uint32_t)((ntl * Cfg::B_TILE + (cc / CPB) * Cfg::I_TILE) >> 4) +
@@ -332,7 +343,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
       if (dbg) { const long long t1 = clock64(); w_full += t1 - t0; t0 = t1; }
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+#ifdef IU_EXP_NO_EPI
+      if (false) {
+#else
       if (a.mode == kEpiBf16) {
+#endif
 #pragma unroll 1
         for (int rb = 0; rb < R / 2; rb += RB) {
           const int r0 = g * (R / 2) + rb;             // first row of this store box
@@ -379,7 +394,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
             bulk_commit();
           }
         }
+#ifdef IU_EXP_NO_EPI
+      } else if (false) {
+#else
       } else {
+#endif
 #pragma unroll 1
         for (int r = g * (R / 2); r < (g + 1) * (R / 2); ++r) {
           const int y = tc.y0 + r;
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
       atomicAdd(a.debug + 9, (unsigned long long)t_body);
     }
     if (leader) bulk_wait_all();
-  } else {
+  } else if ((warp & 3) != 1) {
     // ------------------------------------------------------------ gather: (R+2) rows x 130 pixels x KC channels per stage
     // Thread t owns fixed (plane, pixel) columns of the stage and walks the rows: per copy one bounds test and one
     // pointer add.  Lanes run over the planes of consecutive pixels, so a warp reads contiguous global memory.
@@ -410,7 +429,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     constexpr int PX_STEP = kRowGatherThreads / P;
     constexpr int NHALO = 2 * P * ROWS;
     constexpr int DEPTH = Cfg::A_STAGES - 1;  // cp.async groups kept in flight
-    const int t = threadIdx.x - kRowBaseThreads;
+    const int gw = warp - 10;
+    const int t = (gw - (gw + 1) / 4) * 32 + lane;            // rank among the gather warps * 32 + lane
     const int plane = t % P;
     const int pxm = t / P;                                    // interior pixel 1 + pxm (+ k * PX_STEP)
     const uint32_t dst_col = plane * Cfg::PLANE_STRIDE + (1 + pxm) * 16;
@@ -450,7 +470,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
               if (j >= j_lo && j < j_hi) {
                 const int gy = tc.y0 - 1 + j;
                 const bool ok = xok && (unsigned)gy < (unsigned)a.out_h;
+#ifndef IU_EXP_NO_GATHER
                 rcp_async_16(dst + j * kRowPitch, ok ? col + (size_t)(gy >> up) * row_stride : src, ok ? 16u : 0u);
+#else
+                (void)ok; (void)dst; (void)col;
+#endif
               }
             }
           }

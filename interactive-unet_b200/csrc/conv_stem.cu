@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
     const uint32_t b_lo = (uint32_t)bdesc, b_hi = (uint32_t)(bdesc >> 32);
     if (lane == 0) mbar_wait(b_full, 0);
     __syncwarp();
-    tc_fence_after();
+    operand_ready_fence();
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u;

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
             const int st = it % Cfg::STAGES;
             const uint32_t ph = (it / Cfg::STAGES) & 1;
             mbar_wait(full_bar(st), ph);
-            tc_fence_after();
+            operand_ready_fence();
             for (int j = 0; j < tps; ++j) {
               const uint32_t sa = base + st * Cfg::STAGE_BYTES + j * Cfg::TAP_BYTES;
               const uint64_t adesc = umma_smem_desc<Cfg::SW>(sa);

@@ -51,10 +51,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (a CUDA error the host reports),
 // never as a hung GPU.  ~2^28 polls is seconds; a healthy wait is microseconds.
+// Waiters back off between polls: with ~17 warps of a CTA spinning on mbarrier.try_wait the MMA issuer's stream ran
+// 10-35 % slower (profiles/r01_role_counters_v6.txt); 32 ns costs nothing measurable in wake-up latency.
+#ifndef IU_WAIT_BACKOFF
+#define IU_WAIT_BACKOFF 32
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++polls > (1u << 28)) __trap();
+    if (IU_WAIT_BACKOFF > 0) __nanosleep(IU_WAIT_BACKOFF);
   }
 }
 
@@ -90,6 +96,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// After an mbarrier wait that only says "the shared-memory OPERANDS of the next MMAs have landed" (TMA complete_tx, or
+// cp.async + fence.proxy.async on the producer side).  No tcgen05 state crosses threads there, so no tcgen05 fence is
+// needed -- and an after_thread_sync fence in the issue stream makes the following MMAs wait for the previous ones to
+// drain: with one fence per 4-30 MMAs every kernel ran at ~half the tensor-pipe rate (profiles/r01_fence_finding.txt).
+// The fence stays after waits that hand TMEM between the MMA issuer and the epilogue (accumulator full / empty).
+// -DIU_OPERAND_FENCE=1 restores the old behaviour for A/B runs.
+__device__ __forceinline__ void operand_ready_fence() {
+#if defined(IU_OPERAND_FENCE) && IU_OPERAND_FENCE
+  tc_fence_after();
+#endif
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T, fp16/bf16 inputs (per idesc), fp32 accumulate; issued by ONE thread.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
