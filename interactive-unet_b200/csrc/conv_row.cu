@@ -16,6 +16,11 @@
 //     of 130 pixels: input row i, filter column kx is the same buffer through a descriptor shifted by
 //     i * pitch + kx * 16 bytes (SBO = 128 B: the eight-pixel core matrices of a row are contiguous).  The 2x nearest
 //     upsample of the decoder (`src = dst >> 1`) and the channel concat are folded into the gather as before;
+//   * an UPSAMPLED source (decoder conv1: `F.interpolate(x, 2x nearest)`) is never expanded vertically: the block
+//     gathers its R/2+2 SOURCE rows (each pixel still written twice along x), and because upsampled rows 2s and 2s+1
+//     are the same data, source row s feeds output rows 2s-1 .. 2s+2 with the pre-summed weights
+//     [W(ky=2) | W(1)+W(2) | W(0)+W(1) | W(ky=0)]: one N = 4*CO MMA per source row instead of two N = 3*CO MMAs, and
+//     half the gather traffic (the gather's cp.async rate, ~20 B/clk/SM, is what bounds those layers);
 //   * a residual (ResNet shortcut) is one more K segment against an identity weight tile: the tensor core adds it,
 //     the epilogue never touches global memory for it;
 //   * epilogue: TMEM -> registers -> bias / ReLU / 16-bit pack -> swizzled shared-memory staging -> ONE TMA store
@@ -62,6 +67,8 @@ struct RowCfg {
   static constexpr int SWB = KCB * 2;       // bytes per weight row = TMA / UMMA swizzle span
   static constexpr int B_TILE = NF * SWB;   // one (segment, KCB chunk, kx) weight tile
   static constexpr int I_TILE = CO * SWB;   // one identity tile (residual segment)
+  static constexpr int U_TILE = 4 * CO * SWB;  // one weight tile of an upsampled segment (four slots, see below)
+  static constexpr int ROWS_UP = R / 2 + 2;    // source rows an upsampled segment gathers per block
   static constexpr int STG = RB * kRowSeg * CO * 2;  // one staging buffer: RB output row segments
   static constexpr int STG_TOTAL = 2 * NSTG * STG;   // two epilogue groups x NSTG buffers
   static constexpr int ACC_COLS = R * CO;
@@ -195,20 +202,27 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
   if (warp == 0) {
     // ------------------------------------------------------------ weights: every tile once, resident for the CTA's life
     if (elect_one()) {
-      int ntl = 0;
-      for (int s = 0; s < a.nseg; ++s) ntl += 3 * (a.seg[s].cin / KCB);
-      mbar_arrive_expect_tx(b_full, ntl * Cfg::B_TILE + (has_res ? RES_BTILES * Cfg::I_TILE : 0));
-      int kbase = 0, idx = 0;
+      // segment 0 may be an upsampled source (four-slot tiles from `bmapu`); the others use the three-slot tiles
+      const int up0 = a.seg[0].up;
+      uint32_t wbytes = 0;
+      for (int s = 0; s < a.nseg; ++s) wbytes += 3 * (a.seg[s].cin / KCB) * ((s == 0 && up0) ? Cfg::U_TILE : Cfg::B_TILE);
+      mbar_arrive_expect_tx(b_full, wbytes + (has_res ? RES_BTILES * Cfg::I_TILE : 0));
+      int kbase = 0;
+      uint32_t off = 0;
       for (int s = 0; s < a.nseg; ++s) {
         const int cin = a.seg[s].cin;
+        const bool upseg = s == 0 && up0;
         for (int cb = 0; cb < cin / KCB; ++cb)
-          for (int kx = 0; kx < 3; ++kx, ++idx)
-            tma_load_2d(w_base + idx * Cfg::B_TILE, &a.bmapf, b_full, kbase + kx * cin + cb * KCB, 0);
+          for (int kx = 0; kx < 3; ++kx) {
+            if (upseg) tma_load_2d(w_base + off, &a.bmapu, b_full, kx * cin + cb * KCB, 0);
+            else tma_load_2d(w_base + off, &a.bmapf, b_full, kbase + kx * cin + cb * KCB, 0);
+            off += upseg ? Cfg::U_TILE : Cfg::B_TILE;
+          }
         kbase += 3 * cin;
       }
       if (has_res)
         for (int cb = 0; cb < RES_BTILES; ++cb)
-          tma_load_2d(w_base + ntl * Cfg::B_TILE + cb * Cfg::I_TILE, &a.bmapi, b_full, cb * KCB, 0);
+          tma_load_2d(w_base + off + cb * Cfg::I_TILE, &a.bmapi, b_full, cb * KCB, 0);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
@@ -217,8 +231,10 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     const uint32_t idesc3 = umma_idesc_f16(kTileM, 3 * CO, a.fp16);
     const uint64_t bdesc_base = umma_smem_desc<Cfg::SWB>(w_base);
     const uint32_t b_lo_base = (uint32_t)bdesc_base, b_hi = (uint32_t)(bdesc_base >> 32);
-    int ntl = 0;
-    for (int s = 0; s < a.nseg; ++s) ntl += 3 * (a.seg[s].cin / KCB);
+    const uint32_t idesc4 = umma_idesc_f16(kTileM, 4 * CO, a.fp16);
+    const int up0 = a.seg[0].up;
+    uint32_t wbytes = 0;  // bytes of all conv weight tiles = offset of the identity tiles
+    for (int s = 0; s < a.nseg; ++s) wbytes += 3 * (a.seg[s].cin / KCB) * ((s == 0 && up0) ? Cfg::U_TILE : Cfg::B_TILE);
     const bool dbg = a.debug != nullptr;
     long long w_acc = 0, w_a = 0, w_b = 0, t_begin = dbg ? clock64() : 0, t0 = 0;
     row_warp_wait(b_full, 0, lane);
@@ -239,15 +255,24 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         const int hi_slot = j <= R - 1 ? 2 : R + 1 - j;
         const int nslots = hi_slot - lo_slot + 1;
         const uint32_t idesc = nslots == 3 ? idesc3 : (nslots == 2 ? idesc2 : idesc1);
-#ifdef IU_EXP_A_ALIGNED  // timing experiment only (wrong results): 128-byte aligned A rows
-        umma_f16_lohi(dbase + (uint32_t)((j - 2 + lo_slot) * CO), (a_lo & ~7u) + (uint32_t)((j * 2048) >> 4), a_hi,
-#else
         umma_f16_lohi(dbase + (uint32_t)((j - 2 + lo_slot) * CO), a_lo + (uint32_t)((j * kRowPitch) >> 4), a_hi,
-#endif
+                      b_lo + (uint32_t)((lo_slot * CO * Cfg::SWB) >> 4), b_hi, idesc, accumulate);
+      };
+      // source row js (0 .. R/2+1) of an upsampled segment against its four-slot tile: output rows 2js-3 .. 2js
+      auto issue_up = [&](int js, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t accumulate) {
+        const int r_lo = 2 * js - 3;
+        const int lo_slot = r_lo < 0 ? -r_lo : 0;
+        const int hi_slot = r_lo + 3 > R - 1 ? R - 1 - r_lo : 3;
+        const int nslots = hi_slot - lo_slot + 1;
+        const uint32_t idesc = nslots == 4 ? idesc4 : (nslots == 3 ? idesc3 : (nslots == 2 ? idesc2 : idesc1));
+        umma_f16_lohi(dbase + (uint32_t)((r_lo + lo_slot) * CO), a_lo + (uint32_t)((js * kRowPitch) >> 4), a_hi,
                       b_lo + (uint32_t)((lo_slot * CO * Cfg::SWB) >> 4), b_hi, idesc, accumulate);
       };
       uint32_t chunk = 0;
+      uint32_t tile_off = 0;  // byte offset of the current segment's first weight tile
       for (int s = 0; s < a.nseg; ++s) {
+        const bool upseg = s == 0 && up0;
+        const uint32_t tile_bytes = upseg ? Cfg::U_TILE : Cfg::B_TILE;
         for (int cc = 0; cc < a.seg[s].cin / KC; ++cc, ++ita, ++chunk) {
           const int sta = ita % Cfg::A_STAGES;
           if (dbg) t0 = clock64();
@@ -257,7 +282,33 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::A_STAGE, Cfg::PLANE_STRIDE, 128);
           const uint32_t a_lo = (uint32_t)adesc, a_hi = (uint32_t)(adesc >> 32);
           // weight tile of this chunk: tiles are KCB wide, chunk `chunk` sits (chunk % CPB) * KC channels into its tile
-          const uint32_t b_chunk = b_lo_base + (chunk / CPB) * 3u * (Cfg::B_TILE >> 4) + (chunk % CPB) * (KC / 8u);
+          const uint32_t b_chunk = b_lo_base + ((tile_off + (uint32_t)(cc / CPB) * 3u * tile_bytes) >> 4) +
+                                   (uint32_t)(cc % CPB) * (KC / 8u);
+          if (upseg) {
+            if (elect_one()) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                  const uint32_t a_k = a_lo + (uint32_t)kx + (uint32_t)(2 * kk) * (Cfg::PLANE_STRIDE >> 4);
+                  const uint32_t b_k = b_chunk + (uint32_t)kx * (Cfg::U_TILE >> 4) + 2u * kk;
+                  if (kx == 0 && kk == 0 && chunk == 0) {
+                    // first touch: the odd source rows cover every output row exactly once (windows of four rows, two apart)
+#pragma unroll
+                    for (int js = 1; js < Cfg::ROWS_UP; js += 2) issue_up(js, a_k, a_hi, b_k, 0u);
+#pragma unroll
+                    for (int js = 0; js < Cfg::ROWS_UP; js += 2) issue_up(js, a_k, a_hi, b_k, 1u);
+                  } else {
+#pragma unroll
+                    for (int js = 0; js < Cfg::ROWS_UP; ++js) issue_up(js, a_k, a_hi, b_k, 1u);
+                  }
+                }
+              }
+              umma_commit(a_empty(sta));
+            }
+            __syncwarp();
+            continue;
+          }
           if (elect_one()) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
@@ -283,6 +334,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           }
           __syncwarp();
         }
+        tile_off += 3u * (uint32_t)(a.seg[s].cin / KCB) * tile_bytes;
       }
       if (has_res) {
         // residual: out row r += I * residual row r (gathered like any other source: block row r+1, centre column)
@@ -294,7 +346,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           operand_ready_fence();
           const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::A_STAGE, Cfg::PLANE_STRIDE, 128);
           const uint32_t a_lo = (uint32_t)adesc, a_hi = (uint32_t)(adesc >> 32);
-          const uint32_t b_i = b_lo_base + (uint32_t)((ntl * Cfg::B_TILE + (cc / CPB) * Cfg::I_TILE) >> 4) +
+          const uint32_t b_i = b_lo_base + (uint32_t)((wbytes + (cc / CPB) * Cfg::I_TILE) >> 4) +
                                (uint32_t)(cc % CPB) * (KC / 8u);
           if (elect_one()) {
 #pragma unroll
@@ -343,11 +395,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
       if (dbg) { const long long t1 = clock64(); w_full += t1 - t0; t0 = t1; }
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
-#ifdef IU_EXP_NO_EPI
-      if (false) {
-#else
       if (a.mode == kEpiBf16) {
-#endif
 #pragma unroll 1
         for (int rb = 0; rb < R / 2; rb += RB) {
           const int r0 = g * (R / 2) + rb;             // first row of this store box
@@ -394,11 +442,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
             bulk_commit();
           }
         }
-#ifdef IU_EXP_NO_EPI
-      } else if (false) {
-#else
       } else {
-#endif
 #pragma unroll 1
         for (int r = g * (R / 2); r < (g + 1) * (R / 2); ++r) {
           const int y = tc.y0 + r;
@@ -457,8 +501,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           row_warp_wait(a_empty(st), ((it / Cfg::A_STAGES) & 1) ^ 1u, lane);
           if (dbg) { const long long t1 = clock64(); g_empty += t1 - t0; t0 = t1; }
           const uint32_t stage = a_base + st * Cfg::A_STAGE;
-          // the residual (identity) segment only reads block rows 1..R and the interior pixels
-          const int j_lo = is_res ? 1 : 0, j_hi = is_res ? ROWS - 1 : ROWS;
+          // the residual (identity) segment only reads block rows 1..R and the interior pixels; an upsampled
+          // segment gathers its R/2+2 SOURCE rows (row js = source row y0/2 - 1 + js) and stays upsampled along x
+          const int j_lo = is_res ? 1 : 0, j_hi = is_res ? ROWS - 1 : (up ? Cfg::ROWS_UP : ROWS);
+          const int src_y0 = up ? (tc.y0 >> 1) - 1 : tc.y0 - 1;
+          const int src_h = a.out_h >> up;
 #pragma unroll
           for (int k = 0; k < COLS_PER_THREAD; ++k) {
             const int gx = tc.x0 + pxm + k * PX_STEP;
@@ -468,20 +515,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < ROWS; ++j) {
               if (j >= j_lo && j < j_hi) {
-                const int gy = tc.y0 - 1 + j;
-                const bool ok = xok && (unsigned)gy < (unsigned)a.out_h;
-#ifndef IU_EXP_NO_GATHER
-                rcp_async_16(dst + j * kRowPitch, ok ? col + (size_t)(gy >> up) * row_stride : src, ok ? 16u : 0u);
-#else
-                (void)ok; (void)dst; (void)col;
-#endif
+                const int sy = src_y0 + j;
+                const bool ok = xok && (unsigned)sy < (unsigned)src_h;
+                rcp_async_16(dst + j * kRowPitch, ok ? col + (size_t)sy * row_stride : src, ok ? 16u : 0u);
               }
             }
           }
-          if (halo_thread && !is_res) {
-            const int gy = tc.y0 - 1 + h_row, gx = tc.x0 - 1 + h_side * (kRowSeg + 1);
-            const bool ok = ((unsigned)gy < (unsigned)a.out_h) && ((unsigned)gx < (unsigned)a.out_w);
-            const __nv_bfloat16* gp = ok ? img + (size_t)(gy >> up) * row_stride + (size_t)(gx >> up) * cin + cc * KC + h_plane * 8 : src;
+          if (halo_thread && !is_res && h_row < j_hi) {
+            const int sy = src_y0 + h_row, gx = tc.x0 - 1 + h_side * (kRowSeg + 1);
+            const bool ok = ((unsigned)sy < (unsigned)src_h) && ((unsigned)gx < (unsigned)a.out_w);
+            const __nv_bfloat16* gp = ok ? img + (size_t)sy * row_stride + (size_t)(gx >> up) * cin + cc * KC + h_plane * 8 : src;
             rcp_async_16(stage + dst_halo, gp, ok ? 16u : 0u);
           }
           rcp_async_commit();
@@ -525,10 +568,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
 // The three instantiations: <KC, KCB, CO, R, STAGES, RB, NSTG>
 //   Cout 64 (layer1, decoder block 2 conv2): 32-channel A stages x 2, 128-byte weight tiles, 4-row blocks, one
 //                                            staging buffer per group (72-80 KB of resident weights leave no more)
-//   Cout 32 (decoder block 3):               16-channel A stages x 3, 8-row blocks
+//   Cout 32 (decoder block 3):               16-channel A stages x 3, 8-row blocks, one staging buffer per group
+//                                            (conv1's four-slot + three-slot weight tiles take 84 KB)
 //   Cout 16 (decoder block 4, head):         16-channel A stages x 4, 8-row blocks, 2 rows per TMA store
 #define IU_ROW_CFG64 32, 64, 64, 4, 2, 1, 1
-#define IU_ROW_CFG32 16, 16, 32, 8, 3, 1, 2
+#define IU_ROW_CFG32 16, 16, 32, 8, 3, 1, 1
 #define IU_ROW_CFG16 16, 16, 16, 8, 4, 2, 2
 
 template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
@@ -537,7 +581,8 @@ static bool row_fits(const ConvArgs& a) {
   int bytes = 0;
   for (int s = 0; s < a.nseg; ++s) {
     if (a.seg[s].cin % KCB) return false;
-    bytes += 3 * (a.seg[s].cin / KCB) * Cfg::B_TILE;
+    if (a.seg[s].up && (s != 0 || (a.out_h & 1))) return false;  // only the first segment may be upsampled
+    bytes += 3 * (a.seg[s].cin / KCB) * (a.seg[s].up ? Cfg::U_TILE : Cfg::B_TILE);
   }
   if (a.residual != nullptr) bytes += (CO / KCB) * Cfg::I_TILE;
   return bytes <= Cfg::W_MAX;

@@ -35,6 +35,8 @@ struct alignas(64) ConvArgs {
   CUtensorMap bmap2;    // the same weights with box = (64, 64): one CTA's half tile in the CTA-pair kernel
   // row-folded kernel (conv_row.cu), valid when use_row != 0:
   CUtensorMap bmapf;    // 2-D map (3*sum(cin), 3*Cout_pad) over the fold-packed weights, box = (row KC, 3*Cout_pad)
+  CUtensorMap bmapu;    // 2-D map (3*cin0, 4*Cout_pad) over the four-slot weights of an upsampled segment 0,
+                        // box = (row KC, 4*Cout_pad)
   CUtensorMap bmapi;    // 2-D map over the [Cout][Cout] identity (residual segment), box = (row KC, Cout)
   CUtensorMap omap;     // 4-D map (Cout, W, H, N) over the output tensor, box = (Cout, 128, store rows, 1): TMA store
   int use_row;

@@ -47,6 +47,8 @@ struct ConvLayer {
   // row-folded packing (conv_row.cu) for the stride-1 3x3 layers with cout_pad <= 64; nullptr otherwise
   __nv_bfloat16* d_wf = nullptr;
   int ktot_f = 0;
+  // four-slot packing of an upsampled first segment (conv_row.cu): [W2 | W1+W2 | W0+W1 | W0] per filter column
+  __nv_bfloat16* d_wu = nullptr;
 };
 
 struct Plan {
@@ -291,6 +293,20 @@ void pack_fold_segment(std::vector<uint16_t>& dst, int fp16, int ktot_f, int kba
               to16(w[(((size_t)co * cin_total + coff + c) * 3 + ky) * 3 + kx], fp16);
 }
 
+// Upsampled segment (channels [0, cin0) of the conv): source row s feeds output rows 2s-1 .. 2s+2 through the
+// vertically pre-summed filters; rows = slot * cout_pad + co, K = kx -> channel.
+void pack_up_fold(std::vector<uint16_t>& dst, int fp16, const float* w, int cout, int cout_pad, int cin_total, int cin0) {
+  const int k3 = 3 * cin0;
+  for (int co = 0; co < cout; ++co)
+    for (int kx = 0; kx < 3; ++kx)
+      for (int c = 0; c < cin0; ++c) {
+        const float* f = w + (((size_t)co * cin_total + c) * 3) * 3 + kx;  // f[ky * 3]
+        const float w0 = f[0], w1 = f[3], w2 = f[6];
+        const float slot[4] = {w2, w1 + w2, w0 + w1, w0};
+        for (int t = 0; t < 4; ++t) dst[(size_t)(t * cout_pad + co) * k3 + kx * cin0 + c] = to16(slot[t], fp16);
+      }
+}
+
 int upload_fold(iu_engine* e, ConvLayer& L, const float* w, int cout, int cin_total, int nsrc, const int* src_cin) {
   L.ktot_f = 3 * cin_total;
   std::vector<uint16_t> packed((size_t)3 * L.cout_pad * L.ktot_f, 0);
@@ -303,6 +319,13 @@ int upload_fold(iu_engine* e, ConvLayer& L, const float* w, int cout, int cin_to
   IU_CUDA(e, cudaMalloc(&L.d_wf, packed.size() * 2));
   IU_CUDA(e, cudaMemcpy(L.d_wf, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
   e->weight_bytes += packed.size() * 2;
+  if (L.seg[0].up) {
+    std::vector<uint16_t> pu((size_t)4 * L.cout_pad * 3 * src_cin[0], 0);
+    pack_up_fold(pu, e->fp16, w, cout, L.cout_pad, cin_total, src_cin[0]);
+    IU_CUDA(e, cudaMalloc(&L.d_wu, pu.size() * 2));
+    IU_CUDA(e, cudaMemcpy(L.d_wu, pu.data(), pu.size() * 2, cudaMemcpyHostToDevice));
+    e->weight_bytes += pu.size() * 2;
+  }
   return IU_OK;
 }
 
@@ -331,6 +354,7 @@ void free_weights(iu_engine* e) {
     if (L.d_w) cudaFree(L.d_w);
     if (L.d_b) cudaFree(L.d_b);
     if (L.d_wf) cudaFree(L.d_wf);
+    if (L.d_wu) cudaFree(L.d_wu);
   }
   if (e->d_ident) cudaFree(e->d_ident);
   e->d_ident = nullptr;
@@ -649,6 +673,8 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
       const int kcr = conv_row_kc(L.cout_pad);
       rc = encode_weight_map(e, &a.bmapf, L.d_wf, L.ktot_f, 3 * L.cout_pad, kcr, 3 * L.cout_pad);
       if (rc == IU_OK && L.residual >= 0) rc = encode_weight_map(e, &a.bmapi, e->d_ident, 64, 64, kcr, L.cout_pad);
+      if (rc == IU_OK && L.d_wu)
+        rc = encode_weight_map(e, &a.bmapu, L.d_wu, 3 * L.seg[0].cin, 4 * L.cout_pad, kcr, 4 * L.cout_pad);
       if (rc == IU_OK && L.mode == kEpiBf16) {
         const TensorSpec& to = e->tensors[L.out];
         rc = encode_act_map(e, &a.omap, p.bufs[L.out], L.cout_pad, w / to.hdiv, h / to.hdiv, bp, L.cout_pad, 128,
@@ -1222,6 +1248,7 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
   if (rc == IU_OK) rc = encode_weight_map(e, &a.bmap, d_w, ktot, cout, kc, bn);
   if (rc == IU_OK && kc == 64 && cout % 128 == 0) rc = encode_weight_map(e, &a.bmap2, d_w, ktot, cout, 64, 64);
   void* d_wf = nullptr;
+  void* d_wu = nullptr;
   if (rc == IU_OK) {
     a.cout = cout;
     a.bias = d_b;
@@ -1242,6 +1269,15 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
         cudaMemcpyAsync(d_wf, pf.data(), pf.size() * 2, cudaMemcpyHostToDevice, e->stream);
         cudaStreamSynchronize(e->stream);  // `pf` is a local
         rc = encode_weight_map(e, &a.bmapf, d_wf, ktot_f, 3 * cout, kcr, 3 * cout);
+        if (rc == IU_OK && src0_up) {
+          std::vector<uint16_t> pu((size_t)4 * cout * 3 * cin0, 0);
+          pack_up_fold(pu, e->fp16, weight, cout, cout, cin_total, cin0);
+          if ((rc = scratch_get(e, pu.size() * 2, &d_wu)) == IU_OK) {
+            cudaMemcpyAsync(d_wu, pu.data(), pu.size() * 2, cudaMemcpyHostToDevice, e->stream);
+            cudaStreamSynchronize(e->stream);  // `pu` is a local
+            rc = encode_weight_map(e, &a.bmapu, d_wu, 3 * cin0, 4 * cout, kcr, 4 * cout);
+          }
+        }
         if (rc == IU_OK && residual) rc = encode_weight_map(e, &a.bmapi, e->d_ident, 64, 64, kcr, cout);
         if (rc == IU_OK)
           rc = encode_act_map(e, &a.omap, out, cout, out_w, out_h, batch, cout, 128, conv_row_store_rows(cout), 1, 1);
@@ -1259,6 +1295,7 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
   scratch_put(e, d_w);
   scratch_put(e, d_b);
   scratch_put(e, d_wf);
+  scratch_put(e, d_wu);
   return rc;
 }
 

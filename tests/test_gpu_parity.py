@@ -131,8 +131,12 @@ def test_conv_matches_fp32_reference(dev, iu, case, precision, variant, monkeypa
         y = F.interpolate(y, scale_factor=2, mode="nearest")
     want = y.permute(0, 2, 3, 1)
     ulp = 2.0 ** -10 if precision == "fp16" else 2.0 ** -7         # one output rounding + accumulation order
+    # an upsampled source runs on vertically PRE-SUMMED filters in the row-folded kernel (W1+W2 and W0+W1 are rounded
+    # to 16 bits once, the reference rounds each tap): with bf16's 8-bit significand that reaches ~1e-2 at the maximum
+    # of the small-K cases; fp16 (the default storage) stays inside the common bound
+    atol = 2e-2 if (src_up and precision == "bf16") else 2e-3
     assert got.shape == want.shape
-    assert torch.all((got - want).abs() <= 2e-3 + ulp * want.abs())
+    assert torch.all((got - want).abs() <= atol + ulp * want.abs())
 
 
 # --------------------------------------------------------------------------- K1 gather (bit-exact)
