@@ -25,7 +25,10 @@ __device__ __forceinline__ float2 unpack16(uint32_t v, int fp16) {
 __device__ __forceinline__ void softmax_dst(const ConvArgs& a, int n, int y, int x, float** dst, size_t* cstride) {
   float* outp = reinterpret_cast<float*>(a.out);
   if (a.mode == kEpiSoftmaxNHWC) {
-    const size_t rowoff = ((size_t)(y / a.row_block) * a.slice_count + a.slice0 + n) * a.row_block + (y % a.row_block);
+    // single-GPU layout (row_block == image height): no division; destination-major layout for the all-to-all otherwise
+    const size_t rowoff = a.row_block == a.out_h
+                              ? (size_t)(a.slice0 + n) * a.out_h + y
+                              : ((size_t)(y / a.row_block) * a.slice_count + a.slice0 + n) * a.row_block + (y % a.row_block);
     *dst = outp + (rowoff * a.out_w + x) * a.num_classes;
     *cstride = 1;
   } else {

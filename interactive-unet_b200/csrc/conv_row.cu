@@ -442,6 +442,26 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
             bulk_commit();
           }
         }
+      } else if (a.num_classes <= 4) {
+        // head (2-4 classes): the group's R/2 rows are loaded from TMEM together and their softmaxes run interleaved,
+        // so the TMEM-load, exp and division latencies of one row hide under the others
+        constexpr int HR = R / 2;
+        uint32_t acc[HR][4];
+#pragma unroll
+        for (int i = 0; i < HR; ++i) tmem_ld_32x4(tacc + (uint32_t)((g * HR + i) * CO), acc[i]);
+        tmem_ld_wait();
+        const int x = tc.x0 + px;
+        const bool xok = x < a.out_w;
+#pragma unroll
+        for (int i = 0; i < HR; ++i) {
+          const int y = tc.y0 + g * HR + i;
+          if (xok && y < a.out_h) {
+            if (a.num_classes == 2) softmax_store<2>(a, bias_s, acc[i], tc.n, y, x);
+            else if (a.num_classes == 4) softmax_store<4>(a, bias_s, acc[i], tc.n, y, x);
+            else if (a.num_classes == 3) softmax_store<3>(a, bias_s, acc[i], tc.n, y, x);
+            else softmax_store<1>(a, bias_s, acc[i], tc.n, y, x);
+          }
+        }
       } else {
 #pragma unroll 1
         for (int r = g * (R / 2); r < (g + 1) * (R / 2); ++r) {
