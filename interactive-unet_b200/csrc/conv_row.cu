@@ -400,14 +400,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         for (int rb = 0; rb < R / 2; rb += RB) {
           const int r0 = g * (R / 2) + rb;             // first row of this store box
           if (tc.y0 + r0 >= a.out_h) break;            // ragged last block (uniform over the group)
-          const uint32_t stg = stg_g + (NSTG == 2 ? (nstore & 1u) * Cfg::STG : 0u);
-          const uint32_t stg_px = stg + px_off;
-          ++nstore;
-          if (leader) {                                // the last store out of this buffer has finished reading it
-            if constexpr (NSTG == 2) bulk_wait_read_1();
-            else bulk_wait_read_0();
-          }
-          group_bar(1 + g);
+          // 1. TMEM -> registers -> bias / ReLU / 16-bit pack for the whole box, BEFORE touching the staging buffer:
+          //    this part overlaps with the previous box's TMA store still draining
+          uint4 pk[RB][CO / 8];
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
             const uint32_t taddr = tacc + (uint32_t)((r0 + i) * CO);
@@ -427,12 +422,27 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                                     a.fp16);
                   if (a.relu) o[k] = relu16x2(o[k], a.fp16);
                 }
-                const uint32_t c = (uint32_t)((ch * Cfg::CH + j) / 8);
-                const uint32_t dst = stg_px + (uint32_t)i * (kRowSeg * CO * 2) + ((c ^ swz) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]),
-                             "r"(o[3])
-                             : "memory");
+                pk[i][(ch * Cfg::CH + j) / 8] = make_uint4(o[0], o[1], o[2], o[3]);
               }
+            }
+          }
+          // 2. staging buffer free? (the last store out of it has finished reading)  3. swizzled writes  4. one TMA store
+          const uint32_t stg = stg_g + (NSTG == 2 ? (nstore & 1u) * Cfg::STG : 0u);
+          const uint32_t stg_px = stg + px_off;
+          ++nstore;
+          if (leader) {
+            if constexpr (NSTG == 2) bulk_wait_read_1();
+            else bulk_wait_read_0();
+          }
+          group_bar(1 + g);
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+#pragma unroll
+            for (int c = 0; c < CO / 8; ++c) {
+              const uint32_t dst = stg_px + (uint32_t)i * (kRowSeg * CO * 2) + (((uint32_t)c ^ swz) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[i][c].x), "r"(pk[i][c].y),
+                           "r"(pk[i][c].z), "r"(pk[i][c].w)
+                           : "memory");
             }
           }
           group_bar(1 + g);
