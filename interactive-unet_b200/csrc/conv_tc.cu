@@ -23,7 +23,8 @@
 
 namespace iu {
 
-constexpr int kSmemBudget = 100 * 1024;  // per CTA, so that two CTAs fit in the 227 KB of an SM
+constexpr int kSmemBudget = 100 * 1024;   // per CTA, so that two CTAs fit in the 227 KB of an SM
+constexpr int kSmemBudgetWide = 200 * 1024;  // BN = 256: one CTA per SM (its two accumulators fill TMEM)
 
 template <int KC, int BN>
 struct ConvCfg {
@@ -34,7 +35,10 @@ struct ConvCfg {
   static constexpr int TAP_BYTES = A_BYTES + B_ALLOC;
   static constexpr int TPS = KC <= 32 ? 3 : 1;  // taps per pipeline stage (3x3 layers only)
   static constexpr int STAGE_BYTES = TPS * TAP_BYTES;
-  static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
+  // BN = 256 (Cout >= 256 layers): one A box serves a 256-wide weight tile, i.e. 48 KB of operands per eight
+  // MMA-equivalents instead of 64 KB with two BN = 128 tiles -- the kernel is L2-bandwidth bound (~17 TB/s measured)
+  static constexpr int CTAS_PER_SM = BN == 256 ? 1 : 2;
+  static constexpr int STAGES_RAW = (BN == 256 ? kSmemBudgetWide : kSmemBudget) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;  // TMEM columns per accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;      // double-buffered: 64 / 128 / 256 columns
@@ -47,7 +51,7 @@ struct ConvCfg {
 constexpr int kThreads = 320;
 
 template <int KC, int BN>
-__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
   using Cfg = ConvCfg<KC, BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.amap[0]);
     if (a.nseg > 1) tma_prefetch_desc(&a.amap[1]);
-    tma_prefetch_desc(&a.bmap);
+    tma_prefetch_desc(BN == 256 ? &a.bmap256 : &a.bmap);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
                   const uint32_t sa = base + st * Cfg::STAGE_BYTES + j * Cfg::TAP_BYTES;
                   tma_load_4d(sa, &a.amap[s], full_bar(st), cc * KC, tc.x0 * sg.stride - sg.pad + q,
                               tc.y0 * sg.stride - sg.pad + r, tc.n0);
-                  tma_load_2d(sa + Cfg::A_BYTES, &a.bmap, full_bar(st), kbase + (r * sg.ksize + q) * sg.cin + cc * KC,
+                  tma_load_2d(sa + Cfg::A_BYTES, BN == 256 ? &a.bmap256 : &a.bmap, full_bar(st), kbase + (r * sg.ksize + q) * sg.cin + cc * KC,
                               tc.ntile * BN);
                 }
               }
@@ -217,7 +221,8 @@ static cudaError_t launch_one(const ConvArgs& args_in, cudaStream_t stream) {
   const int cout_pad = (args.mode == kEpiBf16) ? args.cout : BN;
   args.ntiles_n = cout_pad / BN;
   args.total_tiles = mtiles * args.ntiles_n;
-  const int grid = args.total_tiles < 2 * num_sms ? args.total_tiles : 2 * num_sms;
+  const int slots = Cfg::CTAS_PER_SM * num_sms;
+  const int grid = args.total_tiles < slots ? args.total_tiles : slots;
   conv_tc_kernel<KC, BN><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(args);
   return cudaGetLastError();
 }
@@ -226,6 +231,7 @@ static cudaError_t launch_one(const ConvArgs& args_in, cudaStream_t stream) {
   if (kc == KC_ && bn == BN_) return launch_one<KC_, BN_>(args, stream);
 
 cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream) {
+  IU_CONV_DISPATCH(64, 256)
   IU_CONV_DISPATCH(64, 128)
   IU_CONV_DISPATCH(64, 64)
   IU_CONV_DISPATCH(64, 32)
@@ -238,6 +244,7 @@ cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t st
 int conv_tc_smem_bytes(int kc, int bn) {
 #define IU_CONV_SMEM(KC_, BN_) \
   if (kc == KC_ && bn == BN_) return ConvCfg<KC_, BN_>::SMEM_BYTES;
+  IU_CONV_SMEM(64, 256)
   IU_CONV_SMEM(64, 128)
   IU_CONV_SMEM(64, 64)
   IU_CONV_SMEM(64, 32)

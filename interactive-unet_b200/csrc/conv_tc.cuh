@@ -33,6 +33,8 @@ struct alignas(64) ConvArgs {
   CUtensorMap amap[2];  // 4-D maps (C, W, H, N) over the segment sources, box = (KC, tw*stride, th*stride, nb)
   CUtensorMap bmap;     // 2-D map (K, Cout_pad) over the packed weights, box = (KC, BN)
   CUtensorMap bmap2;    // the same weights with box = (64, 64): one CTA's half tile in the CTA-pair kernel
+  CUtensorMap bmap256;  // the same weights with box = (64, 256): per-tap kernel with BN = 256 (valid when use_bn256)
+  int use_bn256;
   // row-folded kernel (conv_row.cu), valid when use_row != 0:
   CUtensorMap bmapf;    // 2-D map (3*sum(cin), 3*Cout_pad) over the fold-packed weights, box = (row KC, 3*Cout_pad)
   CUtensorMap bmapu;    // 2-D map (3*cin0, 4*Cout_pad) over the four-slot weights of an upsampled segment 0,

@@ -110,6 +110,7 @@ struct iu_engine {
   int conv_pair = 0;  // env IU_CONV_PAIR=1 routes the wide layers to the CTA-pair kernel (opt-in: not yet faster end to end)
   int conv_variant = 0;  // 0 = auto (halo kernel where applicable), 1 = per-tap TMA kernel only (env IU_CONV_VARIANT)
   int conv_row = 1;  // env IU_CONV_ROW=0 keeps the narrow layers off the row-folded kernel
+  int conv_bn256 = 1;  // env IU_CONV_BN256=0: per-tap kernel with 128-wide Cout tiles only
   __nv_bfloat16* d_ident = nullptr;  // [64][64] identity in the storage format: the residual segment of conv_row.cu
   unsigned long long* d_debug = nullptr;  // env IU_CONV_DEBUG=1: 16 cycle counters per conv layer (development aid)
   int64_t launches = 0;
@@ -651,6 +652,10 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
     int rc = encode_weight_map(e, &a.bmap, L.d_w, L.ktot, L.cout_pad, L.kc, L.bn);
     if (rc == IU_OK && L.kc == 64 && L.cout_pad % 128 == 0)
       rc = encode_weight_map(e, &a.bmap2, L.d_w, L.ktot, L.cout_pad, 64, 64);
+    if (rc == IU_OK && L.kc == 64 && L.cout_pad % 256 == 0 && L.mode == kEpiBf16) {
+      rc = encode_weight_map(e, &a.bmap256, L.d_w, L.ktot, L.cout_pad, 64, 256);
+      a.use_bn256 = rc == IU_OK;
+    }
     if (rc != IU_OK) {
       free_plan(e);
       return rc;
@@ -739,6 +744,7 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
   else if (e->conv_variant == 2) halo = applicable;
   else halo = has_up || (applicable && (kc <= 32 || bn <= 64) && a.out_h >= kHaloTile && a.out_w >= kHaloTile);
   if (halo) return launch_conv_halo(a, kc, bn, e->stream);
+  if (a.use_bn256 && e->conv_bn256 && kc == 64) return launch_conv_tc(a, kc, 256, e->stream);
   return launch_conv_tc(a, kc, bn, e->stream);
 }
 
@@ -853,6 +859,7 @@ int iu_engine_create(int device, iu_engine** out) {
   if (const char* v = getenv("IU_AUTO_BATCH")) e->auto_batch_override = atoi(v);
   if (const char* v = getenv("IU_CONV_PAIR")) e->conv_pair = atoi(v);
   if (const char* v = getenv("IU_CONV_ROW")) e->conv_row = atoi(v);
+  if (const char* v = getenv("IU_CONV_BN256")) e->conv_bn256 = atoi(v);
   if (const char* v = getenv("IU_CONV_DEBUG")) {
     if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(e->d_debug, 0, 64 * 16 * sizeof(unsigned long long));
@@ -1247,6 +1254,10 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
     rc = encode_act_map(e, &a.amap[1], src1, cin1, w_in, h_in, batch, kc, a.tw * stride, a.th * stride, a.nb, stride);
   if (rc == IU_OK) rc = encode_weight_map(e, &a.bmap, d_w, ktot, cout, kc, bn);
   if (rc == IU_OK && kc == 64 && cout % 128 == 0) rc = encode_weight_map(e, &a.bmap2, d_w, ktot, cout, 64, 64);
+  if (rc == IU_OK && kc == 64 && cout % 256 == 0) {
+    rc = encode_weight_map(e, &a.bmap256, d_w, ktot, cout, 64, 256);
+    a.use_bn256 = rc == IU_OK;
+  }
   void* d_wf = nullptr;
   void* d_wu = nullptr;
   if (rc == IU_OK) {
