@@ -21,6 +21,21 @@ __device__ __forceinline__ float2 unpack16(uint32_t v, int fp16) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
 
+// 16-bit pack with saturation to the finite range (one cvt per pair) and ReLU on the packed pair.
+__device__ __forceinline__ uint32_t pack16_sat(float lo, float hi, int fp16) {
+  uint32_t r;
+  if (fp16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t relu16x2(uint32_t v, int fp16) {
+  uint32_t r;
+  const uint32_t zero = 0u;
+  if (fp16) asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(zero));
+  else asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(zero));
+  return r;
+}
+
 // Address of class 0 of pixel (n, y, x) in the head's output and the stride between classes.
 __device__ __forceinline__ void softmax_dst(const ConvArgs& a, int n, int y, int x, float** dst, size_t* cstride) {
   float* outp = reinterpret_cast<float*>(a.out);

@@ -87,21 +87,6 @@ struct RowCfg {
   static_assert((kRowSeg * PLANES) % kRowGatherThreads == 0, "gather columns per thread");
 };
 
-// 16-bit pack with saturation to the finite range (one cvt per pair) and ReLU on the packed pair.
-__device__ __forceinline__ uint32_t pack16_sat(float lo, float hi, int fp16) {
-  uint32_t r;
-  if (fp16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ uint32_t relu16x2(uint32_t v, int fp16) {
-  uint32_t r;
-  const uint32_t zero = 0u;
-  if (fp16) asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(zero));
-  else asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(zero));
-  return r;
-}
-
 __device__ __forceinline__ void rcp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -118,22 +103,6 @@ __device__ __forceinline__ void row_warp_wait(uint32_t bar, uint32_t parity, int
   if (lane == 0) mbar_wait(bar, parity);
   __syncwarp();
 }
-__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
 struct RowTile {
   int n, y0, x0;
 };

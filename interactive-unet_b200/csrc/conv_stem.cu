@@ -28,9 +28,11 @@ constexpr int kStemAStage = 2 * kStemATile;
 constexpr int kStemBBytes = 64 * 128;
 constexpr int kStemBuilders = 256;
 constexpr int kStemThreads = 320 + kStemBuilders;          // producer warp, MMA warp, 8 epilogue warps, 8 builder warps
-constexpr int kStemSmem = kStemAStages * kStemAStage + kStemBBytes + 2 * kStemPatchBytes + 64 * 4 + 16 * 8 + 16 + 1024;
+constexpr int kStemStage = 128 * 128;                      // epilogue staging of one M tile: 128 pixels x 64 ch x 2 B
+constexpr int kStemSmem = kStemAStages * kStemAStage + 4 * kStemStage + kStemBBytes + 2 * kStemPatchBytes + 64 * 4 + 16 * 8 + 16 + 1024;
 
 struct StemArgs {
+  CUtensorMap omap;  // 4-D map (64, W/2, H/2, N) over the output, box (64, 8, 16, 1), 128B swizzle: the epilogue's TMA store
   CUtensorMap bmap;  // 2-D map (K = 64, Cout = 64) over the packed weights, box = (64, 64), 128B swizzle
   const float* x;    // [batch][h][w] fp32 in [0, 1]
   int batch, h, w;
@@ -42,7 +44,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t a_base = base;
-  const uint32_t b_base = a_base + kStemAStages * kStemAStage;
+  const uint32_t stg_base = a_base + kStemAStages * kStemAStage;  // 2 epilogue groups x 2 buffers, 1024-aligned
+  const uint32_t b_base = stg_base + 4 * kStemStage;
   const uint32_t patch_base = b_base + kStemBBytes;
   const uint32_t bias_base = patch_base + 2 * kStemPatchBytes;
   const uint32_t bar_base = bias_base + 64 * 4;
@@ -67,6 +70,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
   if (threadIdx.x < 64) bias_s[threadIdx.x] = a.bias[threadIdx.x];
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&s.bmap);
+    tma_prefetch_desc(&s.omap);
     for (int st = 0; st < kStemAStages; ++st) {
       mbar_init(a_full(st), kStemBuilders / 32);
       mbar_init(a_empty(st), 1);
@@ -130,23 +134,60 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
     // ------------------------------------------------------------ epilogue: group j owns M tile j (columns 8j..8j+7)
     const int j = (warp - 2) >> 2;
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
+    const int row = quarter * 32 + lane;     // TMEM lane = pixel (row >> 3, row & 7) of the 16 x 8 M tile
+    const bool lead = ((warp - 2) & 3) == 0 && lane == 0;
+    const uint32_t stg_j = stg_base + j * 2 * kStemStage;
+    const uint32_t swz = (uint32_t)(row & 7);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u;
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
-      const int y = ty * kStemTileEdge + (row >> 3);
-      const int x = tx * kStemTileEdge + 8 * j + (row & 7);
       if (lane == 0) mbar_wait(acc_full(buf), (it >> 1) & 1u);
       __syncwarp();
       tc_fence_after();
       const uint32_t taddr = tmem_base + (buf * 2u + j) * 64u + ((uint32_t)(quarter * 32) << 16);
-      uint4 res[EpiCfg<64>::RV];
-      epilogue_pixel<64>(a, bias_s, 0, taddr, n, y, x, (y < a.out_h) && (x < a.out_w), res);
+      // bias + ReLU + 16-bit pack of this pixel's 64 channels, then the accumulator is free again
+      uint4 pk[8];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + ch * 32, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 b2 = *reinterpret_cast<const float2*>(bias_s + ch * 32 + q + 2 * k);
+            o[k] = relu16x2(pack16_sat(__uint_as_float(acc[q + 2 * k]) + b2.x, __uint_as_float(acc[q + 2 * k + 1]) + b2.y, a.fp16),
+                            a.fp16);
+          }
+          pk[(ch * 32 + q) / 8] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
+      // staged TMA store of the 16 x 8 pixel tile (a per-lane 16-byte global store touches 32 lines per instruction
+      // and made this kernel LSU bound): swizzled rows of 128 B, one box (64 ch, 8 px, 16 rows), clipped at the edges
+      const uint32_t stg = stg_j + (it & 1u) * kStemStage;
+      if (lead) bulk_wait_read_1();
+      group_bar(2 + j);  // named barriers 2 / 3: id 1 belongs to the builder warps
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t dst = stg + (uint32_t)row * 128u + (((uint32_t)c ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[c].x), "r"(pk[c].y), "r"(pk[c].z),
+                     "r"(pk[c].w)
+                     : "memory");
+      }
+      group_bar(2 + j);
+      if (lead) {
+        fence_proxy_async();
+        tma_store_4d(&s.omap, stg, 0, tx * kStemTileEdge + 8 * j, ty * kStemTileEdge, n);
+        bulk_commit();
+      }
     }
+    if (lead) bulk_wait_all();
   } else {
     // ------------------------------------------------------------ A builders (8 warps, one thread per output pixel)
     const int t = threadIdx.x - 320;
@@ -221,8 +262,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
-cudaError_t launch_conv_stem(const CUtensorMap& bmap, const float* x, int batch, int h, int w, const ConvArgs& epi,
-                             cudaStream_t stream) {
+cudaError_t launch_conv_stem(const CUtensorMap& bmap, const CUtensorMap& omap, const float* x, int batch, int h, int w,
+                             const ConvArgs& epi, cudaStream_t stream) {
   static_assert(kStemSmem <= 227 * 1024, "stem kernel exceeds the shared memory of an SM");
   static int configured_dev = -1;
   static int num_sms = 148;
@@ -236,6 +277,7 @@ cudaError_t launch_conv_stem(const CUtensorMap& bmap, const float* x, int batch,
   }
   StemArgs s;
   s.bmap = bmap;
+  s.omap = omap;
   s.x = x;
   s.batch = batch;
   s.h = h;

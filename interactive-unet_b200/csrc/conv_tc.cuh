@@ -97,8 +97,9 @@ cudaError_t launch_conv_row(const ConvArgs& args, cudaStream_t stream);
 // Stem (conv_stem.cu): Conv2d(1, 64, 7, stride 2, padding 3) + bias + ReLU on the tensor cores.
 //   bmap: 2-D map over the packed 16-bit weights [64 cout][64 k], k = filter_row * 8 + filter_col (col 7 and
 //         k >= 56 are zero), box (64, 64), 128-byte swizzle;  x: fp32 [batch][h][w];
+//   omap: 4-D map (64, w/2, h/2, batch) over the output, box (64, 8, 16, 1), 128-byte swizzle (the epilogue's TMA store);
 //   epi:  epilogue description (mode kEpiBf16, out = [batch][h/2][w/2][64], bias, relu, fp16, cout = 64, out_h, out_w).
-cudaError_t launch_conv_stem(const CUtensorMap& bmap, const float* x, int batch, int h, int w, const ConvArgs& epi,
-                             cudaStream_t stream);
+cudaError_t launch_conv_stem(const CUtensorMap& bmap, const CUtensorMap& omap, const float* x, int batch, int h, int w,
+                             const ConvArgs& epi, cudaStream_t stream);
 
 }  // namespace iu

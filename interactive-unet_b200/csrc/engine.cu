@@ -57,6 +57,7 @@ struct Plan {
   float* x_in = nullptr;
   std::vector<ConvArgs> args;
   ConvArgs stem_epi;
+  CUtensorMap stem_omap;
   size_t bytes = 0;
 };
 
@@ -704,6 +705,11 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
     a.relu = 1;
     a.fp16 = e->fp16;
     a.mode = kEpiBf16;
+    int rc = encode_act_map(e, &p.stem_omap, p.bufs[e->t_f1], 64, w / 2, h / 2, bp, 64, 8, 16, 1, 1);
+    if (rc != IU_OK) {
+      free_plan(e);
+      return rc;
+    }
   }
   p.batch = batch;
   p.batch_pad = bp;
@@ -752,7 +758,7 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
 int run_network(iu_engine* e, int batch, int head_mode, float* head_out, int slice0, int slice_count, int row_block) {
   Plan& p = e->plan;
   prof_begin(e, IU_PROF_STEM);
-  IU_CUDA(e, launch_conv_stem(e->stem_bmap, p.x_in, batch, p.h, p.w, p.stem_epi, e->stream));
+  IU_CUDA(e, launch_conv_stem(e->stem_bmap, p.stem_omap, p.x_in, batch, p.h, p.w, p.stem_epi, e->stream));
   prof_end(e);
   prof_begin(e, IU_PROF_POOL);
   IU_CUDA(e, launch_maxpool(p.bufs[e->t_f1], batch, p.h / 2, p.w / 2, 64, p.bufs[e->t_p1], e->stream));
