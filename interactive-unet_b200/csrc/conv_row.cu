@@ -56,7 +56,7 @@ constexpr int kRowSmemMax = 227 * 1024;
 //      Direct 16-byte global stores from the epilogue lanes were measured SLOWER even for 32 / 64 bytes per pixel
 //      (dec3/dec4 layers +7..14 %): they share the LSU / L1 wavefront queue with the gather's cp.async traffic,
 //      which is the scarcer resource; the TMA store bypasses it.
-template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM>
 struct RowCfg {
   static constexpr int PLANES = KC / 8;
   static constexpr int ROWS = R + 2;
@@ -75,14 +75,21 @@ struct RowCfg {
   static constexpr int TMEM_COLS = 2 * ACC_COLS;  // double buffered: 512 / 512 / 256
   static constexpr int MISC = 512;  // bias (<= 256 B) + barriers + TMEM slot
   // layout: [weights W_MAX][staging][A ring][bias, barriers]; the swizzled regions come first (1024-aligned base)
-  static constexpr int W_MAX = (kRowSmemMax - STG_TOTAL - A_STAGES * A_STAGE - MISC) / 1024 * 1024;
-  static constexpr int SMEM_BYTES = W_MAX + STG_TOTAL + A_STAGES * A_STAGE + MISC;
+  // STREAM: the layer's weights do not fit in shared memory (decoder block 2 conv1: 264 KB); the three kx tiles of
+  // each A chunk travel WITH that chunk -- same ring slot, same full barrier (TMA complete_tx next to the gather
+  // warps' arrivals) -- instead of staying resident.  Needs KCB == KC.
+  static constexpr int A_PAD = (A_STAGE + 255) / 256 * 256;          // weight tiles start 256-byte aligned
+  static constexpr int W_STAGE = STREAM ? 3 * U_TILE : 0;
+  static constexpr int STAGE_BYTES = STREAM ? A_PAD + W_STAGE : A_STAGE;
+  static constexpr int W_MAX = STREAM ? 0 : (kRowSmemMax - STG_TOTAL - A_STAGES * A_STAGE - MISC) / 1024 * 1024;
+  static constexpr int SMEM_BYTES = W_MAX + STG_TOTAL + A_STAGES * STAGE_BYTES + MISC;
+  static_assert(!STREAM || KCB == KC, "streamed weight tiles are one A chunk wide");
   static constexpr int CH = CO >= 32 ? 32 : 16;  // accumulator columns per tcgen05.ld
   static_assert(NSTG == 1 || NSTG == 2, "one or two staging buffers per epilogue group");
   static_assert(KCB % KC == 0 && (KCB == 64 || KCB == 32 || KCB == 16), "weight tile width");
   static_assert((PLANE_STRIDE / 16) % 2 == 1, "plane stride must be an odd number of 16-byte units");
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
-  static_assert(W_MAX > 0 && SMEM_BYTES <= kRowSmemMax, "shared memory budget");
+  static_assert((STREAM || W_MAX > 0) && SMEM_BYTES <= kRowSmemMax, "shared memory budget");
   static_assert((R / 2) % RB == 0, "each epilogue group stores whole RB-row boxes");
   static_assert((kRowSeg * PLANES) % kRowGatherThreads == 0, "gather columns per thread");
 };
@@ -115,9 +122,9 @@ __device__ __forceinline__ RowTile row_decode(const ConvArgs& a, int tile, int r
   return t;
 }
 
-template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM>
 __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_constant__ ConvArgs a) {
-  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG>;
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM>;
   const long long t_cta = (a.debug != nullptr && threadIdx.x == 0) ? clock64() : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
   const uint32_t w_base = raw;
   const uint32_t stg_base = w_base + Cfg::W_MAX;
   const uint32_t a_base = stg_base + Cfg::STG_TOTAL;
-  const uint32_t bias_base = a_base + Cfg::A_STAGES * Cfg::A_STAGE;
+  const uint32_t bias_base = a_base + Cfg::A_STAGES * Cfg::STAGE_BYTES;
   const uint32_t bar_base = bias_base + 256;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::A_STAGES + s); };
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     if (has_res) tma_prefetch_desc(&a.bmapi);
     if (a.mode == kEpiBf16) tma_prefetch_desc(&a.omap);
     for (int s = 0; s < Cfg::A_STAGES; ++s) {
-      mbar_init(a_full(s), kRowGatherThreads / 32);
+      mbar_init(a_full(s), kRowGatherThreads / 32 + (STREAM ? 1 : 0));  // gather warps (+ the weight TMA's expect_tx)
       mbar_init(a_empty(s), 1);
     }
     mbar_init(b_full, 1);
@@ -168,7 +175,33 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp == 0 && STREAM) {
+    // ------------------------------------------------------------ weights streamed with their A chunk
+    const int up0 = a.seg[0].up;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      int kbase = 0;
+      for (int s = 0; s < a.nseg; ++s) {
+        const int cin = a.seg[s].cin;
+        const bool upseg = s == 0 && up0;
+        const uint32_t tb = upseg ? Cfg::U_TILE : Cfg::B_TILE;
+        for (int cc = 0; cc < cin / KC; ++cc, ++it) {
+          const int st = it % Cfg::A_STAGES;
+          row_warp_wait(a_empty(st), ((it / Cfg::A_STAGES) & 1) ^ 1u, lane);
+          if (elect_one()) {
+            const uint32_t wdst = a_base + st * Cfg::STAGE_BYTES + Cfg::A_PAD;
+            mbar_arrive_expect_tx(a_full(st), 3 * tb);
+            for (int kx = 0; kx < 3; ++kx) {
+              if (upseg) tma_load_2d(wdst + kx * tb, &a.bmapu, a_full(st), kx * cin + cc * KC, 0);
+              else tma_load_2d(wdst + kx * tb, &a.bmapf, a_full(st), kbase + kx * cin + cc * KC, 0);
+            }
+          }
+          __syncwarp();
+        }
+        kbase += 3 * cin;
+      }
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------------------ weights: every tile once, resident for the CTA's life
     if (elect_one()) {
       // segment 0 may be an upsampled source (four-slot tiles from `bmapu`); the others use the three-slot tiles
@@ -206,9 +239,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     for (int s = 0; s < a.nseg; ++s) wbytes += 3 * (a.seg[s].cin / KCB) * ((s == 0 && up0) ? Cfg::U_TILE : Cfg::B_TILE);
     const bool dbg = a.debug != nullptr;
     long long w_acc = 0, w_a = 0, w_b = 0, t_begin = dbg ? clock64() : 0, t0 = 0;
-    row_warp_wait(b_full, 0, lane);
-    if (dbg) w_b = clock64() - t_begin;
-    operand_ready_fence();
+    if constexpr (!STREAM) {
+      row_warp_wait(b_full, 0, lane);
+      if (dbg) w_b = clock64() - t_begin;
+      operand_ready_fence();
+    }
     uint32_t ita = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1u;
@@ -248,11 +283,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           row_warp_wait(a_full(sta), (ita / Cfg::A_STAGES) & 1, lane);
           if (dbg) w_a += clock64() - t0;
           operand_ready_fence();
-          const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::A_STAGE, Cfg::PLANE_STRIDE, 128);
+          const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::STAGE_BYTES, Cfg::PLANE_STRIDE, 128);
           const uint32_t a_lo = (uint32_t)adesc, a_hi = (uint32_t)(adesc >> 32);
           // weight tile of this chunk: tiles are KCB wide, chunk `chunk` sits (chunk % CPB) * KC channels into its tile
-          const uint32_t b_chunk = b_lo_base + ((tile_off + (uint32_t)(cc / CPB) * 3u * tile_bytes) >> 4) +
-                                   (uint32_t)(cc % CPB) * (KC / 8u);
+          const uint32_t b_chunk =
+              STREAM ? (uint32_t)umma_smem_desc<Cfg::SWB>(a_base + sta * Cfg::STAGE_BYTES + Cfg::A_PAD)
+                     : b_lo_base + ((tile_off + (uint32_t)(cc / CPB) * 3u * tile_bytes) >> 4) + (uint32_t)(cc % CPB) * (KC / 8u);
           if (upseg) {
             if (elect_one()) {
 #pragma unroll
@@ -313,7 +349,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           row_warp_wait(a_full(sta), (ita / Cfg::A_STAGES) & 1, lane);
           if (dbg) w_a += clock64() - t0;
           operand_ready_fence();
-          const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::A_STAGE, Cfg::PLANE_STRIDE, 128);
+          const uint64_t adesc = row_desc_planar(a_base + sta * Cfg::STAGE_BYTES, Cfg::PLANE_STRIDE, 128);
           const uint32_t a_lo = (uint32_t)adesc, a_hi = (uint32_t)(adesc >> 32);
           const uint32_t b_i = b_lo_base + (uint32_t)((wbytes + (cc / CPB) * Cfg::I_TILE) >> 4) +
                                (uint32_t)(cc % CPB) * (KC / 8u);
@@ -499,7 +535,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
           if (dbg) t0 = clock64();
           row_warp_wait(a_empty(st), ((it / Cfg::A_STAGES) & 1) ^ 1u, lane);
           if (dbg) { const long long t1 = clock64(); g_empty += t1 - t0; t0 = t1; }
-          const uint32_t stage = a_base + st * Cfg::A_STAGE;
+          const uint32_t stage = a_base + st * Cfg::STAGE_BYTES;
           // the residual (identity) segment only reads block rows 1..R and the interior pixels; an upsampled
           // segment gathers its R/2+2 SOURCE rows (row js = source row y0/2 - 1 + js) and stays upsampled along x
           const int j_lo = is_res ? 1 : 0, j_hi = is_res ? ROWS - 1 : (up ? Cfg::ROWS_UP : ROWS);
@@ -564,19 +600,23 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------- host side
-// The three instantiations: <KC, KCB, CO, R, STAGES, RB, NSTG>
+int conv_row_mode(const ConvArgs& a);
+// The instantiations: <KC, KCB, CO, R, STAGES, RB, NSTG, STREAM>
 //   Cout 64 (layer1, decoder block 2 conv2): 32-channel A stages x 2, 128-byte weight tiles, 4-row blocks, one
 //                                            staging buffer per group (72-80 KB of resident weights leave no more)
+//   Cout 64, streamed weights (decoder block 2 conv1, 264 KB of weights): 16-channel A stages x 3 that also carry the
+//                                            chunk's three weight tiles
 //   Cout 32 (decoder block 3):               16-channel A stages x 3, 8-row blocks, one staging buffer per group
 //                                            (conv1's four-slot + three-slot weight tiles take 84 KB)
 //   Cout 16 (decoder block 4, head):         16-channel A stages x 4, 8-row blocks, 2 rows per TMA store
-#define IU_ROW_CFG64 32, 64, 64, 4, 2, 1, 1
-#define IU_ROW_CFG32 16, 16, 32, 8, 3, 1, 1
-#define IU_ROW_CFG16 16, 16, 16, 8, 4, 2, 2
+#define IU_ROW_CFG64 32, 64, 64, 4, 2, 1, 1, false
+#define IU_ROW_CFG64S 16, 16, 64, 4, 3, 1, 2, true
+#define IU_ROW_CFG32 16, 16, 32, 8, 3, 1, 1, false
+#define IU_ROW_CFG16 16, 16, 16, 8, 4, 2, 2, false
 
-template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM>
 static bool row_fits(const ConvArgs& a) {
-  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG>;
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM>;
   int bytes = 0;
   for (int s = 0; s < a.nseg; ++s) {
     if (a.seg[s].cin % KCB) return false;
@@ -584,39 +624,43 @@ static bool row_fits(const ConvArgs& a) {
     bytes += 3 * (a.seg[s].cin / KCB) * (a.seg[s].up ? Cfg::U_TILE : Cfg::B_TILE);
   }
   if (a.residual != nullptr) bytes += (CO / KCB) * Cfg::I_TILE;
+  if (STREAM) return a.residual == nullptr;  // nothing is resident; the identity segment is not wired for streaming
   return bytes <= Cfg::W_MAX;
 }
 
-int conv_row_kc(int cout_pad) { return cout_pad == 64 ? 64 : 16; }
+int conv_row_kc(int cout_pad, int mode) { return (cout_pad == 64 && mode != 2) ? 64 : 16; }
 int conv_row_store_rows(int cout_pad) { return cout_pad == 16 ? 2 : 1; }
 
-bool conv_row_applicable(const ConvArgs& a) {
-  if (a.nseg < 1 || a.nseg > 2 || a.up2x) return false;
+bool conv_row_applicable(const ConvArgs& a) { return conv_row_mode(a) != 0; }
+
+// 0: not for this kernel; 1: resident weights; 2: streamed weights (Cout 64 layers whose weights exceed shared memory)
+int conv_row_mode(const ConvArgs& a) {
+  if (a.nseg < 1 || a.nseg > 2 || a.up2x) return 0;
   for (int s = 0; s < a.nseg; ++s)
-    if (a.seg[s].ksize != 3 || a.seg[s].stride != 1 || a.seg[s].pad != 1 || a.src_ptr[s] == nullptr) return false;
+    if (a.seg[s].ksize != 3 || a.seg[s].stride != 1 || a.seg[s].pad != 1 || a.src_ptr[s] == nullptr) return 0;
   // any width >= 128: a ragged last segment is zero-filled by the gather and clipped by the TMA store; below 60 %
   // column utilisation the 16x16-block kernels are the better fit
   const int segs = (a.out_w + kRowSeg - 1) / kRowSeg;
-  if (a.out_w < kRowSeg || a.out_w * 5 < 3 * kRowSeg * segs || a.out_h < 1) return false;
+  if (a.out_w < kRowSeg || a.out_w * 5 < 3 * kRowSeg * segs || a.out_h < 1) return 0;
   if (a.mode == kEpiBf16) {
-    if (a.cout == 64) return row_fits<IU_ROW_CFG64>(a);
-    if (a.cout == 32) return row_fits<IU_ROW_CFG32>(a);
-    if (a.cout == 16) return row_fits<IU_ROW_CFG16>(a);
-    return false;
+    if (a.cout == 64) return row_fits<IU_ROW_CFG64>(a) ? 1 : (row_fits<IU_ROW_CFG64S>(a) ? 2 : 0);
+    if (a.cout == 32) return row_fits<IU_ROW_CFG32>(a) ? 1 : 0;
+    if (a.cout == 16) return row_fits<IU_ROW_CFG16>(a) ? 1 : 0;
+    return 0;
   }
   // softmax head: the logits occupy the first num_classes of 16 padded output channels
-  return a.residual == nullptr && a.num_classes <= 16 && row_fits<IU_ROW_CFG16>(a);
+  return (a.residual == nullptr && a.num_classes <= 16 && row_fits<IU_ROW_CFG16>(a)) ? 1 : 0;
 }
 
-template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG>
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM>
 static cudaError_t launch_row_one(const ConvArgs& args_in, cudaStream_t stream) {
-  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG>;
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM>;
   static int configured_dev = -1;
   static int num_sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG>,
+    cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -628,13 +672,15 @@ static cudaError_t launch_row_one(const ConvArgs& args_in, cudaStream_t stream) 
   args.ntiles_n = 1;
   args.total_tiles = args.tiles_x * args.tiles_y * args.batch;
   const int grid = args.total_tiles < num_sms ? args.total_tiles : num_sms;
-  conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG><<<grid, kRowThreads, Cfg::SMEM_BYTES, stream>>>(args);
+  conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM><<<grid, kRowThreads, Cfg::SMEM_BYTES, stream>>>(args);
   return cudaGetLastError();
 }
 
 cudaError_t launch_conv_row(const ConvArgs& args, cudaStream_t stream) {
-  if (!conv_row_applicable(args)) return cudaErrorInvalidValue;
+  const int mode = conv_row_mode(args);
+  if (mode == 0) return cudaErrorInvalidValue;
   const int co = args.mode == kEpiBf16 ? args.cout : 16;
+  if (co == 64 && mode == 2) return launch_row_one<IU_ROW_CFG64S>(args, stream);
   if (co == 64) return launch_row_one<IU_ROW_CFG64>(args, stream);
   if (co == 32) return launch_row_one<IU_ROW_CFG32>(args, stream);
   return launch_row_one<IU_ROW_CFG16>(args, stream);

@@ -90,7 +90,8 @@ cudaError_t launch_conv_pair(const ConvArgs& args, cudaStream_t stream);
 // multiple of 128: vertical taps folded into the MMA's N, residual as an identity K segment, TMA-store epilogue.
 // Needs `bmapf` / `omap` (and `bmapi` with a residual).  conv_row_kc: the K chunk its weight maps are boxed with.
 bool conv_row_applicable(const ConvArgs& args);
-int conv_row_kc(int cout_pad);
+int conv_row_mode(const ConvArgs& args);   // 0 = not applicable, 1 = resident weights, 2 = streamed weights
+int conv_row_kc(int cout_pad, int mode);
 int conv_row_store_rows(int cout_pad);  // output rows per TMA store box (the `omap` box height)
 cudaError_t launch_conv_row(const ConvArgs& args, cudaStream_t stream);
 

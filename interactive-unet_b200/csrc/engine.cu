@@ -675,8 +675,9 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
     a.row_block = h;
     a.debug = (e->d_debug && i < 64) ? e->d_debug + 16 * i : nullptr;
     a.use_row = 0;
-    if (L.d_wf && e->conv_row && conv_row_applicable(a)) {
-      const int kcr = conv_row_kc(L.cout_pad);
+    const int row_mode = (L.d_wf && e->conv_row) ? conv_row_mode(a) : 0;
+    if (row_mode) {
+      const int kcr = conv_row_kc(L.cout_pad, row_mode);
       rc = encode_weight_map(e, &a.bmapf, L.d_wf, L.ktot_f, 3 * L.cout_pad, kcr, 3 * L.cout_pad);
       if (rc == IU_OK && L.residual >= 0) rc = encode_weight_map(e, &a.bmapi, e->d_ident, 64, 64, kcr, L.cout_pad);
       if (rc == IU_OK && L.d_wu)
@@ -1277,8 +1278,9 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
     a.mode = kEpiBf16;
     a.src_ptr[0] = (const __nv_bfloat16*)src0;
     a.src_ptr[1] = (const __nv_bfloat16*)src1;
-    if (e->conv_row && ksize == 3 && conv_row_applicable(a) && (rc = ensure_identity(e)) == IU_OK) {
-      const int ktot_f = 3 * cin_total, kcr = conv_row_kc(cout);
+    const int row_mode = (e->conv_row && ksize == 3) ? conv_row_mode(a) : 0;
+    if (row_mode && (rc = ensure_identity(e)) == IU_OK) {
+      const int ktot_f = 3 * cin_total, kcr = conv_row_kc(cout, row_mode);
       std::vector<uint16_t> pf((size_t)3 * cout * ktot_f, 0);
       pack_fold_segment(pf, e->fp16, ktot_f, 0, weight, cout, cout, cin_total, 0, cin0);
       if (src1) pack_fold_segment(pf, e->fp16, ktot_f, 3 * cin0, weight, cout, cout, cin_total, cin0, cin1);

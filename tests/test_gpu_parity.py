@@ -87,6 +87,9 @@ CONV_CASES = [
     ("row_upsrc_k32n16", 8, 12, 256, 32, 0, 16, 3, 1, False, True, "src"),
     ("row_k16n16", 8, 9, 256, 16, 0, 16, 3, 1, False, True, False),
     ("row_k16n16_tall", 8, 40, 128, 16, 0, 16, 3, 1, False, True, False),
+    # Cout 64 with more weights than shared memory holds: the row kernel streams the weight tiles with the A chunks
+    ("row_stream_upsrc_cat_k64n64", 8, 8, 128, 128, 64, 64, 3, 1, False, True, "src"),
+    ("row_stream_cat_k64n64", 8, 6, 128, 128, 64, 64, 3, 1, False, True, False),
     # ragged last row segment (width % 128 != 0)
     ("row_ragged_w160_k64n64", 8, 8, 160, 64, 0, 64, 3, 1, True, True, False),
     ("row_ragged_w320_upsrc_cat_n32", 8, 12, 320, 64, 64, 32, 3, 1, False, True, "src"),
