@@ -605,7 +605,8 @@ int conv_row_mode(const ConvArgs& a);
 //   Cout 64 (layer1, decoder block 2 conv2): 32-channel A stages x 2, 128-byte weight tiles, 4-row blocks, one
 //                                            staging buffer per group (72-80 KB of resident weights leave no more)
 //   Cout 64, streamed weights (decoder block 2 conv1, 264 KB of weights): 16-channel A stages x 3 that also carry the
-//                                            chunk's three weight tiles
+//                                            chunk's three weight tiles (measured slower than the resident
+//                                            configuration where the weights do fit: 208k vs 179k cycles on layer1)
 //   Cout 32 (decoder block 3):               16-channel A stages x 3, 8-row blocks, one staging buffer per group
 //                                            (conv1's four-slot + three-slot weight tiles take 84 KB)
 //   Cout 16 (decoder block 4, head):         16-channel A stages x 4, 8-row blocks, 2 rows per TMA store
