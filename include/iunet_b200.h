@@ -119,6 +119,32 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
                              const float* g1d_host, float gmax, float lo, uint8_t* out_u8, uint8_t* out_labels,
                              float* out_mean, unsigned flags);
 
+/* Tiled / blended mode of `predict_volumes` (predict.py:153,201,235-256): a uint8 volume
+ * [d][h][w] of any shape (host or device) is predicted in n_blocks cubic blocks of edge s (a multiple of 32) whose
+ * voxel (0,0,0) sits at volume coordinates origins[3*b .. 3*b+2] -- the first three columns of the reference's
+ * `padded_block_coords` from `get_block_coordinates` (predict.py:362-411); origins may be negative / overhang.  Per block,
+ * in the given order: reflect-padded extraction (`get_padded_block`, predict.py:291-316), `predict_block` over `axes`,
+ * `pred += mean * window`, `weight += window` over the part of the block inside the volume (predict.py:244-245); then
+ * out_u8[d][h][w][C] = uint8(255 * pred / max(weight, 1e-3)) (predict.py:255) and, optionally, labels = argmax_c pred.
+ * g1d: host pointer to the s-entry 1-D factor of `gaussian_3d(s)`, gmax / lo as for iu_engine_reduce.
+ * out_u8 / out_labels: host or device, either may be NULL. */
+int iu_engine_predict_tiled(iu_engine* e, const uint8_t* volume, int d, int h, int w, int s, int n_blocks,
+                            const int* origins, const int* axes, int n_axes, const float* g1d_host, float gmax,
+                            float lo, uint8_t* out_u8, uint8_t* out_labels, unsigned flags);
+
+/* The three steps of the tiled mode on their own (device buffers; used by the parity tests):
+ *   extract_block: `get_padded_block` (predict.py:291-316) -> uint8 [s][s][s];
+ *   blend_block:   per-axis probabilities of one block (layouts of iu_engine_predict_axis, row_block == s) ->
+ *                  pred[d][h][w][C] += mean * window, weight[d][h][w] += window (predict.py:244-245), fp32;
+ *   finalise:      `normalize_shard` (predict.py:252-255) over `voxels` voxels (+ optional argmax labels). */
+int iu_engine_extract_block(iu_engine* e, const uint8_t* volume_dev, int d, int h, int w, int i0, int j0, int k0, int s,
+                            uint8_t* out_dev, unsigned flags);
+int iu_engine_blend_block(iu_engine* e, const float* p0, const float* p1, const float* p2, const int* order, int n_axes,
+                          int s, int num_classes, const float* g1d_host, float gmax, float lo, float* pred_dev,
+                          float* weight_dev, int d, int h, int w, const int* origin, unsigned flags);
+int iu_engine_finalise(iu_engine* e, const float* pred_dev, const float* weight_dev, int64_t voxels, int num_classes,
+                       uint8_t* out_u8_dev, uint8_t* out_labels_dev, unsigned flags);
+
 /* Test hook: one tensor-core convolution exactly as the engine runs it.
  *   src0/src1: device bf16 NHWC [batch][h_in][w_in][cin]; src1 may be NULL (cin1 = 0);
  *   weight: host fp32 [cout][cin0+cin1][k][k] (PyTorch layout, source 0's channels first),

@@ -46,6 +46,16 @@ SIGNATURES = {
     "iu_engine_predict_volume": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.POINTER(_c.c_int),
                                             _c.c_int, _c.c_void_p, _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p,
                                             _c.c_void_p, _c.c_uint]),
+    "iu_engine_predict_tiled": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                           _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _c.c_int, _c.c_void_p, _c.c_float,
+                                           _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_uint]),
+    "iu_engine_extract_block": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                           _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint]),
+    "iu_engine_blend_block": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_int), _c.c_int,
+                                         _c.c_int, _c.c_int, _c.c_void_p, _c.c_float, _c.c_float, _c.c_void_p,
+                                         _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.POINTER(_c.c_int), _c.c_uint]),
+    "iu_engine_finalise": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p,
+                                      _c.c_void_p, _c.c_uint]),
     "iu_engine_conv_test": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
                                        _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,
                                        _c.c_int, _c.c_int, _c.c_void_p]),

@@ -189,6 +189,18 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
         if (m[c] > m[best]) best = c;                  // first maximum wins (np.argmax, predict.py:38)
       a.out_labels[vox] = (uint8_t)best;
     }
+    if (a.blend_pred != nullptr) {
+      if (z >= a.l0[0] && z < a.l1[0] && y >= a.l0[1] && y < a.l1[1] && x >= a.l0[2] && x < a.l1[2]) {
+        float wgt = __fmul_rn(__fmul_rn(__ldg(a.g1d + a.z0 + z), __ldg(a.g1d + y)), __ldg(a.g1d + x));
+        wgt = __fdiv_rn(wgt, a.gmax);
+        wgt = fminf(fmaxf(wgt, a.lo), 1.0f);           // predict.py:345
+        const size_t g = ((size_t)(a.b0[0] + z) * a.gh + (a.b0[1] + y)) * a.gw + (a.b0[2] + x);
+#pragma unroll
+        for (int c = 0; c < C; ++c)                    // predict.py:244
+          a.blend_pred[g * C + c] = __fadd_rn(a.blend_pred[g * C + c], __fmul_rn(m[c], wgt));
+        a.blend_weight[g] = __fadd_rn(a.blend_weight[g], wgt);   // predict.py:245
+      }
+    }
     if (a.out_u8 != nullptr) {
       uint8_t q[C];
       if (a.g1d != nullptr) {
@@ -209,6 +221,66 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
       for (int c = 0; c < C; ++c) a.out_u8[vox * C + c] = q[c];
     }
   }
+}
+
+// =========================================================================== tiled mode: block extraction / finalise
+// numpy 'reflect' of index i against a run of length len (period 2*(len-1), the edge sample is not repeated)
+__device__ __forceinline__ int reflect_index(int i, int len) {
+  if (len <= 1) return 0;
+  const int period = 2 * (len - 1);
+  int m = i % period;
+  if (m < 0) m += period;
+  return m < len ? m : period - m;
+}
+
+__global__ void __launch_bounds__(256) extract_block_kernel(const uint8_t* __restrict__ vol, int d, int h, int w, int i0,
+                                                            int j0, int k0, int s, uint8_t* __restrict__ out) {
+  // clipped box (predict.py:300-303); reflection is relative to the CLIPPED block, as np.pad sees it (predict.py:313)
+  const int ci0 = max(i0, 0), ci1 = min(i0 + s, d), cj0 = max(j0, 0), cj1 = min(j0 + s, h), ck0 = max(k0, 0), ck1 = min(k0 + s, w);
+  const size_t total = (size_t)s * s * s;
+  for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(o % s), y = (int)((o / s) % s), z = (int)(o / ((size_t)s * s));
+    const int gz = ci0 + reflect_index(i0 + z - ci0, ci1 - ci0);
+    const int gy = cj0 + reflect_index(j0 + y - cj0, cj1 - cj0);
+    const int gx = ck0 + reflect_index(k0 + x - ck0, ck1 - ck0);
+    out[o] = __ldg(vol + ((size_t)gz * h + gy) * w + gx);
+  }
+}
+
+cudaError_t launch_extract_block(const uint8_t* vol, int d, int h, int w, int i0, int j0, int k0, int s, uint8_t* out,
+                                 cudaStream_t stream) {
+  if (s < 1 || i0 >= d || j0 >= h || k0 >= w || i0 + s <= 0 || j0 + s <= 0 || k0 + s <= 0) return cudaErrorInvalidValue;
+  const size_t total = (size_t)s * s * s;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  extract_block_kernel<<<blocks, 256, 0, stream>>>(vol, d, h, w, i0, j0, k0, s, out);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) finalise_kernel(const float* __restrict__ pred, const float* __restrict__ weight,
+                                                       size_t voxels, int c, uint8_t* __restrict__ out_u8,
+                                                       uint8_t* __restrict__ out_labels) {
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < voxels; v += (size_t)gridDim.x * blockDim.x) {
+    const float den = fmaxf(__ldg(weight + v), 1e-3f);   // predict.py:253,255
+    int best = 0;
+    float best_p = 0.0f;
+    for (int k = 0; k < c; ++k) {
+      const float p = __ldg(pred + v * c + k);
+      if (out_u8 != nullptr) out_u8[v * c + k] = (uint8_t)(int)__fdiv_rn(__fmul_rn(255.0f, p), den);
+      if (k == 0 || p > best_p) {
+        best = k == 0 ? 0 : k;
+        best_p = p;
+      }
+    }
+    if (out_labels != nullptr) out_labels[v] = (uint8_t)best;
+  }
+}
+
+cudaError_t launch_finalise(const float* pred, const float* weight, size_t voxels, int num_classes, uint8_t* out_u8,
+                            uint8_t* out_labels, cudaStream_t stream) {
+  if (num_classes < 1) return cudaErrorInvalidValue;
+  const int blocks = (int)((voxels + 255) / 256 < 148 * 16 ? (voxels + 255) / 256 : 148 * 16);
+  finalise_kernel<<<blocks, 256, 0, stream>>>(pred, weight, voxels, num_classes, out_u8, out_labels);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_reduce(const ReduceArgs& args, cudaStream_t stream) {

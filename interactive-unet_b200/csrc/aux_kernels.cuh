@@ -36,7 +36,26 @@ struct ReduceArgs {
   uint8_t* out_u8;
   uint8_t* out_labels;
   float* out_mean;
+  // tiled / blended mode (`predict.py:235-245`): when blend_pred != nullptr the block's voxels inside the local crop
+  // [l0, l1) are accumulated into the whole-volume buffers
+  //   pred[g][c] += mean[c] * window,  weight[g] += window,   g = (block origin b0) + (z, y, x)
+  // (fp32, one thread per voxel, blocks processed one after the other on the stream: the reference's add order)
+  float* blend_pred;    // [gd][gh][gw][C]
+  float* blend_weight;  // [gd][gh][gw]
+  int gd, gh, gw;
+  int b0[3];            // volume coordinates of the block's voxel (0,0,0); may be negative (padding)
+  int l0[3], l1[3];     // local crop of the block that lies inside the volume
 };
 cudaError_t launch_reduce(const ReduceArgs& args, cudaStream_t stream);
+
+// `get_padded_block` (`predict.py:291-316`): out[s][s][s] = the box [b0, b0+s)^3 of the uint8 volume [d][h][w], clipped
+// to the volume and padded back to s^3 with numpy's 'reflect' mode (mirror without repeating the edge voxel).
+cudaError_t launch_extract_block(const uint8_t* vol, int d, int h, int w, int i0, int j0, int k0, int s, uint8_t* out,
+                                 cudaStream_t stream);
+
+// `normalize_shard` (`predict.py:252-255`): out = uint8(trunc(255 * pred / max(weight, 1e-3))) per voxel and class;
+// optional labels = argmax_c pred (first maximum wins).
+cudaError_t launch_finalise(const float* pred, const float* weight, size_t voxels, int num_classes, uint8_t* out_u8,
+                            uint8_t* out_labels, cudaStream_t stream);
 
 }  // namespace iu

@@ -1101,6 +1101,7 @@ int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float
       num_classes > 10)
     return e->fail(IU_ERR_INVALID, "reduce: bad arguments");
   ReduceArgs a;
+  memset(&a, 0, sizeof(a));
   a.p[0] = p0;
   a.p[1] = p1;
   a.p[2] = p2;
@@ -1210,6 +1211,186 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
   for (void* q : held) scratch_put(e, q);
   if (ce != cudaSuccess) return e->cuda_fail(ce, "predict_volume");
   return IU_OK;
+}
+
+int iu_engine_extract_block(iu_engine* e, const uint8_t* volume_dev, int d, int h, int w, int i0, int j0, int k0, int s,
+                            uint8_t* out_dev, unsigned flags) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!volume_dev || !out_dev || d < 1 || h < 1 || w < 1 || s < 1)
+    return e->fail(IU_ERR_INVALID, "extract_block: bad arguments");
+  cudaError_t ce = launch_extract_block(volume_dev, d, h, w, i0, j0, k0, s, out_dev, e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "launch extract_block (the block must intersect the volume)");
+  e->launches += 1;
+  return finish(e, flags);
+}
+
+int iu_engine_predict_tiled(iu_engine* e, const uint8_t* volume, int d, int h, int w, int s, int n_blocks,
+                            const int* origins, const int* axes, int n_axes, const float* g1d_host, float gmax,
+                            float lo, uint8_t* out_u8, uint8_t* out_labels, unsigned flags) {
+  int rc;
+  if (!check_engine(e, true, &rc)) return rc;
+  if (!volume || !origins || !axes || !g1d_host || n_blocks < 1 || d < 1 || h < 1 || w < 1 || s < 32 || s % 32 ||
+      n_axes < 1 || n_axes > 3 || (!out_u8 && !out_labels))
+    return e->fail(IU_ERR_INVALID, "predict_tiled: bad arguments (block edge must be a multiple of 32)");
+  bool seen[3] = {false, false, false};
+  for (int i = 0; i < n_axes; ++i) {
+    if (axes[i] < 0 || axes[i] > 2 || seen[axes[i]])
+      return e->fail(IU_ERR_INVALID, "predict_tiled: axes must be distinct values from {0,1,2}");
+    seen[axes[i]] = true;
+  }
+  const int c = e->num_classes;
+  const size_t vox = (size_t)d * h * w, bvox = (size_t)s * s * s;
+  std::vector<void*> held;
+  auto release = [&]() {
+    cudaStreamSynchronize(e->stream);
+    for (void* p : held) scratch_put(e, p);
+  };
+  auto grab = [&](size_t bytes, void** out) {
+    int r = scratch_get(e, bytes, out);
+    if (r == IU_OK) held.push_back(*out);
+    return r;
+  };
+#define IU_TILED_TRY(expr_)  \
+  if ((rc = (expr_)) != IU_OK) { \
+    release();               \
+    return rc;               \
+  }
+#define IU_TILED_CUDA(call_, what_)            \
+  {                                            \
+    cudaError_t ce_ = (call_);                 \
+    if (ce_ != cudaSuccess) {                  \
+      release();                               \
+      return e->cuda_fail(ce_, what_);         \
+    }                                          \
+  }
+  const uint8_t* vol_dev = volume;
+  if (!is_device_ptr(volume)) {
+    void* staged = nullptr;
+    IU_TILED_TRY(grab(vox, &staged));
+    IU_TILED_CUDA(cudaMemcpyAsync(staged, volume, vox, cudaMemcpyHostToDevice, e->stream), "cudaMemcpyAsync(volume)");
+    vol_dev = (const uint8_t*)staged;
+  }
+  float *pred = nullptr, *weight = nullptr, *g_dev = nullptr;
+  uint8_t* block = nullptr;
+  float* p[3] = {nullptr, nullptr, nullptr};
+  IU_TILED_TRY(grab(vox * c * 4, (void**)&pred));
+  IU_TILED_TRY(grab(vox * 4, (void**)&weight));
+  IU_TILED_TRY(grab(bvox, (void**)&block));
+  IU_TILED_TRY(grab((size_t)s * 4, (void**)&g_dev));
+  for (int i = 0; i < n_axes; ++i) IU_TILED_TRY(grab(bvox * c * 4, (void**)&p[axes[i]]));
+  IU_TILED_CUDA(cudaMemsetAsync(pred, 0, vox * c * 4, e->stream), "cudaMemsetAsync(pred)");
+  IU_TILED_CUDA(cudaMemsetAsync(weight, 0, vox * 4, e->stream), "cudaMemsetAsync(weight)");
+  IU_TILED_CUDA(cudaMemcpyAsync(g_dev, g1d_host, (size_t)s * 4, cudaMemcpyHostToDevice, e->stream), "cudaMemcpyAsync(window)");
+  for (int b = 0; b < n_blocks; ++b) {                     // the reference's block order (predict.py:235)
+    const int i0 = origins[3 * b], j0 = origins[3 * b + 1], k0 = origins[3 * b + 2];
+    IU_TILED_CUDA(launch_extract_block(vol_dev, d, h, w, i0, j0, k0, s, block, e->stream), "launch extract_block");
+    e->launches += 1;
+    for (int i = 0; i < n_axes; ++i)
+      IU_TILED_TRY(iu_engine_predict_axis(e, block, IU_DTYPE_U8, s, axes[i], 0, s, p[axes[i]], 0, s, s, IU_FLAG_ASYNC));
+    ReduceArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 3; ++i) a.p[i] = p[i];
+    for (int i = 0; i < n_axes; ++i) a.order[i] = axes[i];
+    a.n_axes = n_axes;
+    a.n = s;
+    a.t = s;
+    a.z0 = 0;
+    a.num_classes = c;
+    a.g1d = g_dev;
+    a.gmax = gmax;
+    a.lo = lo;
+    a.blend_pred = pred;
+    a.blend_weight = weight;
+    a.gd = d;
+    a.gh = h;
+    a.gw = w;
+    const int org[3] = {i0, j0, k0}, dims[3] = {d, h, w};
+    for (int k = 0; k < 3; ++k) {
+      a.b0[k] = org[k];
+      a.l0[k] = org[k] < 0 ? -org[k] : 0;                                    // predict.py:401-404
+      a.l1[k] = org[k] + s > dims[k] ? dims[k] - org[k] : s;
+    }
+    prof_begin(e, IU_PROF_REDUCE);
+    cudaError_t ce = launch_reduce(a, e->stream);
+    prof_end(e);
+    e->launches += 1;
+    IU_TILED_CUDA(ce, "launch reduce (blend)");
+  }
+  const bool u8_dev = out_u8 && is_device_ptr(out_u8), lab_dev = out_labels && is_device_ptr(out_labels);
+  uint8_t *d_u8 = out_u8, *d_lab = out_labels;
+  if (out_u8 && !u8_dev) IU_TILED_TRY(grab(vox * c, (void**)&d_u8));
+  if (out_labels && !lab_dev) IU_TILED_TRY(grab(vox, (void**)&d_lab));
+  IU_TILED_CUDA(launch_finalise(pred, weight, vox, c, d_u8, d_lab, e->stream), "launch finalise");
+  e->launches += 1;
+  if (out_u8 && !u8_dev) IU_TILED_CUDA(cudaMemcpyAsync(out_u8, d_u8, vox * c, cudaMemcpyDeviceToHost, e->stream), "copy u8");
+  if (out_labels && !lab_dev) IU_TILED_CUDA(cudaMemcpyAsync(out_labels, d_lab, vox, cudaMemcpyDeviceToHost, e->stream), "copy labels");
+#undef IU_TILED_TRY
+#undef IU_TILED_CUDA
+  (void)flags;  // host outputs and the scratch hand-back need the stream drained: always synchronous
+  cudaError_t ce = cudaStreamSynchronize(e->stream);
+  for (void* q : held) scratch_put(e, q);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "predict_tiled");
+  return IU_OK;
+}
+
+int iu_engine_blend_block(iu_engine* e, const float* p0, const float* p1, const float* p2, const int* order, int n_axes,
+                          int s, int num_classes, const float* g1d_host, float gmax, float lo, float* pred_dev,
+                          float* weight_dev, int d, int h, int w, const int* origin, unsigned flags) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!order || n_axes < 1 || n_axes > 3 || s < 1 || num_classes < 1 || num_classes > 10 || !g1d_host || !pred_dev ||
+      !weight_dev || !origin)
+    return e->fail(IU_ERR_INVALID, "blend_block: bad arguments");
+  ReduceArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p[0] = p0;
+  a.p[1] = p1;
+  a.p[2] = p2;
+  for (int i = 0; i < n_axes; ++i) {
+    if (order[i] < 0 || order[i] > 2 || a.p[order[i]] == nullptr)
+      return e->fail(IU_ERR_INVALID, "blend_block: axis in `order` has no probability buffer");
+    a.order[i] = order[i];
+  }
+  a.n_axes = n_axes;
+  a.n = s;
+  a.t = s;
+  a.num_classes = num_classes;
+  a.gmax = gmax;
+  a.lo = lo;
+  a.blend_pred = pred_dev;
+  a.blend_weight = weight_dev;
+  a.gd = d;
+  a.gh = h;
+  a.gw = w;
+  const int dims[3] = {d, h, w};
+  for (int k = 0; k < 3; ++k) {
+    a.b0[k] = origin[k];
+    a.l0[k] = origin[k] < 0 ? -origin[k] : 0;
+    a.l1[k] = origin[k] + s > dims[k] ? dims[k] - origin[k] : s;
+  }
+  float* g_dev = nullptr;
+  if ((rc = scratch_get(e, (size_t)s * 4, (void**)&g_dev)) != IU_OK) return rc;
+  cudaError_t ce = cudaMemcpyAsync(g_dev, g1d_host, (size_t)s * 4, cudaMemcpyHostToDevice, e->stream);
+  a.g1d = g_dev;
+  if (ce == cudaSuccess) ce = launch_reduce(a, e->stream);
+  e->launches += 1;
+  cudaStreamSynchronize(e->stream);  // the window table goes back to the pool
+  scratch_put(e, g_dev);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "launch reduce (blend)");
+  return finish(e, flags);
+}
+
+int iu_engine_finalise(iu_engine* e, const float* pred_dev, const float* weight_dev, int64_t voxels, int num_classes,
+                       uint8_t* out_u8_dev, uint8_t* out_labels_dev, unsigned flags) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!pred_dev || !weight_dev || voxels < 1 || num_classes < 1 || (!out_u8_dev && !out_labels_dev))
+    return e->fail(IU_ERR_INVALID, "finalise: bad arguments");
+  cudaError_t ce = launch_finalise(pred_dev, weight_dev, (size_t)voxels, num_classes, out_u8_dev, out_labels_dev, e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "launch finalise");
+  e->launches += 1;
+  return finish(e, flags);
 }
 
 int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* src1, int cin1, int batch, int h_in,

@@ -236,6 +236,54 @@ class Engine:
                 self._h, vp, _dtype_code(volume), n, c_axes, len(axes), gp, float(gmax), float(lo),
                 _ptr(out_u8)[0], _ptr(out_labels)[0], _ptr(out_mean)[0], 0))
 
+    # ------------------------------------------------------------------ tiled / blended mode (predict.py:201,235-256)
+    def predict_tiled(self, volume, input_size, origins, axes=(0, 1, 2), window=None, out_u8=None, out_labels=None):
+        """uint8 volume `[D,H,W]` (numpy or CUDA tensor) predicted in cubic blocks of edge `input_size` whose voxel
+        (0,0,0) sits at `origins[b]` (the first three columns of `padded_block_coords`); Gaussian-blended, quantised."""
+        d, h, w = (int(v) for v in volume.shape)
+        org = np.ascontiguousarray(np.asarray(origins, dtype=np.int32).reshape(-1, 3))
+        c_axes = (ctypes.c_int * len(axes))(*[int(a) for a in axes])
+        g, gmax, lo = window if window is not None else gaussian_window_1d(input_size)
+        vp, _ = _ptr(volume)
+        gp, _g = _ptr(g)
+        with self._lock:
+            self._sync_torch(volume, out_u8, out_labels)
+            self._check(self._lib.iu_engine_predict_tiled(
+                self._h, vp, d, h, w, int(input_size), int(org.shape[0]), org.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                c_axes, len(axes), gp, float(gmax), float(lo), _ptr(out_u8)[0], _ptr(out_labels)[0], 0))
+
+    def extract_block(self, volume, origin, size):
+        """`get_padded_block` on a CUDA uint8 volume -> CUDA uint8 `[size,size,size]`."""
+        d, h, w = (int(v) for v in volume.shape)
+        out = torch.empty((size, size, size), dtype=torch.uint8, device=volume.device)
+        with self._lock:
+            self._sync_torch(volume)
+            self._check(self._lib.iu_engine_extract_block(self._h, _ptr(volume)[0], d, h, w, int(origin[0]), int(origin[1]),
+                                                          int(origin[2]), int(size), _ptr(out)[0], 0))
+        return out
+
+    def blend_block(self, probs, order, size, window, pred, weight, origin):
+        """`pred[block] += mean * window; weight[block] += window` (predict.py:244-245) for one block's per-axis
+        probabilities (CUDA fp32, layouts of `predict_axis`); `pred` `[D,H,W,C]`, `weight` `[D,H,W]` CUDA fp32."""
+        d, h, w = (int(v) for v in weight.shape)
+        ptrs = [ctypes.c_void_p(probs[a].data_ptr()) if a in probs and probs[a] is not None else None for a in (0, 1, 2)]
+        c_order = (ctypes.c_int * len(order))(*[int(a) for a in order])
+        c_org = (ctypes.c_int * 3)(*[int(v) for v in origin])
+        g, gmax, lo = window
+        gp, _g = _ptr(g)
+        with self._lock:
+            self._sync_torch(*[p for p in probs.values() if p is not None], pred, weight)
+            self._check(self._lib.iu_engine_blend_block(
+                self._h, ptrs[0], ptrs[1], ptrs[2], c_order, len(order), int(size), int(self.num_classes), gp, float(gmax),
+                float(lo), _ptr(pred)[0], _ptr(weight)[0], d, h, w, c_org, 0))
+
+    def finalise(self, pred, weight, out_u8=None, out_labels=None):
+        """`normalize_shard` (predict.py:252-255) over CUDA fp32 `pred` / `weight` -> CUDA uint8 (and argmax labels)."""
+        with self._lock:
+            self._sync_torch(pred, weight, out_u8, out_labels)
+            self._check(self._lib.iu_engine_finalise(self._h, _ptr(pred)[0], _ptr(weight)[0], int(weight.numel()),
+                                                     int(pred.shape[-1]), _ptr(out_u8)[0], _ptr(out_labels)[0], 0))
+
     # ------------------------------------------------------------------ test hook
     def conv_test(self, src0, src1, weight, bias, ksize, stride, residual=None, relu=True, up2x=False,
                   src0_up=False):

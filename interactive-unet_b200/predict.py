@@ -123,18 +123,70 @@ def predict_block(model, block, num_classes=2, batch_size=8, axes=[0, 1, 2]):
     return out
 
 
+def gaussian_3d(input_size, sigma=0.125, eps=1e-3):
+    """`predict.py:327-347` (host helper, same values): the 3-D blending window of one block."""
+    sigma = sigma * input_size
+    coords = np.arange(input_size, dtype=np.float32) - (input_size - 1) / 2.0
+    g = np.exp(-(coords ** 2) / (2 * sigma ** 2)).astype(np.float32)
+    g /= g.max()
+    gaussian = g[:, None, None] * g[None, :, None] * g[None, None, :]
+    gaussian /= gaussian.max()
+    return np.clip(gaussian, max(gaussian.min(), eps), 1.0)
+
+
+def get_block_coordinates(volume_shape, input_size=256, overlap=0.25):
+    """`predict.py:362-411`: (block_coords, padded_block_coords, local_block_coords), one row of six ints per block,
+    blocks in the reference's nested (i, j, k) order with the padding centred on the volume."""
+    volume_shape = np.asarray(volume_shape)
+    step = input_size - overlap * input_size
+    blocks_per_axis = np.ceil((volume_shape - overlap * input_size) / step).astype(int)
+    padded_volume_shape = np.round(blocks_per_axis * input_size - (blocks_per_axis - 1) * input_size * overlap).astype(int)
+    shift = (padded_volume_shape - volume_shape) // 2
+    shift6 = np.concatenate([shift, shift])
+    block_coords, padded_block_coords, local_block_coords = [], [], []
+    for i in range(blocks_per_axis[0]):
+        for j in range(blocks_per_axis[1]):
+            for k in range(blocks_per_axis[2]):
+                lo = np.array([i, j, k]) * input_size * (1 - overlap)
+                padded = (np.concatenate([lo, lo + input_size]) - shift6).astype(int)
+                clipped = np.concatenate([np.maximum(padded[:3], 0), np.minimum(padded[3:], volume_shape)])
+                padded_block_coords.append(padded)
+                block_coords.append(clipped)
+                local_block_coords.append(clipped - np.concatenate([padded[:3], padded[:3]]))
+    return np.array(block_coords), np.array(padded_block_coords), np.array(local_block_coords)
+
+
+def get_padded_block(volume, i0, j0, k0, i1, j1, k1):
+    """`predict.py:291-316`: the box clipped to the volume and padded back with numpy's 'reflect' mode."""
+    shape = volume.shape
+    before = [max(0, -i0), max(0, -j0), max(0, -k0)]
+    after = [max(0, i1 - shape[0]), max(0, j1 - shape[1]), max(0, k1 - shape[2])]
+    block = volume[max(i0, 0):min(i1, shape[0]), max(j0, 0):min(j1, shape[1]), max(k0, 0):min(k1, shape[2])]
+    return np.pad(block, tuple(zip(before, after)), mode='reflect')
+
+
+def get_shard_coordinates(volume_shape, shard_size=128):
+    """`predict.py:318-325`."""
+    starts = [np.arange(0, s, shard_size) for s in volume_shape]
+    c = np.stack(np.meshgrid(*starts, indexing='ij'), -1).reshape(-1, 3)
+    return np.concatenate([c, np.minimum(c + shard_size, volume_shape)], axis=1)
+
+
 def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=0.25, batch_size=None,
                          axes=[0, 1, 2], return_labels=False, out=None, out_labels=None):
-    """In-memory core of `predict_volumes` (`predict.py:153,201,235-256`): uint8 volume `[N,N,N]`
-    (numpy, or a CUDA tensor to keep everything device-resident) -> uint8 probabilities `[N,N,N,C]`
-    (and uint8 argmax labels `[N,N,N]` with `return_labels=True`), same container kind as the input.
+    """In-memory core of `predict_volumes` (`predict.py:153,201,235-256`): uint8 volume `[D,H,W]` (numpy, or a CUDA
+    tensor to keep everything device-resident) -> uint8 probabilities `[D,H,W,C]` (and uint8 argmax labels `[D,H,W]`
+    with `return_labels=True`), same container kind as the input.  A cubic volume of edge `input_size` is one block
+    (the fused single-block path); anything else is tiled into `input_size`^3 blocks with `overlap`, reflect padding
+    and Gaussian blending exactly as the reference does, all on the device.
     `out` / `out_labels` may be preallocated (e.g. pinned host arrays) to avoid per-call allocation."""
-    n = volume.shape[0]
-    input_size = n if input_size is None else input_size
-    if tuple(volume.shape) != (n, n, n) or input_size != n:
-        raise NotImplementedError(
-            "volumes larger than input_size (tiled / blended mode, predict.py:201,235-245) are not on the "
-            "device path yet: call with input_size == volume edge")
+    shape = tuple(int(v) for v in volume.shape)
+    if len(shape) != 3:
+        raise ValueError("predict_volume_array expects a 3-D uint8 volume")
+    input_size = shape[0] if input_size is None else int(input_size)
+    if input_size % 32:
+        raise RuntimeError(f"Wrong input shape height={input_size}, width={input_size}. Expected image height and width "
+                           f"divisible by 32.")
     eng = model.engine()
     if eng.num_classes != num_classes:
         raise ValueError(f"model has {eng.num_classes} classes, num_classes={num_classes} requested")
@@ -142,18 +194,25 @@ def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=
     window = gaussian_window_1d(input_size, sigma=0.125)               # predict.py:153
     lab = out_labels
     if isinstance(volume, torch.Tensor):
+        volume = volume.contiguous()
         if out is None:
-            out = torch.empty((n, n, n, num_classes), dtype=torch.uint8, device=volume.device)
+            out = torch.empty(shape + (num_classes,), dtype=torch.uint8, device=volume.device)
         if lab is None and return_labels:
-            lab = torch.empty((n, n, n), dtype=torch.uint8, device=volume.device)
+            lab = torch.empty(shape, dtype=torch.uint8, device=volume.device)
     else:
         volume = np.ascontiguousarray(volume)
         if out is None:
-            out = np.empty((n, n, n, num_classes), dtype=np.uint8)
+            out = np.empty(shape + (num_classes,), dtype=np.uint8)
         if lab is None and return_labels:
-            lab = np.empty((n, n, n), dtype=np.uint8)
+            lab = np.empty(shape, dtype=np.uint8)
     try:
-        eng.predict_volume(volume, axes=list(axes), window=window, out_u8=out, out_labels=lab)
+        if shape == (input_size,) * 3:
+            eng.predict_volume(volume, axes=list(axes), window=window, out_u8=out, out_labels=lab)
+        else:
+            if volume.dtype not in (np.uint8, torch.uint8):
+                raise TypeError("the tiled mode reads uint8 volumes (predict.py:237)")
+            _, padded, _ = get_block_coordinates(np.array(shape), input_size=input_size, overlap=overlap)
+            eng.predict_tiled(volume, input_size, padded[:, :3], axes=list(axes), window=window, out_u8=out, out_labels=lab)
     finally:
         eng.set_max_batch(0)
     return (out, lab) if return_labels else out

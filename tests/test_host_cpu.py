@@ -106,6 +106,28 @@ def test_load_from_checkpoint_reference_format(tmp_path):
         assert torch.equal(m.state_dict()[k], v)
 
 
+def test_tiling_helpers_match_reference_golden(golden_dir):
+    """The drop-in `get_block_coordinates` / `get_padded_block` / `get_shard_coordinates` / `gaussian_3d`
+    (predict.py:291-347,362-411) against fixtures recorded from the verbatim reference."""
+    from interactive_unet_b200 import predict as P
+    g = np.load(os.path.join(golden_dir, "coordinates.npz"))
+    n = 0
+    while f"case{n}_args" in g:
+        a = g[f"case{n}_args"]
+        c, p, l = P.get_block_coordinates(np.array(a[:3]), input_size=int(a[3]), overlap=a[4] / 100.0)
+        assert np.array_equal(c, g[f"case{n}_clipped"]) and np.array_equal(p, g[f"case{n}_padded"])
+        assert np.array_equal(l, g[f"case{n}_local"])
+        n += 1
+    assert n >= 7
+    assert np.array_equal(P.get_shard_coordinates((100, 80, 60), 32), g["shards_100_80_60_32"])
+    pb = np.load(os.path.join(golden_dir, "padded_block.npz"))
+    for i, box in enumerate(pb["boxes"]):
+        assert np.array_equal(P.get_padded_block(pb["volume"], *box), pb[f"out{i}"])
+    gw = np.load(os.path.join(golden_dir, "gaussian3d.npz"))
+    for size in (8, 16, 32, 48):
+        assert np.array_equal(P.gaussian_3d(size), gw[f"w{size}"])
+
+
 def test_gaussian_window_parameters():
     from interactive_unet_b200 import gaussian_window_1d
     g, gmax, lo = gaussian_window_1d(64)
