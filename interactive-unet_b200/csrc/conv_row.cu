@@ -140,6 +140,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
   auto acc_full = [&](int b) { return b_full + 8u + 8u * b; };
   auto acc_empty = [&](int b) { return b_full + 24u + 8u * b; };
   const uint32_t tmem_slot = b_full + 40u;
+  // staging hand-off between an epilogue group and its store thread: full (4 warp arrivals) / empty (store thread)
+  auto stg_full = [&](int g, int b) { return b_full + 48u + 8u * (g * 2 + b); };
+  auto stg_empty = [&](int g, int b) { return b_full + 80u + 8u * (g * 2 + b); };
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
 
@@ -164,6 +167,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
       mbar_init(acc_full(b), 1);
       mbar_init(acc_empty(b), 8);
     }
+    for (int g = 0; g < 2; ++g)
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(stg_full(g, b), 4);
+        mbar_init(stg_empty(g, b), 1);
+      }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -383,7 +391,6 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     const int g = (warp - 2) >> 2;
     const int quarter = warp & 3;           // TMEM lanes [32q, 32q+32) = pixels [32q, 32q+32) of the row segment
     const int px = quarter * 32 + lane;
-    const bool leader = (warp - 2) % 4 == 0 && lane == 0;
     const uint32_t stg_g = stg_base + g * NSTG * Cfg::STG;  // this group's staging buffer(s)
     uint32_t nstore = 0;
     // 16-byte chunk c of pixel px lives at chunk (c ^ swz) of its row: the TMA swizzle of a CO*2-byte wide box
@@ -431,15 +438,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
               }
             }
           }
-          // 2. staging buffer free? (the last store out of it has finished reading)  3. swizzled writes  4. one TMA store
-          const uint32_t stg = stg_g + (NSTG == 2 ? (nstore & 1u) * Cfg::STG : 0u);
-          const uint32_t stg_px = stg + px_off;
+          // 2. wait until the store thread has drained this staging buffer  3. swizzled writes + proxy fence
+          // 4. hand the box to the store thread (warp 13 / 17): the TMA issue, its fence and the wait for the bulk
+          //    read never sit on the epilogue warps' critical path, and no CTA-level barrier is involved
+          const uint32_t sb = NSTG == 2 ? (nstore & 1u) : 0u;
+          const uint32_t use = nstore / NSTG;
+          const uint32_t stg_px = stg_g + sb * Cfg::STG + px_off;
           ++nstore;
-          if (leader) {
-            if constexpr (NSTG == 2) bulk_wait_read_1();
-            else bulk_wait_read_0();
-          }
-          group_bar(1 + g);
+          row_warp_wait(stg_empty(g, sb), (use & 1u) ^ 1u, lane);
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
 #pragma unroll
@@ -450,12 +456,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                            : "memory");
             }
           }
-          group_bar(1 + g);
-          if (leader) {
-            fence_proxy_async();  // the group's staging writes (ordered by the barrier) -> visible to the TMA store
-            tma_store_4d(&a.omap, stg, 0, tc.x0, tc.y0 + r0, tc.n);  // rows beyond the image are clipped by the TMA unit
-            bulk_commit();
-          }
+          fence_proxy_async();  // this thread's staging writes -> visible to the async proxy (the TMA store)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(stg_full(g, sb));
         }
       } else if (a.num_classes <= 4) {
         // head (2-4 classes): the group's R/2 rows are loaded from TMEM together and their softmaxes run interleaved,
@@ -495,8 +498,38 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
       atomicAdd(a.debug + 8, (unsigned long long)w_full);
       atomicAdd(a.debug + 9, (unsigned long long)t_body);
     }
-    if (leader) bulk_wait_all();
-  } else if ((warp & 3) != 1) {
+  } else if ((warp & 3) == 1) {
+    // ------------------------------------------------------------ store threads: warp 13 serves epilogue group 0, warp 17 group 1
+    if (a.mode == kEpiBf16 && lane == 0) {
+      const int g = warp == 13 ? 0 : 1;
+      const uint32_t stg_g = stg_base + g * NSTG * Cfg::STG;
+      uint32_t nstore = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const RowTile tc = row_decode(a, tile, R);
+        for (int rb = 0; rb < R / 2; rb += RB) {
+          const int r0 = g * (R / 2) + rb;
+          if (tc.y0 + r0 >= a.out_h) break;
+          const uint32_t sb = NSTG == 2 ? (nstore & 1u) : 0u;
+          const uint32_t use = nstore / NSTG;
+          mbar_wait(stg_full(g, sb), use & 1u);
+          tma_store_4d(&a.omap, stg_g + sb * Cfg::STG, 0, tc.x0, tc.y0 + r0, tc.n);  // rows beyond the image are clipped
+          bulk_commit();
+          if constexpr (NSTG == 2) {
+            // keep one store in flight: the PREVIOUS box has been read out of its buffer -> hand that buffer back
+            if (nstore > 0) {
+              bulk_wait_read_1();
+              mbar_arrive(stg_empty(g, sb ^ 1u));
+            }
+          } else {
+            bulk_wait_read_0();
+            mbar_arrive(stg_empty(g, 0));
+          }
+          ++nstore;
+        }
+      }
+      bulk_wait_all();
+    }
+  } else {
     // ------------------------------------------------------------ gather: (R+2) rows x 130 pixels x KC channels per stage
     // Thread t owns fixed (plane, pixel) columns of the stage and walks the rows: per copy one bounds test and one
     // pointer add.  Lanes run over the planes of consecutive pixels, so a warp reads contiguous global memory.
