@@ -1,4 +1,5 @@
 #!/bin/bash
+# Development loop on a B200 (through gpurun): row-kernel conv tests, the whole parity suite, a short bench, role counters.
 set -u
 O=gpurun_out; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "test_conv and row" > $O/pytest_row.log 2>&1; echo "row conv rc=$?"; tail -4 $O/pytest_row.log

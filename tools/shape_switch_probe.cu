@@ -1,6 +1,6 @@
 // Does switching the MMA shape (instruction descriptor N) between consecutive tcgen05.mma cost anything?  (B200 probe)
 // The row-folded kernel issues, per filter column, MMAs of N = CO, 2CO, 3CO, ..., 3CO, 2CO, CO.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I interactive-unet_b200/csrc tools/idesc_probe.cu -o /tmp/ip
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I interactive-unet_b200/csrc tools/shape_switch_probe.cu -o /tmp/ip
 #include <cstdio>
 #include <vector>
 
