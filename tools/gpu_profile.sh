@@ -7,7 +7,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > $O/b_final_ref.json 2> $
 python tools/profile_forward.py --batch 74 --iters 2 > $O/pf_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_final.csv \
     python tools/profile_forward.py --batch 74 --iters 2 > $O/ncu_launch.log 2>&1
-for spec in "layer1_row64:43" "layer3_pertap:59" "dec2conv1_halo:79" "dec4conv2_row16:84"; do
+for spec in "layer1_row64:43" "layer3_pertap:59" "dec2conv1_rowstream:79" "dec4conv2_row16:84"; do
   name=${spec%%:*}; skip=${spec##*:}
   ncu --set full --clock-control none --import-source on -k regex:'conv_(row|tc|halo)' -s $skip -c 1 \
       -o $O/r01_full_$name python tools/profile_forward.py --batch 74 --iters 2 > $O/ncu_full_$name.log 2>&1
