@@ -677,7 +677,12 @@ int conv_row_mode(const ConvArgs& a) {
   const int segs = (a.out_w + kRowSeg - 1) / kRowSeg;
   if (a.out_w < kRowSeg || a.out_w * 5 < 3 * kRowSeg * segs || a.out_h < 1) return 0;
   if (a.mode == kEpiBf16) {
-    if (a.cout == 64) return row_fits<IU_ROW_CFG64>(a) ? 1 : (row_fits<IU_ROW_CFG64S>(a) ? 2 : 0);
+    if (a.cout == 64) {
+      // with resident weights the 16x16-block kernel is nearly as fast, so it takes over below 75 % utilisation
+      // (width 160: two segments for 1.25); the streamed-weights layer stays here down to 60 %
+      if (row_fits<IU_ROW_CFG64>(a)) return a.out_w * 4 >= 3 * kRowSeg * segs ? 1 : 0;
+      return row_fits<IU_ROW_CFG64S>(a) ? 2 : 0;
+    }
     if (a.cout == 32) return row_fits<IU_ROW_CFG32>(a) ? 1 : 0;
     if (a.cout == 16) return row_fits<IU_ROW_CFG16>(a) ? 1 : 0;
     return 0;
