@@ -52,7 +52,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug must surface as a trapped kernel (a CUDA error the host reports),
 // never as a hung GPU.  ~2^28 polls is seconds; a healthy wait is microseconds.
 // Waiters back off between polls: with ~17 warps of a CTA spinning on mbarrier.try_wait the MMA issuer's stream ran
-// 10-35 % slower (profiles/r01_role_counters_v9.txt); 32 ns costs nothing measurable in wake-up latency.
+// 10-35 % slower (profiles/r01_role_counters_v10.txt); 32 ns costs nothing measurable in wake-up latency.
 #ifndef IU_WAIT_BACKOFF
 #define IU_WAIT_BACKOFF 32
 #endif
