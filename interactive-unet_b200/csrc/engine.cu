@@ -731,17 +731,19 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
   return IU_OK;
 }
 
-// Slices per internal batch.  Every conv tiles its output in 128- or 256-pixel blocks whose count per slice is a
-// power of two (>= 4 with the Cout tiles at 512^2 and above), and a B200 has 148 = 4 x 37 SMs: a multiple of 37
-// slices makes every layer's tile count a multiple of the SM count (no partial last wave).  74 slices at 512^2
-// also halve the per-layer launch overhead relative to 37; larger images use 37 to bound the workspace.
+// Slices per internal batch.  Bigger batches amortise the 46 launches per pass and their prologues (weight tiles,
+// TMEM allocation); measured on B200 at 512^2: 37 / 74 / 148 / 256 slices -> 141.4 / 136.5 / 135.4 / 133.9 ms per
+// 512^3 volume (keeping producer -> consumer tensors inside L2 with small batches does NOT pay).  Target 256 slices
+// of 512^2 (12 GB of 16-bit activations), scaled by the image area, and split the work into equal batches so that no
+// small ragged batch is left over.
 int auto_batch(const iu_engine* e, int h, int w, int want) {
   const double rel = ((double)h * w) / (512.0 * 512.0);
-  int mult = (int)std::floor(2.0 / rel + 0.5);
-  mult = std::max(1, std::min(4, mult));
-  int nb = e->auto_batch_override > 0 ? e->auto_batch_override : 37 * mult;
-  if (e->max_batch > 0) nb = std::min(nb, e->max_batch);
-  return std::max(1, std::min(nb, want));
+  int target = std::max(1, (int)std::floor(256.0 / rel + 0.5));
+  if (e->auto_batch_override > 0) target = e->auto_batch_override;
+  if (e->max_batch > 0) target = std::min(target, e->max_batch);
+  target = std::max(1, std::min(target, want));
+  const int nbatches = (want + target - 1) / target;
+  return (want + nbatches - 1) / nbatches;
 }
 
 // Kernel choice per conv.  The halo-tile kernel fetches every activation once per channel chunk instead of once

@@ -19,8 +19,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
 }
 
 // every CTA streams `iters` boxes (rows x 130 px x planes) from its own region of a big NHWC tensor, 3 in flight
-__global__ void __launch_bounds__(128) tma_gather(const __grid_constant__ CUtensorMap map, int rows, int planes, int iters, int h, int w,
-                                                  unsigned long long* out) {
+__device__ __forceinline__ void cpa16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// `with_cpasync`: 8 more warps run a 16-byte cp.async gather (same volume per box) concurrently -- do the two paths add up?
+__global__ void __launch_bounds__(384) tma_gather(const __grid_constant__ CUtensorMap map, int rows, int planes, int iters, int h, int w,
+                                                  unsigned long long* out, const uint4* gsrc, int with_cpasync, int with_tma) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   __shared__ uint64_t bars[4];
@@ -31,7 +36,27 @@ __global__ void __launch_bounds__(128) tma_gather(const __grid_constant__ CUtens
     fence_mbar_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  __shared__ volatile int tma_done;
+  if (threadIdx.x == 0) tma_done = 0;
+  __syncthreads();
+  if (threadIdx.x >= 128) {
+    if (with_cpasync) {
+      const int t = threadIdx.x - 128;
+      const uint32_t dst0 = base + 150 * 1024 + t * 16;
+      const uint4* src = gsrc + (size_t)blockIdx.x * 65536 + t;
+      const int per_box = rows * 130 * planes / 256 + 1;  // copies per thread per box
+      long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        for (int k = 0; k < per_box; ++k) cpa16(dst0 + (k & 7) * 4096, src + ((i * per_box + k) * 256 & 65535));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (t == 0) out[256 + blockIdx.x] = (unsigned long long)(clock64() - t0);
+    }
+    return;
+  }
+  if (threadIdx.x == 0 && with_tma) {
     long long t0 = clock64();
     const int blocks_y = h / 8, blocks_x = w / 128;
     for (int i = 0; i < iters + 3; ++i) {
@@ -58,6 +83,9 @@ int main() {
   EncodeFn encode = (EncodeFn)fn;
   unsigned long long* d_out;
   cudaMalloc(&d_out, 1024 * 8);
+  void* gsrc;
+  cudaMalloc(&gsrc, (size_t)149 * 65536 * 16);
+  cudaMemset(gsrc, 0, (size_t)149 * 65536 * 16);
   const int n = 74, h = 512, w = 512;
   for (int c : {16, 32, 64}) {
     void* src;
@@ -79,20 +107,26 @@ int main() {
       }
       const int iters = 64;
       cudaFuncSetAttribute(tma_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      tma_gather<<<148, 128, 200 * 1024>>>(map, rows, planes, iters, h, w, d_out);
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) {
-        printf("C=%d rows=%d: %s\n", c, rows, cudaGetErrorString(e));
-        return 1;
-      }
-      std::vector<unsigned long long> hcyc(148);
-      cudaMemcpy(hcyc.data(), d_out, 148 * 8, cudaMemcpyDeviceToHost);
-      double cyc = 0;
-      for (auto v : hcyc) cyc += (double)v;
-      cyc /= 148.0;
       const double box_bytes = (double)rows * 130 * planes * 16;
-      printf("C=%2d  box %2d rows x 130 px x %d planes (%5.1f KB): %7.0f cycles per box, %5.1f B/clk/SM\n", c, rows, planes,
-             box_bytes / 1024.0, cyc / iters, box_bytes * iters / cyc);
+      if (box_bytes > 48 * 1024) continue;  // the probe's ring slots are 48 KB
+      for (int mode = 0; mode < 3; ++mode) {  // 0: TMA only, 1: cp.async only, 2: both at once
+        cudaMemset(d_out, 0, 1024 * 8);
+        tma_gather<<<148, 384, 200 * 1024>>>(map, rows, planes, iters, h, w, d_out, (const uint4*)gsrc, mode >= 1, mode != 1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+          printf("C=%d rows=%d: %s\n", c, rows, cudaGetErrorString(e));
+          return 1;
+        }
+        std::vector<unsigned long long> hcyc(512);
+        cudaMemcpy(hcyc.data(), d_out, 512 * 8, cudaMemcpyDeviceToHost);
+        double cyc = 0, cyc2 = 0;
+        for (int i = 0; i < 148; ++i) { cyc += (double)hcyc[i]; cyc2 += (double)hcyc[256 + i]; }
+        cyc /= 148.0; cyc2 /= 148.0;
+        const double cp_bytes = (double)((int)(rows * 130 * planes / 256) + 1) * 256 * 16;
+        printf("C=%2d  box %2d rows x %d planes (%5.1f KB)  %-13s: TMA %5.1f B/clk/SM   cp.async %5.1f B/clk/SM\n", c, rows, planes,
+               box_bytes / 1024.0, mode == 0 ? "TMA only" : (mode == 1 ? "cp.async only" : "both"),
+               cyc > 0 ? box_bytes * iters / cyc : 0.0, cyc2 > 0 ? cp_bytes * iters / cyc2 : 0.0);
+      }
     }
     cudaFree(src);
   }
