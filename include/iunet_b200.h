@@ -67,7 +67,7 @@ int iu_engine_synchronize(iu_engine* e);
  * tensors named with smp's state_dict keys WITHOUT the Lightning `model.` prefix
  * (e.g. "encoder.layer1.0.conv1.weight", "decoder.blocks.0.conv1.1.running_var",
  * "segmentation_head.0.bias"; `num_batches_tracked` entries may be omitted).  The engine folds every
- * eval-mode BatchNorm into the preceding conv, converts to bf16 and packs for the tensor cores.
+ * eval-mode BatchNorm into the preceding conv, converts to the 16-bit storage format and packs for the tensor cores.
  * Replaces `UNet.load_from_checkpoint(...).to(device).eval()` (predict.py:22-27,130-135). */
 int iu_engine_load_weights(iu_engine* e, int num_classes, int n_tensors, const char* const* names,
                            const float* const* data, const int64_t* numel);
@@ -146,10 +146,11 @@ int iu_engine_finalise(iu_engine* e, const float* pred_dev, const float* weight_
                        uint8_t* out_u8_dev, uint8_t* out_labels_dev, unsigned flags);
 
 /* Test hook: one tensor-core convolution exactly as the engine runs it.
- *   src0/src1: device bf16 NHWC [batch][h_in][w_in][cin]; src1 may be NULL (cin1 = 0);
+ *   src0/src1: device 16-bit (engine precision) NHWC [batch][h_in][w_in][cin]; src1 may be NULL (cin1 = 0);
  *   weight: host fp32 [cout][cin0+cin1][k][k] (PyTorch layout, source 0's channels first),
- *   bias: host fp32 [cout]; residual: device bf16 NHWC at output geometry or NULL;
- *   out: device bf16 NHWC [batch][h_out*(1+up2x)][w_out*(1+up2x)][cout]. */
+ *   bias: host fp32 [cout]; residual: device 16-bit NHWC at output geometry or NULL;
+ *   out: device 16-bit NHWC [batch][h_out*(1+up2x)][w_out*(1+up2x)][cout];
+ *   up2x bit 1: src0 is stored at half resolution and read through a 2x nearest upsample (decoder conv1). */
 int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* src1, int cin1, int batch, int h_in,
                         int w_in, int ksize, int stride, const float* weight, const float* bias, int cout,
                         const void* residual, int relu, int up2x, void* out);

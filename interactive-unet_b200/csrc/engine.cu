@@ -746,11 +746,15 @@ int auto_batch(const iu_engine* e, int h, int w, int want) {
   return (want + nbatches - 1) / nbatches;
 }
 
-// Kernel choice per conv.  The halo-tile kernel fetches every activation once per channel chunk instead of once
-// per tap and keeps small weight matrices resident; the per-tap TMA kernel covers strided / 1x1 segments.
-// Measured on B200 (profiles/): the per-tap kernel is L2->SM bandwidth bound on every layer (24-32 KB of operands
-// per four MMAs); the halo kernel is ahead wherever the weights are resident or the source is upsampled.
-// IU_CONV_VARIANT: 0 = automatic, 1 = per-tap kernel wherever it can run, 2 = halo kernel wherever it applies.
+// Kernel choice per conv (measurements in profiles/r01_findings.md):
+//   * row-folded kernel (conv_row.cu): stride-1 3x3 layers with Cout <= 64 on images at least 128 wide -- three
+//     vertical taps per MMA; weights resident, or streamed with the A chunks when they exceed shared memory;
+//   * halo kernel (conv_halo.cu): the other layers that read an upsampled source (decoder blocks 0-1 conv1) and the
+//     narrow layers on small images -- every activation fetched once per channel chunk instead of once per tap;
+//   * per-tap TMA kernel (conv_tc.cu): Cout >= 128 layers, strided / 1x1 segments; L2-bandwidth bound, so Cout >= 256
+//     layers use 256-wide weight tiles (one A box per 32 KB of weights).
+// IU_CONV_VARIANT: 0 = automatic, 1 = per-tap kernel wherever it can run, 2 = halo kernel wherever it applies;
+// IU_CONV_ROW=0 / IU_CONV_BN256=0 / IU_CONV_PAIR=1 switch the row-folded kernel, the wide tiles, the CTA-pair kernel.
 cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
   bool has_up = false;
   for (int s = 0; s < a.nseg; ++s) has_up |= a.seg[s].up != 0;
