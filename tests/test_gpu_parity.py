@@ -405,6 +405,9 @@ def test_extract_block_matches_reference_padding(dev, iu, golden_dir):
     for s, org in ((32, (-5, -3, 12)), (32, (10, 0, -20)), (16, (30, 20, 35)), (64, (-13, -17, -11)), (8, (0, 0, 0))):
         want = iu.predict.get_padded_block(big, *org, *(o + s for o in org))
         assert np.array_equal(eng.extract_block(big_d, org, s).cpu().numpy(), want)
+    tiny = rng.integers(0, 256, (5, 6, 7), dtype=np.uint8)        # pads several times the volume: repeated reflection
+    want = iu.predict.get_padded_block(tiny, -5, -5, -4, 11, 11, 12)
+    assert np.array_equal(eng.extract_block(torch.from_numpy(tiny).to(dev), (-5, -5, -4), 16).cpu().numpy(), want)
 
 
 @pytest.mark.parametrize("name", ["volume_tiled_s16_c3", "volume_tiled_s32_c2"])
