@@ -26,33 +26,50 @@ namespace iu {
 constexpr int kSmemBudget = 100 * 1024;   // per CTA, so that two CTAs fit in the 227 KB of an SM
 constexpr int kSmemBudgetWide = 200 * 1024;  // BN = 256: one CTA per SM (its two accumulators fill TMEM)
 
-template <int KC, int BN>
+// BM: M tiles (of 128 pixels) per CTA tile.  BM = 2 fetches ONE weight box for two pixel tiles: with BN = 128 that is
+// 48 KB of operands per eight MMA-equivalents (instead of 64), with BN = 256 it is 64 KB per sixteen (instead of 96).
+template <int KC, int BN, int BM = 1>
 struct ConvCfg {
   static constexpr int SW = KC * 2;  // bytes per operand row == TMA/UMMA swizzle span
   static constexpr int A_BYTES = kTileM * KC * 2;
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int B_ALLOC = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int TAP_BYTES = A_BYTES + B_ALLOC;
+  static constexpr int TAP_BYTES = BM * A_BYTES + B_ALLOC;
   static constexpr int TPS = KC <= 32 ? 3 : 1;  // taps per pipeline stage (3x3 layers only)
   static constexpr int STAGE_BYTES = TPS * TAP_BYTES;
   // BN = 256 (Cout >= 256 layers): one A box serves a 256-wide weight tile, i.e. 48 KB of operands per eight
   // MMA-equivalents instead of 64 KB with two BN = 128 tiles -- the kernel is L2-bandwidth bound (~17 TB/s measured)
-  static constexpr int CTAS_PER_SM = BN == 256 ? 1 : 2;
-  static constexpr int STAGES_RAW = (BN == 256 ? kSmemBudgetWide : kSmemBudget) / STAGE_BYTES;
+  static constexpr int CTAS_PER_SM = (BN == 256 || BM == 2) ? 1 : 2;
+  static constexpr int STAGES_RAW = (CTAS_PER_SM == 1 ? kSmemBudgetWide : kSmemBudget) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;  // TMEM columns per accumulator
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;      // double-buffered: 64 / 128 / 256 columns
+  static constexpr int TILE_COLS = BN < 32 ? 32 : BN;   // TMEM columns of one M tile's accumulator
+  static constexpr int ACC_COLS = BM * TILE_COLS;       // ... of one CTA tile
+  static constexpr int NBUF = 2 * ACC_COLS <= 512 ? 2 : 1;  // double-buffered unless one CTA tile fills TMEM (BN 256, BM 2)
+  static constexpr int TMEM_COLS = NBUF * ACC_COLS;
+  static_assert(BM == 1 || (BM == 2 && KC == 64), "two-M-tile CTA tiles are instantiated for 64-channel chunks only");
   static constexpr int BAR_BYTES = (2 * STAGES + 4 + 1) * 8;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
   static constexpr int CHUNK = BN >= 32 ? 32 : 16;                            // accumulator columns per tcgen05.ld
 };
 
+// CTA tile `tile` -> Cout tile and its first M tile; M tile m -> pixel coordinates.  With BM == 2 a CTA tile is the
+// pair of M tiles (2p, 2p + 1); an odd tail pairs with a tile beyond the batch, whose TMA boxes are zero-filled and
+// whose epilogue rows are masked (n >= batch).
+__device__ __forceinline__ TileCoord mtile_coord(const ConvArgs& a, int m, int ntile) {
+  TileCoord t;
+  t.ntile = ntile;
+  t.x0 = (m % a.tiles_x) * a.tw;
+  t.y0 = ((m / a.tiles_x) % a.tiles_y) * a.th;
+  t.n0 = (m / (a.tiles_x * a.tiles_y)) * a.nb;
+  return t;
+}
+
 // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5 / 6-9: epilogue groups 0 / 1
 constexpr int kThreads = 320;
 
-template <int KC, int BN>
-__global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
-  using Cfg = ConvCfg<KC, BN>;
+template <int KC, int BN, int BM>
+__global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
+  using Cfg = ConvCfg<KC, BN, BM>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -77,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_t
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full_bar(b), 1);
-      mbar_init(acc_empty_bar(b), 4);  // one arrival per warp of the epilogue group that drained it
+      mbar_init(acc_empty_bar(b), BM == 2 ? 8 : 4);  // one arrival per epilogue warp that drains this buffer
     }
     fence_mbar_init();
   }
@@ -95,7 +112,9 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_t
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(a, tile);
+        const int ntile = tile % a.ntiles_n, m0 = (tile / a.ntiles_n) * BM;
+        const TileCoord tc = mtile_coord(a, m0, ntile);
+        const TileCoord tc1 = mtile_coord(a, m0 + BM - 1, ntile);  // second M tile (BM == 2)
         int kbase = 0;
         for (int s = 0; s < a.nseg; ++s) {
           const ConvSegment sg = a.seg[s];
@@ -107,14 +126,17 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_t
                 const int st = it % Cfg::STAGES;
                 const uint32_t ph = (it / Cfg::STAGES) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1u);
-                mbar_arrive_expect_tx(full_bar(st), tps * (Cfg::A_BYTES + Cfg::B_BYTES));
+                mbar_arrive_expect_tx(full_bar(st), tps * (BM * Cfg::A_BYTES + Cfg::B_BYTES));
                 for (int j = 0; j < tps; ++j) {
                   const int q = q0 + j;
                   const uint32_t sa = base + st * Cfg::STAGE_BYTES + j * Cfg::TAP_BYTES;
                   tma_load_4d(sa, &a.amap[s], full_bar(st), cc * KC, tc.x0 * sg.stride - sg.pad + q,
                               tc.y0 * sg.stride - sg.pad + r, tc.n0);
-                  tma_load_2d(sa + Cfg::A_BYTES, BN == 256 ? &a.bmap256 : &a.bmap, full_bar(st), kbase + (r * sg.ksize + q) * sg.cin + cc * KC,
-                              tc.ntile * BN);
+                  if constexpr (BM == 2)
+                    tma_load_4d(sa + Cfg::A_BYTES, &a.amap[s], full_bar(st), cc * KC, tc1.x0 * sg.stride - sg.pad + q,
+                                tc1.y0 * sg.stride - sg.pad + r, tc1.n0);
+                  tma_load_2d(sa + BM * Cfg::A_BYTES, BN == 256 ? &a.bmap256 : &a.bmap, full_bar(st),
+                              kbase + (r * sg.ksize + q) * sg.cin + cc * KC, tc.ntile * BN);
                 }
               }
             }
@@ -134,8 +156,9 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_t
       }
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t buf = tcount & 1u;
-        mbar_wait(acc_empty_bar(buf), ((tcount >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        const uint32_t buf = Cfg::NBUF == 2 ? (tcount & 1u) : 0u;
+        const uint32_t use = Cfg::NBUF == 2 ? (tcount >> 1) : tcount;  // how often this buffer has been used before
+        mbar_wait(acc_empty_bar(buf), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * Cfg::ACC_COLS;
         uint32_t first = 1;
@@ -152,11 +175,15 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_t
             for (int j = 0; j < tps; ++j) {
               const uint32_t sa = base + st * Cfg::STAGE_BYTES + j * Cfg::TAP_BYTES;
               const uint64_t adesc = umma_smem_desc<Cfg::SW>(sa);
-              const uint64_t bdesc = umma_smem_desc<Cfg::SW>(sa + Cfg::A_BYTES);
+              const uint64_t bdesc = umma_smem_desc<Cfg::SW>(sa + BM * Cfg::A_BYTES);
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k) {
                 // advancing K by 16 elements = 32 bytes inside the swizzle span = +2 in the (addr >> 4) field
                 umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, first ? 0u : 1u);
+                if constexpr (BM == 2) {
+                  const uint64_t adesc1 = umma_smem_desc<Cfg::SW>(sa + Cfg::A_BYTES);
+                  umma_f16(tmem_d + Cfg::TILE_COLS, adesc1 + 2u * k, bdesc + 2u * k, idesc, first ? 0u : 1u);
+                }
                 first = 0;
               }
             }
@@ -175,9 +202,11 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_t
     const int row = quarter * 32 + lane;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t buf = tcount & 1u;
-      if ((int)buf != group) continue;
-      const TileCoord tc = decode_tile(a, tile);
+      const uint32_t buf = Cfg::NBUF == 2 ? (tcount & 1u) : 0u;
+      const uint32_t use = Cfg::NBUF == 2 ? (tcount >> 1) : tcount;
+      // BM == 1: group g drains the tiles of buffer g; BM == 2: group g drains M tile g of every CTA tile
+      if (BM == 1 && (int)buf != group) continue;
+      const TileCoord tc = mtile_coord(a, (tile / a.ntiles_n) * BM + (BM == 2 ? group : 0), tile % a.ntiles_n);
       const int per_img = a.th * a.tw;
       const int n = tc.n0 + row / per_img;
       const int y = tc.y0 + (row % per_img) / a.tw;
@@ -185,9 +214,10 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_t
       const bool valid = (n < a.batch) && (y < a.out_h) && (x < a.out_w);
       uint4 res[EpiCfg<BN>::RV];
       residual_prefetch<BN>(a, tc.ntile, n, y, x, valid, res);
-      mbar_wait(acc_full_bar(buf), (tcount >> 1) & 1u);
+      mbar_wait(acc_full_bar(buf), use & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + buf * Cfg::ACC_COLS + (BM == 2 ? group * Cfg::TILE_COLS : 0) +
+                             ((uint32_t)(quarter * 32) << 16);
       epilogue_pixel<BN>(a, a.bias, tc.ntile, taddr, n, y, x, valid, res);
       tc_fence_before();
       __syncwarp();
@@ -200,15 +230,15 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN>::CTAS_PER_SM) conv_t
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int KC, int BN>
+template <int KC, int BN, int BM = 1>
 static cudaError_t launch_one(const ConvArgs& args_in, cudaStream_t stream) {
-  using Cfg = ConvCfg<KC, BN>;
+  using Cfg = ConvCfg<KC, BN, BM>;
   static int configured_dev = -1;  // per kernel instantiation; the attribute is per device
   static int num_sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, BN, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -220,17 +250,19 @@ static cudaError_t launch_one(const ConvArgs& args_in, cudaStream_t stream) {
   const int mtiles = args.tiles_x * args.tiles_y * ((args.batch + args.nb - 1) / args.nb);
   const int cout_pad = (args.mode == kEpiBf16) ? args.cout : BN;
   args.ntiles_n = cout_pad / BN;
-  args.total_tiles = mtiles * args.ntiles_n;
+  args.total_tiles = ((mtiles + BM - 1) / BM) * args.ntiles_n;
   const int slots = Cfg::CTAS_PER_SM * num_sms;
   const int grid = args.total_tiles < slots ? args.total_tiles : slots;
-  conv_tc_kernel<KC, BN><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(args);
+  conv_tc_kernel<KC, BN, BM><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(args);
   return cudaGetLastError();
 }
 
 #define IU_CONV_DISPATCH(KC_, BN_) \
   if (kc == KC_ && bn == BN_) return launch_one<KC_, BN_>(args, stream);
 
-cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream) {
+cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream, int bm) {
+  if (bm == 2 && kc == 64 && bn == 256) return launch_one<64, 256, 2>(args, stream);
+  if (bm == 2 && kc == 64 && bn == 128) return launch_one<64, 128, 2>(args, stream);
   IU_CONV_DISPATCH(64, 256)
   IU_CONV_DISPATCH(64, 128)
   IU_CONV_DISPATCH(64, 64)

@@ -69,7 +69,8 @@ struct alignas(64) ConvArgs {
 };
 
 // Launch on `stream`; KC = min(64, cin), BN = min(128, Cout_pad).  Returns cudaGetLastError().
-cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream);
+// bm = 2 (64-channel chunks, BN 128 / 256 only): CTA tiles of two M tiles that share every weight box.
+cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream, int bm = 1);
 
 // Shared memory the kernel variant needs (for occupancy planning / tests).
 int conv_tc_smem_bytes(int kc, int bn);
