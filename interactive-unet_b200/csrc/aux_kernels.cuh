@@ -58,4 +58,19 @@ cudaError_t launch_extract_block(const uint8_t* vol, int d, int h, int w, int i0
 cudaError_t launch_finalise(const float* pred, const float* weight, size_t voxels, int num_classes, uint8_t* out_u8,
                             uint8_t* out_labels, cudaStream_t stream);
 
+// ---- Zarr staging: the byte shuffling either side of the store, on the device.
+// A volume is C-order [d][h][w] voxels of `elem` bytes (classes x item size); the store keeps it as inner chunks of
+// cz x cy x cx voxels.  `staged` is chunk-major: chunk (gz, gy, gx) of the ceil(d/cz) x ceil(h/cy) x ceil(w/cx) grid,
+// C order, each chunk a contiguous [cz][cy][cx] block of voxels.  to_chunks zero-fills the padding of edge chunks
+// (the arrays' fill value); from_chunks ignores it.
+cudaError_t launch_chunk_layout(const uint8_t* src, uint8_t* dst, int d, int h, int w, int elem, int cz, int cy, int cx,
+                                bool to_chunks, cudaStream_t stream);
+
+// `scipy.ndimage.zoom(block, scale, order=0)` applied block by block as `utils.resize_volume` does
+// (`utils.py:29-48`), collapsed into one separable gather: dst[z][y][x][c] = src[tz[z]][ty[y]][tx[x]][tc[c]], or 0
+// where any table entry is -1 (scipy's `mode='constant'` fill for a coordinate that rounds past the last sample).
+// Items are `item` bytes (1, 2, 4 or 8); the tables live on the device.
+cudaError_t launch_zoom_gather(const uint8_t* src, const int* sdims, uint8_t* dst, const int* ddims, const int* tz,
+                               const int* ty, const int* tx, const int* tc, int item, cudaStream_t stream);
+
 }  // namespace iu

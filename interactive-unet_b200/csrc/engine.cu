@@ -1414,6 +1414,74 @@ int iu_engine_finalise(iu_engine* e, const float* pred_dev, const float* weight_
   return finish(e, flags);
 }
 
+int iu_engine_to_chunks(iu_engine* e, const void* volume_dev, int d, int h, int w, int elem, int cz, int cy, int cx,
+                        void* staged_dev, unsigned flags) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!volume_dev || !staged_dev) return e->fail(IU_ERR_INVALID, "to_chunks: null buffer");
+  cudaError_t ce = launch_chunk_layout((const uint8_t*)volume_dev, (uint8_t*)staged_dev, d, h, w, elem, cz, cy, cx, true,
+                                       e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "launch to_chunks");
+  e->launches += 1;
+  return finish(e, flags);
+}
+
+int iu_engine_from_chunks(iu_engine* e, const void* staged_dev, int d, int h, int w, int elem, int cz, int cy, int cx,
+                          void* volume_dev, unsigned flags) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!volume_dev || !staged_dev) return e->fail(IU_ERR_INVALID, "from_chunks: null buffer");
+  cudaError_t ce = launch_chunk_layout((const uint8_t*)staged_dev, (uint8_t*)volume_dev, d, h, w, elem, cz, cy, cx,
+                                       false, e->stream);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "launch from_chunks");
+  e->launches += 1;
+  return finish(e, flags);
+}
+
+int iu_engine_zoom_nearest(iu_engine* e, const void* src_dev, const int* src_dims, void* dst_dev, const int* dst_dims,
+                           const int* t0, const int* t1, const int* t2, const int* t3, int item_bytes, unsigned flags) {
+  int rc;
+  if (!check_engine(e, false, &rc)) return rc;
+  if (!src_dev || !src_dims || !dst_dims || !t0 || !t1 || !t2 || !t3)
+    return e->fail(IU_ERR_INVALID, "zoom_nearest: null argument");
+  size_t n = 0, total = 1;
+  for (int k = 0; k < 4; ++k) {
+    if (src_dims[k] < 0 || dst_dims[k] < 0) return e->fail(IU_ERR_INVALID, "zoom_nearest: negative extent");
+    n += (size_t)dst_dims[k];
+    total *= (size_t)dst_dims[k];
+  }
+  if (total == 0) return IU_OK;  // an empty level (the reference halves the class axis too: C = 1 -> 0)
+  if (!dst_dev) return e->fail(IU_ERR_INVALID, "zoom_nearest: null destination");
+  if (item_bytes != 1 && item_bytes != 2 && item_bytes != 4 && item_bytes != 8)
+    return e->fail(IU_ERR_INVALID, "zoom_nearest: item size must be 1, 2, 4 or 8 bytes");
+  const int* tabs[4] = {t0, t1, t2, t3};
+  std::vector<int> host(n);
+  size_t off = 0;
+  for (int k = 0; k < 4; ++k) {
+    for (int i = 0; i < dst_dims[k]; ++i) {
+      const int v = tabs[k][i];
+      if (v < -1 || v >= src_dims[k]) return e->fail(IU_ERR_INVALID, "zoom_nearest: table entry outside the source");
+      host[off + i] = v;
+    }
+    off += (size_t)dst_dims[k];
+  }
+  int* tab_dev = nullptr;
+  if ((rc = scratch_get(e, n * sizeof(int), (void**)&tab_dev)) != IU_OK) return rc;
+  cudaError_t ce = cudaMemcpyAsync(tab_dev, host.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream);
+  const int* dz = tab_dev;
+  const int* dy = dz + dst_dims[0];
+  const int* dx = dy + dst_dims[1];
+  const int* dc = dx + dst_dims[2];
+  if (ce == cudaSuccess)
+    ce = launch_zoom_gather((const uint8_t*)src_dev, src_dims, (uint8_t*)dst_dev, dst_dims, dz, dy, dx, dc, item_bytes,
+                            e->stream);
+  e->launches += 1;
+  cudaStreamSynchronize(e->stream);  // the tables (pageable host copy, pooled device copy) are released here
+  scratch_put(e, tab_dev);
+  if (ce != cudaSuccess) return e->cuda_fail(ce, "launch zoom_nearest");
+  return finish(e, flags);
+}
+
 int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* src1, int cin1, int batch, int h_in,
                         int w_in, int ksize, int stride, const float* weight, const float* bias, int cout,
                         const void* residual, int relu, int up2x, void* out) {

@@ -277,6 +277,69 @@ class Engine:
                 self._h, ptrs[0], ptrs[1], ptrs[2], c_order, len(order), int(size), int(self.num_classes), gp, float(gmax),
                 float(lo), _ptr(pred)[0], _ptr(weight)[0], d, h, w, c_org, 0))
 
+    # ------------------------------------------------------------------ Zarr staging
+    @staticmethod
+    def _voxel_layout(shape, chunks, itemsize):
+        """(d, h, w, bytes per voxel, cz, cy, cx) for an array chunked over its first three axes only."""
+        shape, chunks = tuple(int(v) for v in shape), tuple(int(v) for v in chunks)
+        if len(shape) < 3 or len(chunks) != len(shape) or shape[3:] != chunks[3:]:
+            raise ValueError(f"chunk layout {chunks} of an array of shape {shape}: only the first three axes may be "
+                             f"chunked (the reference chunks (128,128,128,C), predict.py:177)")
+        elem = int(np.prod(shape[3:], dtype=np.int64)) * int(itemsize)
+        return shape[:3] + (elem,) + chunks[:3]
+
+    def to_chunks(self, volume, chunks, out=None):
+        """CUDA array `[D,H,W,...]` -> chunk-major CUDA staging `[n_chunks, *chunks]` (edge padding zeroed), the
+        layout `zarr3.Array.write_chunk_major` compresses from."""
+        d, h, w, elem, cz, cy, cx = self._voxel_layout(volume.shape, chunks, volume.element_size())
+        n = -(-d // cz) * -(-h // cy) * -(-w // cx)
+        if out is None:
+            out = torch.empty((n,) + tuple(int(v) for v in chunks), dtype=volume.dtype, device=volume.device)
+        if out.numel() != n * int(np.prod(chunks, dtype=np.int64)) or out.dtype != volume.dtype:
+            raise ValueError("to_chunks: staging tensor has the wrong size / dtype")
+        with self._lock:
+            self._sync_torch(volume, out)
+            self._check(self._lib.iu_engine_to_chunks(self._h, _ptr(volume)[0], d, h, w, elem, cz, cy, cx, _ptr(out)[0], 0))
+        return out
+
+    def from_chunks(self, staged, shape, chunks, out=None):
+        """Chunk-major CUDA staging (as `zarr3.Array.read_chunk_major` decodes it) -> CUDA array of `shape`."""
+        d, h, w, elem, cz, cy, cx = self._voxel_layout(shape, chunks, staged.element_size())
+        n = -(-d // cz) * -(-h // cy) * -(-w // cx)
+        if staged.numel() != n * int(np.prod(chunks, dtype=np.int64)):
+            raise ValueError("from_chunks: staging tensor has the wrong size")
+        if out is None:
+            out = torch.empty(tuple(int(v) for v in shape), dtype=staged.dtype, device=staged.device)
+        with self._lock:
+            self._sync_torch(staged, out)
+            self._check(self._lib.iu_engine_from_chunks(self._h, _ptr(staged)[0], d, h, w, elem, cz, cy, cx, _ptr(out)[0], 0))
+        return out
+
+    def zoom_nearest(self, src, tables, out=None):
+        """One pyramid level on the device: `out[i,j,k(,l)] = src[t0[i], t1[j], t2[k](, t3[l])]`, 0 where a table holds
+        -1.  `tables` come from `utils.zoom_tables` (the reference's block-wise `ndimage.zoom(order=0)`)."""
+        if src.dim() not in (3, 4) or len(tables) != src.dim():
+            raise ValueError("zoom_nearest: 3-D or 4-D arrays with one table per axis")
+        tabs = [np.ascontiguousarray(t, dtype=np.int32) for t in tables]
+        dshape = tuple(int(t.size) for t in tabs)
+        if out is None:
+            out = torch.empty(dshape, dtype=src.dtype, device=src.device)
+        if tuple(out.shape) != dshape or out.dtype != src.dtype:
+            raise ValueError("zoom_nearest: destination has the wrong shape / dtype")
+        if out.numel() == 0:
+            return out          # an empty level (the reference halves the class axis too: C = 1 -> 0)
+        sd = [int(v) for v in src.shape] + [1] * (4 - src.dim())
+        dd = list(dshape) + [1] * (4 - src.dim())
+        if src.dim() == 3:
+            tabs.append(np.zeros(1, np.int32))
+        ip = ctypes.POINTER(ctypes.c_int)
+        with self._lock:
+            self._sync_torch(src, out)
+            self._check(self._lib.iu_engine_zoom_nearest(
+                self._h, _ptr(src)[0], (ctypes.c_int * 4)(*sd), _ptr(out)[0],
+                (ctypes.c_int * 4)(*dd), *[t.ctypes.data_as(ip) for t in tabs], int(src.element_size()), 0))
+        return out
+
     def finalise(self, pred, weight, out_u8=None, out_labels=None):
         """`normalize_shard` (predict.py:252-255) over CUDA fp32 `pred` / `weight` -> CUDA uint8 (and argmax labels)."""
         with self._lock:

@@ -220,26 +220,47 @@ def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=
 
 def predict_volumes(input_size=256, num_channels=1, num_classes=2, overlap=0.25, chunk_size=128, shard_size=256,
                     batch_size=None, axes=[0, 1, 2]):
-    """`predict.py:114-266`: predict every `data/image_volumes/*.zarr` into `data/predicted_volumes/`."""
-    try:
-        import zarr
-    except ImportError as e:
-        raise RuntimeError("predict_volumes reads and writes Zarr stores; the `zarr` package is not installed. "
-                           "Use predict_volume_array for in-memory volumes.") from e
+    """`predict.py:114-266`: predict every `data/image_volumes/*.zarr` (level '0', uint8) into
+    `data/predicted_volumes/<same name>` -- level '0' uint8 `[D,H,W,C]` with chunks `(chunk_size,)*3 + (C,)` and shards
+    `(shard_size,)*3 + (C,)`, then the multiscale pyramid (`utils.add_multiscales`, `predict.py:261`).
+
+    Data flow: host threads decompress the store's inner chunks into pinned memory -> one H2D copy -> the device puts
+    them in `[D,H,W]` order -> prediction (single block, or tiled + blended) entirely on the device -> the device
+    re-orders the uint8 result into inner chunks and zooms each pyramid level -> one D2H copy per level -> host threads
+    compress and write one shard file each.  The reference's float32 `temp/pred.zarr` / `temp/weight.zarr` accumulators
+    (`predict.py:181-198`) live in HBM instead, so no `temp/` directory is created (or removed, `predict.py:259`)."""
+    import signal
+    from . import utils, zarr3
+
+    if threading.current_thread() is threading.main_thread():
+        def handle_sigint(sig, frame):                       # predict.py:118-122
+            print("\nCaught Ctrl+C \u2192 force exit")
+            os._exit(1)
+        signal.signal(signal.SIGINT, handle_sigint)
+
     device = _require_cuda()
     model = _load_model(num_channels, num_classes, device)
     volume_files = np.sort(glob.glob('data/image_volumes/*.zarr'))
     for f in volume_files:
         start_time = time.time()
-        volume = np.asarray(zarr.open(f, mode='r')['0'][:])
+        volume = zarr3.open(f, mode='r')['0']                # highest resolution (predict.py:167)
+        if volume.dtype != np.uint8 or volume.ndim != 3:
+            raise TypeError(f"{f}: level '0' must be a 3-D uint8 array (predict.py:237 divides by 255), "
+                            f"got {volume.dtype} {volume.shape}")
         save_path = f.replace('image_volumes', 'predicted_volumes')
-        root = zarr.open(save_path, mode='w')
-        final = root.create_array(name='0', shape=list(volume.shape) + [num_classes],
-                                  chunks=(chunk_size, chunk_size, chunk_size, num_classes),
-                                  shards=(shard_size, shard_size, shard_size, num_classes), dtype='uint8',
-                                  overwrite=True)
+        root = zarr3.open(save_path, mode='w')
+        final_predictions = root.create_array(name='0', shape=list(volume.shape) + [num_classes],
+                                              chunks=(chunk_size, chunk_size, chunk_size, num_classes),
+                                              shards=(shard_size, shard_size, shard_size, num_classes), dtype='uint8',
+                                              overwrite=True)
         print(f'\nSegmenting {os.path.basename(f)}...')
-        final[:] = predict_volume_array(model, volume, input_size=input_size, num_classes=num_classes,
-                                        overlap=overlap, batch_size=batch_size, axes=axes)
+        volume_dev = utils.read_array_to_device(volume, device)
+        out_dev = predict_volume_array(model, volume_dev, input_size=input_size, num_classes=num_classes,
+                                       overlap=overlap, batch_size=batch_size, axes=axes)
+        del volume_dev
+        print('Postprocessing and generating multiscale pyramid...')
+        utils.write_array_from_device(final_predictions, out_dev)
+        utils.add_multiscales(save_path, scale=0.5, level0=out_dev)
+        del out_dev
         print(f'Completed volume {os.path.basename(f)} {tuple(volume.shape)} in {time.time() - start_time}.')
     print('\nAll volumes segmented.\n')

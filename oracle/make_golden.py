@@ -110,9 +110,9 @@ def run_reference_predict_volumes(volume_u8, model, input_size, num_classes, ove
                                   axes=(0, 1, 2), chunk_size=16, shard_size=32):
     """Drive the verbatim `predict_volumes` on one in-memory volume; returns the level-0 uint8 result.
 
-    `utils.add_multiscales` (`predict.py:261`, the pyramid post-step, SURVEY.md row f2: out of scope) is
-    switched off: it runs after level 0 is complete and cannot change it, and it raises on some 4-D
-    shapes (it zooms the class axis too)."""
+    `utils.add_multiscales` (`predict.py:261`, the pyramid post-step) is switched off here: it runs after
+    level 0 is complete and cannot change it, and it raises on some 4-D shapes (it zooms the class axis
+    too).  It is recorded on its own by `make_multiscales`."""
     ref = reference_loader.load()
     utils_mod = sys.modules["interactive_unet.utils"]
     unet_mod = sys.modules["interactive_unet.unet"]
@@ -138,6 +138,63 @@ def run_reference_predict_volumes(volume_u8, model, input_size, num_classes, ove
         ref.zarr, utils_mod.zarr, unet_mod.UNet, utils_mod.add_multiscales = saved
         os.chdir(cwd)
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_reference_add_multiscales(volume, chunks, shards, scale=0.5):
+    """Drive the verbatim `utils.add_multiscales` (`utils.py:50-80`) on one in-memory store; returns the levels it
+    created as {name: ndarray}, and the exception it ended with (None, or (type name, message))."""
+    reference_loader.load()
+    utils_mod = sys.modules["interactive_unet.utils"]
+    fake = _FakeZarr()
+    saved = utils_mod.zarr
+    tmp = tempfile.mkdtemp(prefix="iu_golden_")
+    try:
+        utils_mod.zarr = fake
+        g = fake.open(os.path.join(tmp, "x.zarr"), mode="w")
+        arr = g.create_array("0", volume.shape, chunks, shards, volume.dtype)
+        arr[:] = volume
+        err = None
+        try:
+            utils_mod.add_multiscales(os.path.join(tmp, "x.zarr"), scale=scale)
+        except Exception as e:                      # the reference's own failure modes are part of the record
+            err = (type(e).__name__, str(e))
+        return {k: v.data.copy() for k, v in g.items() if k != "0"}, err
+    finally:
+        utils_mod.zarr = saved
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+MULTISCALE_CASES = [
+    # name, shape, inner chunk edge, shard edge
+    ("c2", (32, 32, 32, 2), 8, 16),             # class axis 2 -> 1 -> 0
+    ("c4", (32, 32, 32, 4), 8, 16),             # class axis 4 -> 2 -> 1 (keeps classes 0 and 3)
+    ("ragged_c2", (48, 20, 36, 2), 4, 8),       # several levels, edge blocks shorter than a shard
+    ("image", (40, 36, 44), 16, 32),            # 3-D image volume (create_multiscale_zarr)
+    ("fill_c2", (64, 32, 32, 2), 16, 32),       # 32 -> 16 blocks: scipy's constant fill on the last plane of a block
+    ("u16", (24, 32, 16), 4, 8),                # 16-bit image volume
+    ("odd", (38, 32, 32), 8, 16),               # ValueError at level 2 (19 -> 9)
+    ("c3", (32, 16, 16, 3), 8, 16),             # ValueError at level 1 (class axis 3: round(1.5) = 2 vs int(1.5) = 1)
+    ("small", (8, 8, 8, 2), 8, 16),             # fits a chunk: UnboundLocalError in the reference (utils.py:77)
+]
+
+
+def make_multiscales():
+    """6. utils.add_multiscales / resize_volume (utils.py:29-80): the pyramid, incl. the zoomed class axis."""
+    rng = np.random.default_rng(20261019)
+    rec = {}
+    for name, shape, chunk, shard in MULTISCALE_CASES:
+        dtype = np.uint16 if name == "u16" else np.uint8
+        vol = rng.integers(1, np.iinfo(dtype).max, shape, dtype=dtype)     # no zeros: scipy's fill voxels stand out
+        tail = shape[3:]
+        levels, err = run_reference_add_multiscales(vol, (chunk,) * 3 + tail, (shard,) * 3 + tail)
+        rec[f"{name}_volume"] = vol
+        rec[f"{name}_grid"] = np.array([chunk, shard])
+        rec[f"{name}_levels"] = np.array(sorted(int(k) for k in levels))
+        for k, v in levels.items():
+            rec[f"{name}_level{k}"] = v
+        rec[f"{name}_error"] = np.array(list(err) if err else ["", ""])
+        print(name, shape, {k: v.shape for k, v in levels.items()}, err)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "multiscales.npz"), **rec)
 
 
 def main():
@@ -189,6 +246,8 @@ def main():
         out = run_reference_predict_volumes(vol, ExactToyModel(classes), size, classes, axes=axes)
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), volume=vol, input_size=size,
                             num_classes=classes, axes=np.array(axes), out_u8=out)
+
+    make_multiscales()
 
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
         print(f"{os.path.getsize(f):8d}  {os.path.relpath(f)}")

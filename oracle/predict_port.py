@@ -144,3 +144,32 @@ def slice_overlay(probs_1hwc, num_classes, palette):
     for i in range(num_classes):
         out[lab == i] = palette[i + 1]
     return out
+
+
+def resize_volume(src, dst, scale=0.5, block_size=512, order=0):
+    """`utils.py:29-48`: block-wise `scipy.ndimage.zoom` of `src` assigned into `dst` (numpy arrays; `dst` modified in
+    place).  scipy is a pinned dependency of the reference (`pyproject.toml:20`) and supplies the zoom here too; the
+    product derives the equivalent index tables itself (`utils.zoom_tables`)."""
+    from scipy import ndimage
+    n = src.shape
+    for i in range(0, n[0], block_size):
+        i0, i1 = i, min(i + block_size, n[0])
+        for j in range(0, n[1], block_size):
+            j0, j1 = j, min(j + block_size, n[1])
+            for k in range(0, n[2], block_size):
+                k0, k1 = k, min(k + block_size, n[2])
+                dst[int(i0 * scale):int(i1 * scale), int(j0 * scale):int(j1 * scale), int(k0 * scale):int(k1 * scale)] = \
+                    ndimage.zoom(src[i0:i1, j0:j1, k0:k1], scale, order=order)
+
+
+def multiscale_levels(level0, chunk_shape, shard_shape, scale=0.5):
+    """`utils.py:50-80` on in-memory arrays: the list of levels 1, 2, ... that `add_multiscales` creates from `level0`
+    (raises where the reference raises, except its `UnboundLocalError` for zero steps: an empty list here)."""
+    steps = int(np.floor(np.log((np.array(level0.shape) / np.array(chunk_shape)).max()) / np.log(1 / scale)))
+    levels, cur = [], level0
+    for _ in range(steps):
+        nxt = np.zeros(tuple(int(x * scale) for x in cur.shape), cur.dtype)     # a fresh zarr array reads as fill 0
+        resize_volume(cur, nxt, scale=scale, block_size=shard_shape[0], order=0)
+        levels.append(nxt)
+        cur = nxt
+    return levels

@@ -454,6 +454,119 @@ def test_tiled_prediction_matches_reference_algorithm(dev, fitted, iu):
     assert np.array_equal(got_d.cpu().numpy(), got)
 
 
+# --------------------------------------------------------------------------- Zarr staging + pyramid
+@pytest.mark.parametrize("shape,chunks,dtype", [
+    ((40, 36, 44), (16, 16, 16), torch.uint8),              # byte path (row segments not 16-byte aligned)
+    ((40, 36, 48, 2), (16, 16, 16, 2), torch.uint8),        # 16-byte vector path, ragged in z and y
+    ((128, 64, 256, 2), (128, 128, 128, 2), torch.uint8),   # the reference's chunk shape, chunk larger than the array in y
+    ((20, 24, 40, 3), (8, 8, 8, 3), torch.float32),         # 12-byte voxels (the reference's fp32 `pred` store layout)
+    ((7, 5, 3), (4, 4, 4), torch.uint8),
+])
+def test_chunk_layout_round_trip(dev, iu, shape, chunks, dtype):
+    """`iu_engine_to_chunks` / `iu_engine_from_chunks` vs numpy slicing, bit-exact, padding zeroed."""
+    from interactive_unet_b200 import utils
+    eng = utils._engine(dev)
+    rng = np.random.default_rng(5)
+    data = torch.from_numpy(rng.integers(1, 255, shape).astype(np.uint8)).to(dtype)
+    grid = [-(-n // c) for n, c in zip(shape[:3], chunks[:3])]
+    want = torch.zeros((int(np.prod(grid)),) + tuple(chunks), dtype=dtype)
+    for n, (gz, gy, gx) in enumerate(np.ndindex(*grid)):
+        piece = data[gz * chunks[0]:(gz + 1) * chunks[0], gy * chunks[1]:(gy + 1) * chunks[1],
+                     gx * chunks[2]:(gx + 1) * chunks[2]]
+        want[n, :piece.shape[0], :piece.shape[1], :piece.shape[2]] = piece
+    staged = torch.full(want.shape, 77, dtype=dtype, device=dev)          # stale contents must be overwritten
+    eng.to_chunks(data.to(dev), chunks, out=staged)
+    assert torch.equal(staged.cpu(), want)
+    back = eng.from_chunks(staged, shape, chunks)
+    assert torch.equal(back.cpu(), data)
+    if len(shape) == 4:
+        with pytest.raises(ValueError):
+            eng.to_chunks(data.to(dev), (4, 4, 4, 1))                     # the class axis must not be chunked
+
+
+@pytest.mark.parametrize("name", ["c2", "c4", "ragged_c2", "image", "fill_c2", "u16", "odd", "c3", "small"])
+def test_pyramid_matches_reference_add_multiscales_golden(dev, iu, golden_dir, tmp_path, name):
+    """`utils.create_multiscale_zarr` / `add_multiscales` through real stores: every level the verbatim reference
+    made (recorded in multiscales.npz), bit-exact, and its ValueError where it raises."""
+    from interactive_unet_b200 import utils, zarr3
+    z = np.load(os.path.join(golden_dir, "multiscales.npz"))
+    vol, (chunk, shard) = z[f"{name}_volume"], [int(v) for v in z[f"{name}_grid"]]
+    levels = {int(k): z[f"{name}_level{k}"] for k in z[f"{name}_levels"]}
+    etype, emsg = (str(v) for v in z[f"{name}_error"])
+    store = str(tmp_path / "p.zarr")
+    if vol.ndim == 3:                                   # image volumes: create_multiscale_zarr (utils.py:82-98)
+        call = lambda: utils.create_multiscale_zarr(vol, store, scale=0.5, chunk_size=chunk, shard_size=shard)
+    else:                                               # predictions: level 0 written first, then add_multiscales
+        tail = vol.shape[3:]
+        root = zarr3.open(store, mode="w")
+        z0 = root.create_array(name="0", shape=vol.shape, chunks=(chunk,) * 3 + tail, shards=(shard,) * 3 + tail,
+                               dtype=vol.dtype, overwrite=True)
+        z0[:] = vol                                     # through the host slicing path, as a zarr user would
+        call = lambda: utils.add_multiscales(store, scale=0.5)
+    if etype == "ValueError":
+        with pytest.raises(ValueError) as ei:
+            call()
+        assert str(ei.value) == emsg
+    else:
+        call()
+    root = zarr3.open(store, mode="r")
+    assert np.array_equal(root["0"][...], vol)
+    assert sorted(int(k) for k in root.array_keys()) == [0] + sorted(levels)
+    for k, want in levels.items():
+        got = root[str(k)]
+        assert got.shape == want.shape and got.dtype == want.dtype
+        assert got.chunks == root["0"].chunks and got.shards == root["0"].shards
+        if etype != "ValueError" or k < max(levels):    # the level the reference failed in is created but incomplete
+            assert np.array_equal(got[...], want), f"level {k}"
+    assert utils.read_volume(store, level=0).shape == vol.shape
+
+
+def test_zoom_nearest_large_matches_oracle_port(dev, iu):
+    """One pyramid level at the reference's real block size (shard 256) against the scipy-based port."""
+    from interactive_unet_b200 import utils
+    from oracle import predict_port as pp
+    rng = np.random.default_rng(9)
+    src = rng.integers(1, 255, (384, 256, 320, 2), dtype=np.uint8)
+    want = np.zeros((192, 128, 160, 1), np.uint8)
+    pp.resize_volume(src, want, 0.5, 256, 0)
+    got = utils.resize_volume(torch.from_numpy(src).to(dev), torch.empty(want.shape, dtype=torch.uint8, device=dev),
+                              0.5, 256, 0)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_predict_volumes_drop_in_through_zarr_stores(dev, fitted, iu, tmp_path, monkeypatch):
+    """`predict_volumes` (predict.py:114-266) end to end on disk: image stores in, prediction stores + pyramid out.
+    Level 0 must equal `predict_volume_array` on the same voxels bit for bit; the pyramid must equal the port of
+    `add_multiscales` applied to level 0."""
+    from interactive_unet_b200 import utils, zarr3
+    from oracle import predict_port as pp
+    from oracle import synth
+    ref, model = fitted[2]
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("model")
+    torch.save({"state_dict": ref.state_dict(),
+                "hyper_parameters": dict(lr=1e-4, num_channels=1, num_classes=2, architecture="U-Net",
+                                         encoder_name="resnet34", pretrained=False)}, "model/model.ckpt")
+    vols = {"cube": synth.blob_volume(64, 3)[0], "slab": synth.blob_volume(96, 4)[0][:80, :96, :72].copy()}
+    for name, v in vols.items():
+        utils.create_multiscale_zarr(v, f"data/image_volumes/{name}.zarr", chunk_size=16, shard_size=32)
+    os.makedirs("data/predicted_volumes")
+    iu.predict.predict_volumes(input_size=64, num_classes=2, chunk_size=16, shard_size=32, batch_size=16)
+    assert not os.path.exists("temp")
+    for name, v in vols.items():
+        assert np.array_equal(zarr3.open(f"data/image_volumes/{name}.zarr")["0"][...], v)
+        root = zarr3.open(f"data/predicted_volumes/{name}.zarr", mode="r")
+        lvl0 = root["0"]
+        assert lvl0.shape == v.shape + (2,) and lvl0.chunks == (16, 16, 16, 2) and lvl0.shards == (32, 32, 32, 2)
+        want = iu.predict.predict_volume_array(model, v, input_size=64, num_classes=2, batch_size=16)
+        got = lvl0[...]
+        assert np.array_equal(got, want)
+        pyramid = pp.multiscale_levels(got, lvl0.chunks, lvl0.shards)
+        assert sorted(int(k) for k in root.array_keys()) == list(range(len(pyramid) + 1)) and len(pyramid) >= 2
+        for k, lv in enumerate(pyramid):
+            assert np.array_equal(root[str(k + 1)][...], lv)
+
+
 # --------------------------------------------------------------------------- sharded path on one GPU
 def test_z_slab_partition_is_bit_identical(dev, fitted, iu):
     """The G-way z-slab partition executed rank by rank on ONE GPU, with the
