@@ -148,7 +148,9 @@ int iu_engine_finalise(iu_engine* e, const float* pred_dev, const float* weight_
 /* Zarr staging, the steps either side of the path (device buffers).
  *   A volume is C-order [d][h][w] voxels of `elem` bytes (classes x item size).  `staged` is the same data as the
  *   store's inner chunks (predict.py:174-179: chunks (128,128,128,C)), chunk-major: chunk (gz,gy,gx) of the
- *   ceil(d/cz) x ceil(h/cy) x ceil(w/cx) grid in C order, each a contiguous [cz][cy][cx] block of voxels.
+ *   ceil(d/cz) x ceil(h/cy) x ceil(w/cx) grid in C order, each a contiguous [cz][cy][cx] block of voxels of
+ *   `chunk_elem` >= `elem` bytes (pyramid levels keep level 0's chunk shape while their class axis is halved,
+ *   utils.py:66-71, so a chunk's class extent can exceed the array's; the excess is padding).
  *   to_chunks:   volume -> staged, edge-chunk padding zero-filled (the arrays' fill value) -- what
  *                `final_predictions[i0:i1, j0:j1, k0:k1] = ...` (predict.py:255) makes zarr do on the host;
  *   from_chunks: staged -> volume, padding ignored -- `zarr.open(f)['0'][...]` (predict.py:167, :299).
@@ -156,10 +158,10 @@ int iu_engine_finalise(iu_engine* e, const float* pred_dev, const float* weight_
  *                per shard-sized block) as one gather dst[i][j][k][l] = src[t0[i]][t1[j]][t2[k]][t3[l]] over 4-D
  *                arrays of `item_bytes`-byte items; tables are HOST int32 arrays of dst_dims[k] entries, -1 = scipy's
  *                constant fill (0).  3-D arrays pass a trailing extent of 1. */
-int iu_engine_to_chunks(iu_engine* e, const void* volume_dev, int d, int h, int w, int elem, int cz, int cy, int cx,
-                        void* staged_dev, unsigned flags);
-int iu_engine_from_chunks(iu_engine* e, const void* staged_dev, int d, int h, int w, int elem, int cz, int cy, int cx,
-                          void* volume_dev, unsigned flags);
+int iu_engine_to_chunks(iu_engine* e, const void* volume_dev, int d, int h, int w, int elem, int chunk_elem, int cz,
+                        int cy, int cx, void* staged_dev, unsigned flags);
+int iu_engine_from_chunks(iu_engine* e, const void* staged_dev, int d, int h, int w, int elem, int chunk_elem, int cz,
+                          int cy, int cx, void* volume_dev, unsigned flags);
 int iu_engine_zoom_nearest(iu_engine* e, const void* src_dev, const int* src_dims, void* dst_dev, const int* dst_dims,
                            const int* t0, const int* t1, const int* t2, const int* t3, int item_bytes, unsigned flags);
 

@@ -57,9 +57,9 @@ SIGNATURES = {
     "iu_engine_finalise": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p,
                                       _c.c_void_p, _c.c_uint]),
     "iu_engine_to_chunks": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
-                                       _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint]),
+                                       _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint]),
     "iu_engine_from_chunks": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
-                                         _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint]),
+                                         _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint]),
     "iu_engine_zoom_nearest": (_c.c_int, [_engine_p, _c.c_void_p, _c.POINTER(_c.c_int), _c.c_void_p,
                                           _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _c.POINTER(_c.c_int),
                                           _c.POINTER(_c.c_int), _c.POINTER(_c.c_int), _c.c_int, _c.c_uint]),

@@ -311,81 +311,124 @@ cudaError_t launch_reduce(const ReduceArgs& args, cudaStream_t stream) {
 }
 
 // =========================================================================== Zarr staging: chunk layout, pyramid
+// `elem` = bytes per voxel in the volume, `celem` >= elem = bytes per voxel in a chunk (a chunk's class extent may
+// exceed the array's: pyramid levels keep level 0's chunk shape while their class axis is halved, utils.py:66-71).
 template <typename V>
 __global__ void __launch_bounds__(256) chunk_layout_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                           int d, int h, int w, int elem, int cz, int cy, int cx, int gy,
-                                                           int gx, size_t total, bool to_chunks) {
+                                                           int d, int h, int w, int elem, int celem, int cz, int cy,
+                                                           int cx, int gy, int gx, size_t total, bool to_chunks) {
   constexpr int VEC = (int)sizeof(V);
-  const int row_units = cx * elem / VEC;
-  const size_t row_bytes = (size_t)w * elem;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int u = (int)(i % row_units);
-    size_t r = i / row_units;
-    const int y = (int)(r % cy);
-    r /= cy;
-    const int z = (int)(r % cz);
-    const size_t chunk = r / cz;
-    const int gxi = (int)(chunk % gx), gyi = (int)((chunk / gx) % gy), gzi = (int)(chunk / ((size_t)gx * gy));
-    const int Z = gzi * cz + z, Y = gyi * cy + y;
-    const size_t xbyte = (size_t)gxi * cx * elem + (size_t)u * VEC;
-    const bool inside = Z < d && Y < h && xbyte < row_bytes;
-    const size_t vol_off = ((size_t)Z * h + Y) * row_bytes + xbyte;
-    if (to_chunks) {
-      V v = V();
-      if (inside) v = *reinterpret_cast<const V*>(src + vol_off);
-      *reinterpret_cast<V*>(dst + i * VEC) = v;
-    } else if (inside) {
-      *reinterpret_cast<V*>(dst + vol_off) = *reinterpret_cast<const V*>(src + i * VEC);
+  constexpr int UNROLL = 4;  // independent loads in flight per thread before the first store
+  const int row_units = cx * celem / VEC;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * UNROLL) {
+    size_t vol_off[UNROLL];
+    bool inside[UNROLL];
+    V v[UNROLL];
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) {
+      const size_t i = i0 + k * stride;
+      const int u = (int)(i % row_units);
+      size_t r = i / row_units;
+      const int y = (int)(r % cy);
+      r /= cy;
+      const int z = (int)(r % cz);
+      const size_t chunk = r / cz;
+      const int gxi = (int)(chunk % gx), gyi = (int)((chunk / gx) % gy), gzi = (int)(chunk / ((size_t)gx * gy));
+      const int Z = gzi * cz + z, Y = gyi * cy + y;
+      // vector path: celem == elem, so a row of a chunk is a contiguous piece of a volume row
+      const int xb = u * VEC;                                    // byte inside the chunk row
+      const int X = gxi * cx + (VEC == 1 ? xb / celem : 0);      // byte path: voxel and byte inside the voxel
+      const int b = VEC == 1 ? xb % celem : xb;
+      const size_t xbyte = (size_t)X * elem + b;
+      inside[k] = i < total && Z < d && Y < h && (VEC == 1 ? (X < w && b < elem) : xbyte < (size_t)w * elem);
+      vol_off[k] = ((size_t)Z * h + Y) * w * elem + xbyte;
+      v[k] = V();
+      if (to_chunks) {
+        if (inside[k]) v[k] = *reinterpret_cast<const V*>(src + vol_off[k]);
+      } else if (inside[k]) {
+        v[k] = *reinterpret_cast<const V*>(src + i * VEC);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) {
+      const size_t i = i0 + k * stride;
+      if (to_chunks) {
+        if (i < total) *reinterpret_cast<V*>(dst + i * VEC) = v[k];
+      } else if (inside[k]) {
+        *reinterpret_cast<V*>(dst + vol_off[k]) = v[k];
+      }
     }
   }
 }
 
-cudaError_t launch_chunk_layout(const uint8_t* src, uint8_t* dst, int d, int h, int w, int elem, int cz, int cy, int cx,
-                                bool to_chunks, cudaStream_t stream) {
-  if (d < 1 || h < 1 || w < 1 || elem < 1 || cz < 1 || cy < 1 || cx < 1) return cudaErrorInvalidValue;
+cudaError_t launch_chunk_layout(const uint8_t* src, uint8_t* dst, int d, int h, int w, int elem, int celem, int cz, int cy,
+                                int cx, bool to_chunks, cudaStream_t stream) {
+  if (d < 1 || h < 1 || w < 1 || elem < 1 || celem < elem || cz < 1 || cy < 1 || cx < 1) return cudaErrorInvalidValue;
   const int gz = (d + cz - 1) / cz, gy = (h + cy - 1) / cy, gx = (w + cx - 1) / cx;
-  const size_t staged_bytes = (size_t)gz * gy * gx * cz * cy * cx * elem;
+  const size_t staged_bytes = (size_t)gz * gy * gx * cz * cy * cx * celem;
   // 16-byte accesses when every row segment starts and ends on a 16-byte boundary in both layouts
-  const bool vec = ((size_t)cx * elem) % 16 == 0 && ((size_t)w * elem) % 16 == 0 &&
+  const bool vec = celem == elem && ((size_t)cx * elem) % 16 == 0 && ((size_t)w * elem) % 16 == 0 &&
                    reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0;
   const size_t total = vec ? staged_bytes / 16 : staged_bytes;
   const size_t want = (total + 255) / 256;
-  const int blocks = (int)(want < (size_t)148 * 16 ? want : (size_t)148 * 16);
+  const int blocks = (int)(want < (size_t)148 * 8 ? want : (size_t)148 * 8);
   if (vec)
-    chunk_layout_kernel<uint4><<<blocks, 256, 0, stream>>>(src, dst, d, h, w, elem, cz, cy, cx, gy, gx, total, to_chunks);
+    chunk_layout_kernel<uint4><<<blocks, 256, 0, stream>>>(src, dst, d, h, w, elem, celem, cz, cy, cx, gy, gx, total,
+                                                           to_chunks);
   else
-    chunk_layout_kernel<uint8_t><<<blocks, 256, 0, stream>>>(src, dst, d, h, w, elem, cz, cy, cx, gy, gx, total, to_chunks);
+    chunk_layout_kernel<uint8_t><<<blocks, 256, 0, stream>>>(src, dst, d, h, w, elem, celem, cz, cy, cx, gy, gx, total,
+                                                             to_chunks);
   return cudaGetLastError();
 }
 
-template <typename T>
+// PER consecutive items of one output row (x, class) per thread, stored as one aligned pack.
+template <typename T, int PER>
+struct alignas(sizeof(T) * PER <= 16 ? sizeof(T) * PER : 16) ZoomPack {
+  T v[PER];
+};
+
+template <typename T, int PER>
 __global__ void __launch_bounds__(256) zoom_gather_kernel(const T* __restrict__ src, int sh, int sw, int sc,
                                                           T* __restrict__ dst, int dh, int dw, int dc, size_t total,
                                                           const int* __restrict__ tz, const int* __restrict__ ty,
                                                           const int* __restrict__ tx, const int* __restrict__ tc) {
+  const int row = dw * dc / PER;  // packs per output row (the launcher picks PER so that it divides dw * dc)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % dc);
-    size_t r = i / dc;
-    const int x = (int)(r % dw);
-    r /= dw;
+    const int e0 = (int)(i % row) * PER;
+    size_t r = i / row;
     const int y = (int)(r % dh);
     const int z = (int)(r / dh);
-    const int iz = __ldg(tz + z), iy = __ldg(ty + y), ix = __ldg(tx + x), ic = __ldg(tc + c);
-    T v = T();
-    if ((iz | iy | ix | ic) >= 0) v = src[(((size_t)iz * sh + iy) * sw + ix) * sc + ic];
-    dst[i] = v;
+    const int iz = __ldg(tz + z), iy = __ldg(ty + y);
+    const T* line = src + ((size_t)(iz < 0 ? 0 : iz) * sh + (iy < 0 ? 0 : iy)) * sw * sc;
+    ZoomPack<T, PER> p;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int e = e0 + k;
+      const int ix = __ldg(tx + e / dc), ic = __ldg(tc + e % dc);
+      p.v[k] = (iz | iy | ix | ic) >= 0 ? line[(size_t)ix * sc + ic] : T();
+    }
+    *reinterpret_cast<ZoomPack<T, PER>*>(dst + i * PER) = p;
   }
 }
 
 template <typename T>
 static cudaError_t zoom_launch(const uint8_t* src, const int* sd, uint8_t* dst, const int* dd, const int* tz,
                                const int* ty, const int* tx, const int* tc, cudaStream_t stream) {
-  const size_t total = (size_t)dd[0] * dd[1] * dd[2] * dd[3];
-  if (total == 0) return cudaSuccess;
+  const size_t items = (size_t)dd[0] * dd[1] * dd[2] * dd[3];
+  if (items == 0) return cudaSuccess;
+  const bool packed = ((size_t)dd[2] * dd[3]) % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0;
+  const size_t total = packed ? items / 4 : items;
   const size_t want = (total + 255) / 256;
   const int blocks = (int)(want < (size_t)148 * 16 ? want : (size_t)148 * 16);
-  zoom_gather_kernel<T><<<blocks, 256, 0, stream>>>(reinterpret_cast<const T*>(src), sd[1], sd[2], sd[3],
-                                                    reinterpret_cast<T*>(dst), dd[1], dd[2], dd[3], total, tz, ty, tx, tc);
+  if (packed)
+    zoom_gather_kernel<T, 4><<<blocks, 256, 0, stream>>>(reinterpret_cast<const T*>(src), sd[1], sd[2], sd[3],
+                                                         reinterpret_cast<T*>(dst), dd[1], dd[2], dd[3], total, tz, ty, tx,
+                                                         tc);
+  else
+    zoom_gather_kernel<T, 1><<<blocks, 256, 0, stream>>>(reinterpret_cast<const T*>(src), sd[1], sd[2], sd[3],
+                                                         reinterpret_cast<T*>(dst), dd[1], dd[2], dd[3], total, tz, ty, tx,
+                                                         tc);
   return cudaGetLastError();
 }
 

@@ -63,8 +63,9 @@ cudaError_t launch_finalise(const float* pred, const float* weight, size_t voxel
 // cz x cy x cx voxels.  `staged` is chunk-major: chunk (gz, gy, gx) of the ceil(d/cz) x ceil(h/cy) x ceil(w/cx) grid,
 // C order, each chunk a contiguous [cz][cy][cx] block of voxels.  to_chunks zero-fills the padding of edge chunks
 // (the arrays' fill value); from_chunks ignores it.
-cudaError_t launch_chunk_layout(const uint8_t* src, uint8_t* dst, int d, int h, int w, int elem, int cz, int cy, int cx,
-                                bool to_chunks, cudaStream_t stream);
+// `celem` >= `elem`: bytes per voxel inside a chunk when the chunk's class extent exceeds the array's (padding zeroed).
+cudaError_t launch_chunk_layout(const uint8_t* src, uint8_t* dst, int d, int h, int w, int elem, int celem, int cz, int cy,
+                                int cx, bool to_chunks, cudaStream_t stream);
 
 // `scipy.ndimage.zoom(block, scale, order=0)` applied block by block as `utils.resize_volume` does
 // (`utils.py:29-48`), collapsed into one separable gather: dst[z][y][x][c] = src[tz[z]][ty[y]][tx[x]][tc[c]], or 0

@@ -1414,25 +1414,25 @@ int iu_engine_finalise(iu_engine* e, const float* pred_dev, const float* weight_
   return finish(e, flags);
 }
 
-int iu_engine_to_chunks(iu_engine* e, const void* volume_dev, int d, int h, int w, int elem, int cz, int cy, int cx,
-                        void* staged_dev, unsigned flags) {
+int iu_engine_to_chunks(iu_engine* e, const void* volume_dev, int d, int h, int w, int elem, int chunk_elem, int cz,
+                        int cy, int cx, void* staged_dev, unsigned flags) {
   int rc;
   if (!check_engine(e, false, &rc)) return rc;
   if (!volume_dev || !staged_dev) return e->fail(IU_ERR_INVALID, "to_chunks: null buffer");
-  cudaError_t ce = launch_chunk_layout((const uint8_t*)volume_dev, (uint8_t*)staged_dev, d, h, w, elem, cz, cy, cx, true,
+  cudaError_t ce = launch_chunk_layout((const uint8_t*)volume_dev, (uint8_t*)staged_dev, d, h, w, elem, chunk_elem, cz, cy, cx, true,
                                        e->stream);
   if (ce != cudaSuccess) return e->cuda_fail(ce, "launch to_chunks");
   e->launches += 1;
   return finish(e, flags);
 }
 
-int iu_engine_from_chunks(iu_engine* e, const void* staged_dev, int d, int h, int w, int elem, int cz, int cy, int cx,
-                          void* volume_dev, unsigned flags) {
+int iu_engine_from_chunks(iu_engine* e, const void* staged_dev, int d, int h, int w, int elem, int chunk_elem, int cz,
+                          int cy, int cx, void* volume_dev, unsigned flags) {
   int rc;
   if (!check_engine(e, false, &rc)) return rc;
   if (!volume_dev || !staged_dev) return e->fail(IU_ERR_INVALID, "from_chunks: null buffer");
-  cudaError_t ce = launch_chunk_layout((const uint8_t*)staged_dev, (uint8_t*)volume_dev, d, h, w, elem, cz, cy, cx,
-                                       false, e->stream);
+  cudaError_t ce = launch_chunk_layout((const uint8_t*)staged_dev, (uint8_t*)volume_dev, d, h, w, elem, chunk_elem, cz,
+                                       cy, cx, false, e->stream);
   if (ce != cudaSuccess) return e->cuda_fail(ce, "launch from_chunks");
   e->launches += 1;
   return finish(e, flags);

@@ -280,18 +280,22 @@ class Engine:
     # ------------------------------------------------------------------ Zarr staging
     @staticmethod
     def _voxel_layout(shape, chunks, itemsize):
-        """(d, h, w, bytes per voxel, cz, cy, cx) for an array chunked over its first three axes only."""
+        """(d, h, w, bytes per voxel, bytes per voxel inside a chunk, cz, cy, cx) for an array chunked over its first
+        three axes only; one trailing (class) axis may be shorter than the chunk's (padding)."""
         shape, chunks = tuple(int(v) for v in shape), tuple(int(v) for v in chunks)
-        if len(shape) < 3 or len(chunks) != len(shape) or shape[3:] != chunks[3:]:
+        ok = len(shape) >= 3 and len(chunks) == len(shape) and \
+            (shape[3:] == chunks[3:] or (len(shape) == 4 and 0 < shape[3] <= chunks[3]))
+        if not ok:
             raise ValueError(f"chunk layout {chunks} of an array of shape {shape}: only the first three axes may be "
                              f"chunked (the reference chunks (128,128,128,C), predict.py:177)")
         elem = int(np.prod(shape[3:], dtype=np.int64)) * int(itemsize)
-        return shape[:3] + (elem,) + chunks[:3]
+        celem = int(np.prod(chunks[3:], dtype=np.int64)) * int(itemsize)
+        return shape[:3] + (elem, celem) + chunks[:3]
 
     def to_chunks(self, volume, chunks, out=None):
         """CUDA array `[D,H,W,...]` -> chunk-major CUDA staging `[n_chunks, *chunks]` (edge padding zeroed), the
         layout `zarr3.Array.write_chunk_major` compresses from."""
-        d, h, w, elem, cz, cy, cx = self._voxel_layout(volume.shape, chunks, volume.element_size())
+        d, h, w, elem, celem, cz, cy, cx = self._voxel_layout(volume.shape, chunks, volume.element_size())
         n = -(-d // cz) * -(-h // cy) * -(-w // cx)
         if out is None:
             out = torch.empty((n,) + tuple(int(v) for v in chunks), dtype=volume.dtype, device=volume.device)
@@ -299,12 +303,13 @@ class Engine:
             raise ValueError("to_chunks: staging tensor has the wrong size / dtype")
         with self._lock:
             self._sync_torch(volume, out)
-            self._check(self._lib.iu_engine_to_chunks(self._h, _ptr(volume)[0], d, h, w, elem, cz, cy, cx, _ptr(out)[0], 0))
+            self._check(self._lib.iu_engine_to_chunks(self._h, _ptr(volume)[0], d, h, w, elem, celem, cz, cy, cx,
+                                                      _ptr(out)[0], 0))
         return out
 
     def from_chunks(self, staged, shape, chunks, out=None):
         """Chunk-major CUDA staging (as `zarr3.Array.read_chunk_major` decodes it) -> CUDA array of `shape`."""
-        d, h, w, elem, cz, cy, cx = self._voxel_layout(shape, chunks, staged.element_size())
+        d, h, w, elem, celem, cz, cy, cx = self._voxel_layout(shape, chunks, staged.element_size())
         n = -(-d // cz) * -(-h // cy) * -(-w // cx)
         if staged.numel() != n * int(np.prod(chunks, dtype=np.int64)):
             raise ValueError("from_chunks: staging tensor has the wrong size")
@@ -312,7 +317,8 @@ class Engine:
             out = torch.empty(tuple(int(v) for v in shape), dtype=staged.dtype, device=staged.device)
         with self._lock:
             self._sync_torch(staged, out)
-            self._check(self._lib.iu_engine_from_chunks(self._h, _ptr(staged)[0], d, h, w, elem, cz, cy, cx, _ptr(out)[0], 0))
+            self._check(self._lib.iu_engine_from_chunks(self._h, _ptr(staged)[0], d, h, w, elem, celem, cz, cy, cx,
+                                                        _ptr(out)[0], 0))
         return out
 
     def zoom_nearest(self, src, tables, out=None):

@@ -259,8 +259,11 @@ def predict_volumes(input_size=256, num_channels=1, num_classes=2, overlap=0.25,
                                        overlap=overlap, batch_size=batch_size, axes=axes)
         del volume_dev
         print('Postprocessing and generating multiscale pyramid...')
-        utils.write_array_from_device(final_predictions, out_dev)
-        utils.add_multiscales(save_path, scale=0.5, level0=out_dev)
+        level0 = utils.write_array_from_device(final_predictions, out_dev, wait=False)
+        try:
+            utils.add_multiscales(save_path, scale=0.5, level0=out_dev)      # zoomed while level 0 is being compressed
+        finally:
+            level0.result()
         del out_dev
         print(f'Completed volume {os.path.basename(f)} {tuple(volume.shape)} in {time.time() - start_time}.')
     print('\nAll volumes segmented.\n')

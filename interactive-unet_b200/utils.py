@@ -17,6 +17,7 @@ Shapes where numpy cannot assign the zoomed block (`round(n*scale) != int(i1*sca
 extents, C = 3) raise the same `ValueError` as the reference.
 """
 import os
+import threading
 
 import numpy as np
 import torch
@@ -110,7 +111,55 @@ def zoom_tables(src_shape, dst_shape, scale=0.5, block_size=512):
 
 # ------------------------------------------------------------------------------------------------- device <-> store
 def _chunked_on_three_axes(arr):
-    return arr.ndim >= 3 and tuple(arr.chunks[3:]) == tuple(arr.shape[3:])
+    """The bulk path's precondition: one chunk spans the trailing (class) extent -- exactly, or with padding when a
+    pyramid level inherits level 0's chunk shape (`utils.py:66-71`) while its class axis was halved."""
+    if arr.ndim < 3 or arr.chunk_grid[3:] != (1,) * (arr.ndim - 3):
+        return False
+    return tuple(arr.chunks[3:]) == tuple(arr.shape[3:]) or arr.ndim == 4
+
+
+class _PinnedPool:
+    """Page-locked staging buffers, kept between calls: `cudaHostAlloc` of a few hundred MiB costs more than the copy
+    it serves (measured 0.1 s for 256 MiB), and `predict_volumes` needs the same sizes for every volume."""
+
+    def __init__(self):
+        self._free = []
+        self._lock = threading.Lock()
+
+    def acquire(self, shape, dtype):
+        nbytes = int(np.prod(shape, dtype=np.int64)) * torch.empty(0, dtype=dtype).element_size()
+        with self._lock:
+            fits = [k for k, b in enumerate(self._free) if b.numel() >= nbytes]
+            buf = self._free.pop(min(fits, key=lambda k: self._free[k].numel())) if fits else None
+        if buf is None:
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        return buf, buf[:nbytes].view(dtype).view(*shape)
+
+    def release(self, buf):
+        with self._lock:
+            self._free.append(buf)
+            self._free.sort(key=lambda b: b.numel())
+            while sum(b.numel() for b in self._free) > (8 << 30):        # keep at most 8 GiB parked
+                self._free.pop(0)
+
+
+_pinned = _PinnedPool()
+
+
+class PendingWrite:
+    """A store write whose compression / file tasks are still running in the pool (`wait=False`)."""
+
+    def __init__(self, futures, buf):
+        self._futures, self._buf = futures, buf
+
+    def result(self):
+        try:
+            for f in self._futures:
+                f.result()
+        finally:
+            if self._buf is not None:
+                _pinned.release(self._buf)
+                self._buf = None
 
 
 def read_array_to_device(arr, device=None):
@@ -120,34 +169,44 @@ def read_array_to_device(arr, device=None):
     eng = _engine(device)
     if not isinstance(arr, zarr3.Array):
         return torch.as_tensor(np.ascontiguousarray(arr)).to(eng.device)
+    tdtype = torch.from_numpy(np.empty(0, arr.dtype)).dtype
     if arr.size == 0:
-        return torch.empty(arr.shape, dtype=torch.from_numpy(np.empty(0, arr.dtype)).dtype, device=eng.device)
+        return torch.empty(arr.shape, dtype=tdtype, device=eng.device)
     if not _chunked_on_three_axes(arr):
         return torch.from_numpy(arr[...]).to(eng.device)
-    staged = torch.empty(arr.chunk_major_shape(), dtype=torch.from_numpy(np.empty(0, arr.dtype)).dtype, pin_memory=True)
-    arr.read_chunk_major(out=staged.numpy())
-    return eng.from_chunks(staged.to(eng.device, non_blocking=True), arr.shape, arr.chunks)
+    buf, staged = _pinned.acquire(arr.chunk_major_shape(), tdtype)
+    try:
+        arr.read_chunk_major(out=staged.numpy())
+        staged_dev = staged.to(eng.device, non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+    finally:
+        _pinned.release(buf)
+    return eng.from_chunks(staged_dev, arr.shape, arr.chunks)
 
 
-def write_array_from_device(arr, data):
+def write_array_from_device(arr, data, wait=True):
     """CUDA tensor of `arr.shape` -> the whole `zarr3.Array`: `iu_engine_to_chunks` on the device, one D2H copy into
-    pinned memory, host threads compress and write one shard file each."""
+    pinned memory, host threads compress the inner chunks and write one shard file each.  `wait=False` returns a
+    `PendingWrite` as soon as the data has left the device; call its `result()` before relying on the files."""
     if tuple(data.shape) != tuple(arr.shape):
         raise ValueError(f"could not broadcast input array from shape {tuple(data.shape)} into shape {tuple(arr.shape)}")
     if arr.size == 0:
-        return
+        return PendingWrite([], None)
     if not _chunked_on_three_axes(arr):
         arr[...] = data.cpu().numpy()
-        return
+        return PendingWrite([], None)
     eng = _engine(data.device)
     staged_dev = eng.to_chunks(data.contiguous(), arr.chunks)
-    staged = torch.empty(staged_dev.shape, dtype=staged_dev.dtype, pin_memory=True)
+    buf, staged = _pinned.acquire(staged_dev.shape, staged_dev.dtype)
     staged.copy_(staged_dev)
     del staged_dev
-    arr.write_chunk_major(staged.numpy())
+    pending = PendingWrite(arr.write_chunk_major(staged.numpy(), wait=False), buf)
+    if wait:
+        pending.result()
+    return pending
 
 
-def resize_volume(src_vol, dst_vol, scale=0.5, block_size=512, order=0):
+def resize_volume(src_vol, dst_vol, scale=0.5, block_size=512, order=0, _pending=None):
     """`utils.py:29-48` for `order=0` (the reference's only use, `utils.py:74`): `dst_vol` <- block-wise nearest zoom of
     `src_vol`.  `src_vol` may be a `zarr3.Array`, a numpy array or a CUDA tensor; `dst_vol` a `zarr3.Array` or a CUDA
     tensor of the target shape.  Returns the zoomed level as a CUDA tensor (so a pyramid never re-reads the store)."""
@@ -158,7 +217,9 @@ def resize_volume(src_vol, dst_vol, scale=0.5, block_size=512, order=0):
     eng = _engine(src.device)
     out = eng.zoom_nearest(src.contiguous(), tables, out=dst_vol if isinstance(dst_vol, torch.Tensor) else None)
     if isinstance(dst_vol, zarr3.Array):
-        write_array_from_device(dst_vol, out)
+        pending = write_array_from_device(dst_vol, out, wait=_pending is None)
+        if _pending is not None:
+            _pending.append(pending)
     elif not isinstance(dst_vol, torch.Tensor):
         dst_vol[...] = out.cpu().numpy()
     return out
@@ -183,12 +244,18 @@ def add_multiscales(src_file, scale=0.5, level0=None):
         raise ValueError(f"{src_file}: level '0' is not sharded (the reference creates every level with shards=)")
     num_steps = _num_steps(volume_shape, chunk_shape, scale)
     cur = level0
-    for i in range(num_steps):
-        z0 = root[str(i)]
-        z1_shape = tuple(int(x * scale) for x in z0.shape)
-        z1 = root.create_array(name=str(i + 1), shape=z1_shape, chunks=chunk_shape, shards=shard_shape, dtype=z0.dtype,
-                               overwrite=True)
-        cur = resize_volume(cur if cur is not None else z0, z1, scale=scale, block_size=shard_shape[0], order=0)
+    pending = []              # every level's compression runs in the pool while the next level is zoomed on the device
+    try:
+        for i in range(num_steps):
+            z0 = root[str(i)]
+            z1_shape = tuple(int(x * scale) for x in z0.shape)
+            z1 = root.create_array(name=str(i + 1), shape=z1_shape, chunks=chunk_shape, shards=shard_shape,
+                                   dtype=z0.dtype, overwrite=True)
+            cur = resize_volume(cur if cur is not None else z0, z1, scale=scale, block_size=shard_shape[0], order=0,
+                                _pending=pending)
+    finally:
+        for p in pending:
+            p.result()
 
 
 def create_multiscale_zarr(volume, dst_file, scale=0.5, chunk_size=128, shard_size=256):

@@ -93,7 +93,7 @@ class _Zstd:
         r = self.lib.ZSTD_compress(dst, cap, arr.ctypes.data, n, int(level))
         if self.lib.ZSTD_isError(r):
             raise RuntimeError("zstd: " + self.lib.ZSTD_getErrorName(r).decode())
-        return dst.raw[:r]
+        return ctypes.string_at(dst, r)
 
     def decompress_into(self, src, out: np.ndarray):
         """`src`: bytes-like frame; `out`: C-contiguous array that receives exactly `out.nbytes` bytes."""
@@ -323,14 +323,17 @@ class Array:
     def _encode_shard(self, pieces):
         """`pieces`: inner chunks (C-contiguous arrays, or None for "equals the fill value") in C order of the shard's
         inner grid -> file bytes, or None when every piece is empty (zarr-python then deletes / skips the file)."""
-        n = len(pieces)
+        return self._assemble_shard([None if p is None else self._inner.encode(p) for p in pieces])
+
+    def _assemble_shard(self, encoded):
+        """Encoded inner chunks (bytes, or None for empty) in the shard's C order -> file bytes (or None)."""
+        n = len(encoded)
         index = np.full((n, 2), _EMPTY, np.uint64)
         body = []
         pos = 0 if self._index_at_end else self._index_nbytes()
-        for k, p in enumerate(pieces):
-            if p is None:
+        for k, enc in enumerate(encoded):
+            if enc is None:
                 continue
-            enc = self._inner.encode(p)
             index[k] = (pos, len(enc))
             body.append(enc)
             pos += len(enc)
@@ -463,51 +466,70 @@ class Array:
 
     def read_chunk_major(self, out=None, pool=None):
         """Decode the whole array into chunk-major order: `out[id]` is inner chunk `id` (C order over `chunk_grid`),
-        edge chunks padded with whatever was stored (the fill value).  Only decompression happens on the host; the
-        scatter into `[D,H,W,...]` order is `Engine.from_chunks` on the device."""
+        edge chunks padded with whatever was stored (the fill value).  Only decompression happens on the host -- one
+        pool task per stored file to read it and parse its index, then one per inner chunk to decompress; the scatter
+        into `[D,H,W,...]` order is `Engine.from_chunks` on the device."""
         if out is None:
             out = np.empty(self.chunk_major_shape(), self.dtype)
         if tuple(out.shape) != self.chunk_major_shape() or out.dtype != self.dtype or not out.flags.c_contiguous:
             raise ValueError("read_chunk_major: staging buffer has the wrong shape / dtype / layout")
+        pool = pool or default_pool()
 
-        def one(sc):
+        def open_file(sc):
             ids = self._shard_chunk_ids(sc)
             blob = self._read_file(sc)
             if blob is None:
-                for i in ids:
-                    if i >= 0:
-                        out[i] = self.fill_value
-                return
+                return [(None, None, 0, i) for i in ids if i >= 0]
             if self.shards is None:
-                self._inner.decode_into(blob, out[ids[0]])
-                return
+                return [(blob, None, 0, ids[0])]
             index, view = self._split_shard(blob)
-            for k, i in enumerate(ids):
-                if i >= 0:
-                    self._decode_inner(view, index, k, out[i])
+            return [(view, index, k, i) for k, i in enumerate(ids) if i >= 0]
 
-        list((pool or default_pool()).map(one, list(np.ndindex(*self.shard_grid))))
+        def decode(job):
+            view, index, k, i = job
+            if view is None:
+                out[i] = self.fill_value
+            elif index is None:
+                self._inner.decode_into(view, out[i])
+            else:
+                self._decode_inner(view, index, k, out[i])
+
+        jobs = [j for js in pool.map(open_file, list(np.ndindex(*self.shard_grid))) for j in js]
+        list(pool.map(decode, jobs))
         return out
 
-    def write_chunk_major(self, staged, pool=None):
+    def write_chunk_major(self, staged, pool=None, wait=True):
         """Inverse of `read_chunk_major`: `staged[id]` holds inner chunk `id` with its edge padding already set to the
-        fill value (`Engine.to_chunks` writes zeros there).  One task per stored file: test for all-fill, compress,
-        index, write."""
+        fill value (`Engine.to_chunks` writes zeros there).  One pool task per inner chunk (test for all-fill,
+        compress), then one per stored file (index, checksum, write).  With `wait=False` the list of futures of the
+        file tasks is returned instead of being waited for; `staged` must stay untouched until they are done."""
         if not self.writable:
             raise PermissionError(f"{self.path} was opened read-only")
         if tuple(staged.shape) != self.chunk_major_shape() or staged.dtype != self.dtype:
             raise ValueError("write_chunk_major: staging buffer has the wrong shape / dtype")
+        pool = pool or default_pool()
 
-        def one(sc):
+        def encode(i):
+            p = staged[i]
+            return None if self._is_fill(p) else self._inner.encode(p)
+
+        encoded = [pool.submit(encode, i) for i in range(staged.shape[0])]
+
+        def store(sc):
             ids = self._shard_chunk_ids(sc)
+            pieces = [None if i < 0 else encoded[i].result() for i in ids]
             if self.shards is None:
-                p = staged[ids[0]]
-                self._store_file(sc, None if self._is_fill(p) else self._inner.encode(p))
-                return
-            pieces = [None if i < 0 or self._is_fill(staged[i]) else staged[i] for i in ids]
-            self._store_file(sc, self._encode_shard(pieces))
+                self._store_file(sc, pieces[0])
+            else:
+                self._store_file(sc, self._assemble_shard(pieces))
 
-        list((pool or default_pool()).map(one, list(np.ndindex(*self.shard_grid))))
+        # file tasks wait on chunk tasks submitted before them, so a FIFO pool cannot deadlock
+        files = [pool.submit(store, sc) for sc in np.ndindex(*self.shard_grid)]
+        if not wait:
+            return files
+        for f in files:
+            f.result()
+        return None
 
 
 # ------------------------------------------------------------------------------------------------- groups
