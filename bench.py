@@ -39,8 +39,12 @@ AXES = (0, 1, 2)
 NCU_CONV_DRAM_BYTES_PER_LAUNCH = 228.1e6
 
 
-def flops_per_voxel(classes, n_axes=3):
-    per_axis = FLOP_PER_VOXEL_AXIS.get(classes, 235.62e3 + (classes - 2) * 0.285e3)
+ENCODER = "resnet34"                                       # --encoder
+ENCODER_FLOP_DELTA = {"resnet34": 0.0, "resnet18": -73.728e3}    # resnet18 has 8 fewer BasicBlocks (first step)
+
+
+def flops_per_voxel(classes, n_axes=3, encoder="resnet34"):
+    per_axis = FLOP_PER_VOXEL_AXIS.get(classes, 235.62e3 + (classes - 2) * 0.285e3) + ENCODER_FLOP_DELTA[encoder]
     return per_axis * n_axes
 
 
@@ -112,7 +116,7 @@ def cpu_reference_sample(edge, classes, slices_per_axis, threads, repeats=1):
     torch.set_num_threads(threads)
     key = (edge, classes)
     if key not in _CPU_SETUP:                       # weights / volume are set-up, not part of the timed sample
-        _CPU_SETUP[key] = (synth.make_model(classes), synth.noise_volume(edge, 1))
+        _CPU_SETUP[key] = (synth.make_model(classes, encoder_name=ENCODER), synth.noise_volume(edge, 1))
     model, vol = _CPU_SETUP[key]
     best = None
     for _ in range(repeats):
@@ -151,7 +155,7 @@ def run_reference_arm(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"3-axis prediction of a synthetic {edge}^3 uint8 volume, {args.classes} classes",
                    "edge": edge, "classes": args.classes, "axes": list(AXES),
-                   "network": "smp.Unet(resnet34) restated (oracle/), reference predict.py arithmetic (port)"},
+                   "network": f"smp.Unet({ENCODER}) restated (oracle/), reference predict.py arithmetic (port)"},
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -173,8 +177,8 @@ def run_ours(args, rank, world, local_rank):
     if edge % world or edge % 32:
         raise SystemExit(f"edge {edge} must be divisible by 32 and by the number of GPUs {world}")
     t_slab = edge // world
-    ref = synth.make_model(classes)                                   # random-init weights of the named architecture
-    model = iu.UNet(num_classes=classes)
+    ref = synth.make_model(classes, encoder_name=ENCODER)             # random-init weights of the named architecture
+    model = iu.UNet(num_classes=classes, encoder_name=ENCODER)
     model.precision = args.precision
     model.load_state_dict(ref.state_dict())
     model = model.to(dev).eval()
@@ -263,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
     peaks = measured_peaks()
     value = voxels * args.steps / (dev_ms * 1e-3)
     conv_ms, conv_n = prof["conv"]
-    conv_flops = flops_per_voxel(classes) * voxels / world * prof_steps        # this rank's share
+    conv_flops = flops_per_voxel(classes, encoder=ENCODER) * voxels / world * prof_steps        # this rank's share
     conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     gather_ms, gather_n = prof["gather"]
     reduce_ms, reduce_n = prof["reduce"]
@@ -278,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "impl": "ours",
         "config": {"workload": f"3-axis prediction of a synthetic {edge}^3 uint8 volume, {classes} classes, "
                                f"{'1 B200' if world == 1 else f'z-slab sharded across {world} B200'}",
-                   "edge": edge, "classes": classes, "axes": list(AXES), "network": "smp.Unet(resnet34), random init",
+                   "edge": edge, "classes": classes, "axes": list(AXES), "network": f"smp.Unet({ENCODER}), random init",
                    "storage": f"{args.precision} activations/weights, fp32 accumulate (TMEM), fp32 tail",
                    "l2": "inputs_exceed_l2 (per-step working set of several GB >> 126 MB L2; no explicit flush)",
                    "slices_per_gpu_per_axis": t_slab},
@@ -287,7 +291,7 @@ def run_ours(args, rank, world, local_rank):
                 "api": "interactive_unet_b200.predict.predict_volume_array (pinned host buffers)" if world == 1
                        else "interactive_unet_b200.distributed.predict_volume_sharded + pinned host copies"},
         "gpu_launches": int(launches),
-        "algorithmic_tflops": flops_per_voxel(classes) * value / 1e12,
+        "algorithmic_tflops": flops_per_voxel(classes, encoder=ENCODER) * value / 1e12,
         "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM, all conv layers + head)", "bound": "tensor",
                      "achieved": conv_tflops, "peak": peaks["tc_tflops"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["tc_tflops"],
@@ -296,7 +300,7 @@ def run_ours(args, rank, world, local_rank):
                      "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH if (edge == 512 and world == 1) else None,
                      "traffic_source": "profiles/r01_ncu_full_conv_pass_b74.txt (9.81 GB per 43-launch pass)",
                      "peak_source": peaks["source"],
-                     "flops_per_voxel": flops_per_voxel(classes), "launches": int(conv_n),
+                     "flops_per_voxel": flops_per_voxel(classes, encoder=ENCODER), "launches": int(conv_n),
                      "kernel_ms_per_step": conv_ms / prof_steps,
                      "share_of_step": conv_ms / total_prof_ms if total_prof_ms else None},
         "roofline_hbm": {
@@ -319,6 +323,7 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
+    global ENCODER
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -326,10 +331,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--edge", type=int, default=None, help="volume edge (default: 512 at 1 GPU, weak-scaled above)")
     ap.add_argument("--classes", type=int, default=2)
+    ap.add_argument("--encoder", default="resnet34", choices=sorted(ENCODER_FLOP_DELTA),
+                    help="BASELINE.json's configuration is resnet34; resnet18 is the other supported BasicBlock encoder")
     ap.add_argument("--precision", default=os.environ.get("IU_PRECISION", "fp16"), choices=["fp16", "bf16"])
     ap.add_argument("--cpu-slices", type=int, default=32, help="slices per axis in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    ENCODER = args.encoder
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -474,8 +474,16 @@ int build_network(iu_engine* e, const HostTensors& ht, int num_classes) {
   e->t_f1 = new_tensor(e, 64, 2);
   e->t_p1 = new_tensor(e, 64, 4);
 
-  // ---- encoder: torchvision ResNet-34 BasicBlocks [3,4,6,3]
-  const int nblocks[4] = {3, 4, 6, 3};
+  // ---- encoder: torchvision BasicBlock ResNets -- resnet34 [3,4,6,3] (the reference's accelerated configuration)
+  //      and resnet18 [2,2,2,2]; the block counts are read off the tensor names
+  int nblocks[4] = {0, 0, 0, 0};
+  for (int li = 0; li < 4; ++li) {
+    const std::string layer = "encoder.layer" + std::to_string(li + 1) + ".";
+    while (ht.t.count(layer + std::to_string(nblocks[li]) + ".conv1.weight")) ++nblocks[li];
+    if (nblocks[li] < 1) return e->fail(IU_ERR_INVALID, "missing tensor '" + layer + "0.conv1.weight'");
+    if (ht.t.count(layer + "0.conv3.weight"))
+      return e->fail(IU_ERR_INVALID, "bottleneck encoders (resnet50 and up) are not supported: BasicBlock ResNets only");
+  }
   const int chans[4] = {64, 128, 256, 512};
   int cur = e->t_p1, cur_c = 64, cur_hdiv = 4;
   int feat[6] = {-1, e->t_f1, -1, -1, -1, -1};

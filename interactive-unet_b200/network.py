@@ -12,7 +12,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-LAYER_BLOCKS = (3, 4, 6, 3)
+ENCODER_BLOCKS = {"resnet34": (3, 4, 6, 3), "resnet18": (2, 2, 2, 2)}     # torchvision BasicBlock ResNets
+LAYER_BLOCKS = ENCODER_BLOCKS["resnet34"]
 LAYER_CHANNELS = (64, 128, 256, 512)
 DECODER_CHANNELS = (256, 128, 64, 32, 16)
 SKIP_CHANNELS = (256, 128, 64, 64, 0)
@@ -40,12 +41,12 @@ class _BasicBlock(nn.Module):
 
 
 class _Encoder(nn.Module):
-    def __init__(self, in_channels):
+    def __init__(self, in_channels, layer_blocks=LAYER_BLOCKS):
         super().__init__()
         self.conv1 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         cin = 64
-        for i, (nb, c) in enumerate(zip(LAYER_BLOCKS, LAYER_CHANNELS)):
+        for i, (nb, c) in enumerate(zip(layer_blocks, LAYER_CHANNELS)):
             blocks = []
             for b in range(nb):
                 blocks.append(_BasicBlock(cin, c, 2 if (i > 0 and b == 0) else 1))
@@ -74,11 +75,16 @@ class _Decoder(nn.Module):
 
 
 class SmpUnetResnet34(nn.Module):
-    def __init__(self, in_channels=1, classes=2):
+    """`smp.Unet(encoder_name, in_channels=1, classes=C)` for the BasicBlock ResNets (`resnet34`, the default, and
+    `resnet18`: same channel widths and decoder, fewer blocks per stage)."""
+
+    def __init__(self, in_channels=1, classes=2, encoder_name="resnet34"):
         super().__init__()
+        if encoder_name not in ENCODER_BLOCKS:
+            raise NotImplementedError(f"encoder {encoder_name!r}: supported are {sorted(ENCODER_BLOCKS)}")
         if in_channels != 1:
             raise NotImplementedError("the B200 engine implements num_channels=1 (uint8 grey volumes) only")
-        self.encoder = _Encoder(in_channels)
+        self.encoder = _Encoder(in_channels, ENCODER_BLOCKS[encoder_name])
         self.decoder = _Decoder()
         self.segmentation_head = nn.Sequential(_conv(DECODER_CHANNELS[-1], classes, 3, bias=True))
         nn.init.xavier_uniform_(self.segmentation_head[0].weight)

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from .engine import Engine
-from .network import SmpUnetResnet34
+from .network import ENCODER_BLOCKS, SmpUnetResnet34
 
 try:                                    # the reference subclasses LightningModule (unet.py:9)
     import lightning as _L
@@ -81,15 +81,15 @@ class UNet(_Base):
         self.save_hyperparameters()
         self.lr = lr
         self.loss_function = loss_function
-        if architecture != 'U-Net' or encoder_name != 'resnet34':
+        if architecture != 'U-Net' or encoder_name not in ENCODER_BLOCKS:
             raise NotImplementedError(
-                f"interactive_unet_b200 accelerates architecture='U-Net' with encoder_name='resnet34' only "
-                f"(got {architecture!r}, {encoder_name!r}); use the stock interactive_unet.unet.UNet for others")
+                f"interactive_unet_b200 accelerates architecture='U-Net' with encoder_name in {sorted(ENCODER_BLOCKS)} "
+                f"only (got {architecture!r}, {encoder_name!r}); use the stock interactive_unet.unet.UNet for others")
         if pretrained:
             raise NotImplementedError("ImageNet weights cannot be downloaded here; load a checkpoint instead")
         self.num_channels = num_channels
         self.num_classes = num_classes
-        self.model = SmpUnetResnet34(num_channels, num_classes)      # attribute name = checkpoint key prefix
+        self.model = SmpUnetResnet34(num_channels, num_classes, encoder_name)     # attribute name = checkpoint key prefix
         self.softmax = nn.Softmax(dim=1)
         self._engine = None
         self._engine_key = None

@@ -77,11 +77,14 @@ class _Decoder(nn.Module):
 
 
 class RefSmpUnetResnet34(nn.Module):
-    """`smp.Unet('resnet34', encoder_weights=None, in_channels, classes)`."""
+    """`smp.Unet(encoder_name, encoder_weights=None, in_channels, classes)` for `resnet34` (default) or `resnet18`
+    (same feature widths, so the same decoder; smp's `resnet18` encoder is torchvision's class as well)."""
 
-    def __init__(self, in_channels=1, classes=2):
+    def __init__(self, in_channels=1, classes=2, encoder_name="resnet34"):
         super().__init__()
-        enc = torchvision.models.resnet34(weights=None)
+        if encoder_name not in ("resnet34", "resnet18"):
+            raise NotImplementedError(encoder_name)
+        enc = getattr(torchvision.models, encoder_name)(weights=None)
         del enc.fc                                          # smp: `del self.fc`
         enc.avgpool = nn.Identity()                         # never called
         if in_channels != 3:
@@ -123,9 +126,9 @@ class RefSmpUnetResnet34(nn.Module):
 class RefUNet(nn.Module):
     """The reference's `UNet` (`unet.py:10-69`) minus Lightning: probabilities out."""
 
-    def __init__(self, num_channels=1, num_classes=2):
+    def __init__(self, num_channels=1, num_classes=2, encoder_name="resnet34"):
         super().__init__()
-        self.model = RefSmpUnetResnet34(num_channels, num_classes)
+        self.model = RefSmpUnetResnet34(num_channels, num_classes, encoder_name)
         self.softmax = nn.Softmax(dim=1)                    # unet.py:63
 
     def forward(self, x):
@@ -136,9 +139,9 @@ class RefUNet(nn.Module):
         return next(self.parameters()).device
 
 
-def conv_macs_per_slice(size, classes=2):
+def conv_macs_per_slice(size, classes=2, encoder_name="resnet34"):
     """Dense multiply-accumulates of every conv for one `size` x `size` slice."""
-    net = RefSmpUnetResnet34(1, classes).eval()
+    net = RefSmpUnetResnet34(1, classes, encoder_name).eval()
     total = [0]
 
     def hook(m, inp, out):

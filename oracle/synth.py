@@ -50,11 +50,11 @@ def _calibrate_bn(model, size, gen):
         m.running_var *= 0.75 + 0.5 * torch.rand(m.num_features, generator=gen)
 
 
-def make_model(num_classes=2, seed=1234, calib_size=64):
+def make_model(num_classes=2, seed=1234, calib_size=64, encoder_name="resnet34"):
     """Random-init `RefUNet` in eval mode with randomised, calibrated BatchNorm statistics."""
     torch.manual_seed(seed)
     gen = torch.Generator().manual_seed(seed + 1)
-    model = RefUNet(1, num_classes)
+    model = RefUNet(1, num_classes, encoder_name)
     _randomise_bn(model, gen)
     _calibrate_bn(model, calib_size, gen)
     head = model.model.segmentation_head[0]

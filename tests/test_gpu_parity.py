@@ -279,6 +279,36 @@ def test_forward_matches_fp32_oracle(dev, fitted, c, size):
     assert torch.allclose(got.sum(1), torch.ones_like(got[:, 0]), atol=1e-5)
 
 
+def test_resnet18_encoder_matches_fp32_oracle(dev, iu):
+    """`encoder_name='resnet18'` (first step): the engine reads the block counts off the
+    state_dict; same kernels, same gates -- forward and a 3-axis block prediction."""
+    from oracle import predict_port as pp
+    from oracle import synth
+    vol, lab = synth.blob_volume(64, 2)
+    ref = synth.fit_decisive(synth.make_model(2, encoder_name="resnet18"), vol, lab % 2, steps=100, batch=8,
+                             device=dev).to(dev).eval()
+    model = iu.UNet(num_classes=2, encoder_name="resnet18")
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev).eval()
+    for size, batch in ((64, 8), (256, 3), (512, 2)):
+        reps = (size + 63) // 64
+        img = np.tile(vol[:batch], (1, reps, reps))[:, :size, :size]
+        x = torch.from_numpy(img.astype(np.float32) / 255.0)[:, None].to(dev)
+        with torch.inference_mode():
+            _check_probs(model(x), ref(x))
+    block = torch.from_numpy(pp.normalise_u8(vol))
+
+    def fwd(x):
+        with torch.inference_mode():
+            return ref(torch.from_numpy(x).to(dev)).cpu().numpy()
+    want = pp.predict_block(fwd, block.numpy(), 2, 16, (0, 1, 2))
+    got = iu.predict.predict_block(model, block, num_classes=2, batch_size=16, axes=[0, 1, 2])
+    assert np.abs(got - want).max() <= PROB_TOL
+    resnet34 = iu.UNet(num_classes=2)
+    with pytest.raises(RuntimeError):
+        resnet34.load_state_dict(ref.state_dict())
+
+
 def test_forward_rectangular_and_ragged_batch(dev, fitted):
     ref, model = fitted[2]
     x = torch.rand(5, 1, 96, 160, device=dev)

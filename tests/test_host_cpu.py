@@ -87,6 +87,31 @@ def test_state_dict_matches_oracle_and_training_forward():
     assert torch.equal(m(x), ref(x))                 # autograd path kept for the reference's trainer
 
 
+def test_resnet18_encoder_state_dict_and_checkpoint(tmp_path):
+    """SURVEY section 8 row f3 (first step): the other BasicBlock ResNet behind the same kernels."""
+    import interactive_unet_b200 as iu
+    from oracle.smp_unet_resnet34 import RefUNet
+    ref = RefUNet(1, 3, "resnet18")
+    m = iu.UNet(num_classes=3, encoder_name="resnet18")
+    assert list(m.state_dict()) == list(ref.state_dict())
+    assert "model.encoder.layer3.1.conv2.weight" in m.state_dict()
+    assert "model.encoder.layer3.2.conv1.weight" not in m.state_dict()
+    m.load_state_dict(ref.state_dict())
+    m.train(), ref.train()
+    x = torch.rand(2, 1, 64, 64)
+    assert torch.equal(m(x), ref(x))
+    path = tmp_path / "r18.ckpt"
+    torch.save({"state_dict": ref.state_dict(),
+                "hyper_parameters": dict(lr=1e-4, num_channels=1, num_classes=3, architecture="U-Net",
+                                         encoder_name="resnet18", pretrained=False)}, path)
+    again = iu.UNet.load_from_checkpoint(checkpoint_path=str(path))
+    assert all(torch.equal(again.state_dict()[k], v) for k, v in ref.state_dict().items())
+    with pytest.raises(RuntimeError):                                # a resnet34 checkpoint does not fit
+        iu.UNet(num_classes=3, encoder_name="resnet18").load_state_dict(RefUNet(1, 3).state_dict())
+    with pytest.raises(NotImplementedError):
+        iu.UNet(encoder_name="resnet50")
+
+
 def test_load_from_checkpoint_reference_format(tmp_path):
     """Lightning checkpoint layout of `trainer.py:46-49`: state_dict under `model.`, hyper_parameters
     including a pickled `interactive_unet.metrics` loss function."""
