@@ -13,6 +13,7 @@ import glob
 import os
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -241,29 +242,59 @@ def predict_volumes(input_size=256, num_channels=1, num_classes=2, overlap=0.25,
     device = _require_cuda()
     model = _load_model(num_channels, num_classes, device)
     volume_files = np.sort(glob.glob('data/image_volumes/*.zarr'))
-    for f in volume_files:
-        start_time = time.time()
+
+    def open_and_stage(f):
         volume = zarr3.open(f, mode='r')['0']                # highest resolution (predict.py:167)
         if volume.dtype != np.uint8 or volume.ndim != 3:
             raise TypeError(f"{f}: level '0' must be a 3-D uint8 array (predict.py:237 divides by 255), "
                             f"got {volume.dtype} {volume.shape}")
-        save_path = f.replace('image_volumes', 'predicted_volumes')
-        root = zarr3.open(save_path, mode='w')
-        final_predictions = root.create_array(name='0', shape=list(volume.shape) + [num_classes],
-                                              chunks=(chunk_size, chunk_size, chunk_size, num_classes),
-                                              shards=(shard_size, shard_size, shard_size, num_classes), dtype='uint8',
-                                              overwrite=True)
-        print(f'\nSegmenting {os.path.basename(f)}...')
-        volume_dev = utils.read_array_to_device(volume, device)
-        out_dev = predict_volume_array(model, volume_dev, input_size=input_size, num_classes=num_classes,
-                                       overlap=overlap, batch_size=batch_size, axes=axes)
-        del volume_dev
-        print('Postprocessing and generating multiscale pyramid...')
-        level0 = utils.write_array_from_device(final_predictions, out_dev, wait=False)
+        return utils.stage_array(volume)
+
+    def finish(job):
+        """Wait for a volume's compression / file tasks and report it."""
+        if job is not None:
+            name, shape, start_time, pending = job
+            for p in pending:
+                p.result()
+            print(f'Completed volume {name} {shape} in {time.time() - start_time}.')
+
+    # Three volumes are in flight: i + 1 is being decompressed into pinned memory by a helper thread, i is on the
+    # device, and the shards of i - 1 are still being compressed and written by the pool.
+    prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="iu-prefetch")
+    staged_next = prefetch.submit(open_and_stage, volume_files[0]) if len(volume_files) else None
+    previous = None
+    try:
+        for n, f in enumerate(volume_files):
+            start_time = time.time()
+            staged = staged_next.result()
+            staged_next = prefetch.submit(open_and_stage, volume_files[n + 1]) if n + 1 < len(volume_files) else None
+            shape = tuple(staged.arr.shape)
+            save_path = f.replace('image_volumes', 'predicted_volumes')
+            root = zarr3.open(save_path, mode='w')
+            final_predictions = root.create_array(name='0', shape=list(shape) + [num_classes],
+                                                  chunks=(chunk_size, chunk_size, chunk_size, num_classes),
+                                                  shards=(shard_size, shard_size, shard_size, num_classes),
+                                                  dtype='uint8', overwrite=True)
+            print(f'\nSegmenting {os.path.basename(f)}...')
+            volume_dev = staged.to_device(device)
+            out_dev = predict_volume_array(model, volume_dev, input_size=input_size, num_classes=num_classes,
+                                           overlap=overlap, batch_size=batch_size, axes=axes)
+            del volume_dev
+            finish(previous)
+            previous = None
+            print('Postprocessing and generating multiscale pyramid...')
+            pending = [utils.write_array_from_device(final_predictions, out_dev, wait=False)]
+            previous = (os.path.basename(f), shape, start_time, pending)
+            utils.add_multiscales(save_path, scale=0.5, level0=out_dev, _defer=pending)
+            del out_dev
+    finally:
         try:
-            utils.add_multiscales(save_path, scale=0.5, level0=out_dev)      # zoomed while level 0 is being compressed
+            finish(previous)
         finally:
-            level0.result()
-        del out_dev
-        print(f'Completed volume {os.path.basename(f)} {tuple(volume.shape)} in {time.time() - start_time}.')
+            if staged_next is not None:
+                try:
+                    staged_next.result().release()
+                except Exception:
+                    pass
+            prefetch.shutdown(wait=True)
     print('\nAll volumes segmented.\n')

@@ -26,7 +26,7 @@ from . import zarr3
 from .engine import Engine
 
 __all__ = ["read_volume", "resize_volume", "add_multiscales", "create_multiscale_zarr", "zoom_tables",
-           "write_array_from_device", "read_array_to_device"]
+           "write_array_from_device", "read_array_to_device", "stage_array"]
 
 _engines = {}
 
@@ -162,6 +162,43 @@ class PendingWrite:
                 self._buf = None
 
 
+class StagedArray:
+    """A store array decoded into pinned host memory in chunk-major order (`stage_array`), waiting for its upload."""
+
+    def __init__(self, arr, buf, staged):
+        self.arr, self._buf, self._staged = arr, buf, staged
+
+    def to_device(self, device=None):
+        """One H2D copy + `iu_engine_from_chunks`; the pinned buffer goes back to the pool."""
+        eng = _engine(device)
+        try:
+            staged_dev = self._staged.to(eng.device, non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+        finally:
+            self.release()
+        return eng.from_chunks(staged_dev, self.arr.shape, self.arr.chunks)
+
+    def release(self):
+        if self._buf is not None:
+            _pinned.release(self._buf)
+            self._buf = self._staged = None
+
+
+def stage_array(arr):
+    """Host half of `read_array_to_device` for a store array on the bulk path: pool threads decompress the inner
+    chunks into a pinned buffer.  Touches no device state, so it can run ahead on another thread (the next volume is
+    staged while the current one is being predicted, `predict_volumes`)."""
+    if not isinstance(arr, zarr3.Array) or arr.size == 0 or not _chunked_on_three_axes(arr):
+        raise ValueError("stage_array: a non-empty zarr3.Array chunked over its first three axes is required")
+    buf, staged = _pinned.acquire(arr.chunk_major_shape(), torch.from_numpy(np.empty(0, arr.dtype)).dtype)
+    try:
+        arr.read_chunk_major(out=staged.numpy())
+    except BaseException:
+        _pinned.release(buf)
+        raise
+    return StagedArray(arr, buf, staged)
+
+
 def read_array_to_device(arr, device=None):
     """Whole `zarr3.Array` (or any array-like) -> CUDA tensor of its shape.  Store arrays chunked over the first three
     axes take the bulk path: host threads decompress inner chunks into pinned memory, one H2D copy, and
@@ -169,19 +206,11 @@ def read_array_to_device(arr, device=None):
     eng = _engine(device)
     if not isinstance(arr, zarr3.Array):
         return torch.as_tensor(np.ascontiguousarray(arr)).to(eng.device)
-    tdtype = torch.from_numpy(np.empty(0, arr.dtype)).dtype
     if arr.size == 0:
-        return torch.empty(arr.shape, dtype=tdtype, device=eng.device)
+        return torch.empty(arr.shape, dtype=torch.from_numpy(np.empty(0, arr.dtype)).dtype, device=eng.device)
     if not _chunked_on_three_axes(arr):
         return torch.from_numpy(arr[...]).to(eng.device)
-    buf, staged = _pinned.acquire(arr.chunk_major_shape(), tdtype)
-    try:
-        arr.read_chunk_major(out=staged.numpy())
-        staged_dev = staged.to(eng.device, non_blocking=True)
-        torch.cuda.current_stream(eng.device).synchronize()
-    finally:
-        _pinned.release(buf)
-    return eng.from_chunks(staged_dev, arr.shape, arr.chunks)
+    return stage_array(arr).to_device(eng.device)
 
 
 def write_array_from_device(arr, data, wait=True):
@@ -230,7 +259,7 @@ def _num_steps(volume_shape, chunk_shape, scale):
     return int(np.floor(np.log((np.array(volume_shape) / np.array(chunk_shape)).max()) / np.log(1 / scale)))
 
 
-def add_multiscales(src_file, scale=0.5, level0=None):
+def add_multiscales(src_file, scale=0.5, level0=None, _defer=None):
     """`utils.py:50-80`: levels '1', '2', ... of `src_file`, each the block-wise nearest 0.5x zoom of the previous one
     (block = one shard), until the volume fits a chunk.  `level0`: the level-'0' data as a CUDA tensor if the caller
     still holds it (saves reading the store back).
@@ -254,8 +283,11 @@ def add_multiscales(src_file, scale=0.5, level0=None):
             cur = resize_volume(cur if cur is not None else z0, z1, scale=scale, block_size=shard_shape[0], order=0,
                                 _pending=pending)
     finally:
-        for p in pending:
-            p.result()
+        if _defer is not None:
+            _defer.extend(pending)     # the caller waits (predict_volumes overlaps them with the next volume)
+        else:
+            for p in pending:
+                p.result()
 
 
 def create_multiscale_zarr(volume, dst_file, scale=0.5, chunk_size=128, shard_size=256):
