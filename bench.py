@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 FLOP_PER_VOXEL_AXIS = {2: 235.62e3, 4: 236.19e3}          # BASELINE.md section 3 (dense conv FLOPs per pixel per axis)
 WEAK_EDGES = {1: 512, 2: 640, 4: 800, 8: 1024}             # ~512^3 voxels per GPU (edge % 32 == 0, edge % G == 0)
 AXES = (0, 1, 2)
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 228.1e6
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 228.7e6
 
 
 ENCODER = "resnet34"                                       # --encoder
@@ -298,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
                      # DRAM bytes per conv launch (read + write, mean over the 43 launches of one 74-slice pass at
                      # 512^2) from the committed `ncu --set full` capture; activations only, weights are L2 resident
                      "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH if (edge == 512 and world == 1) else None,
-                     "traffic_source": "profiles/r01_ncu_full_conv_pass_b74.txt (9.81 GB per 43-launch pass)",
+                     "traffic_source": "profiles/r01_ncu_full_conv_pass_v12.txt (9.84 GB per 43-launch pass of 74 slices)",
                      "peak_source": peaks["source"],
                      "flops_per_voxel": flops_per_voxel(classes, encoder=ENCODER), "launches": int(conv_n),
                      "kernel_ms_per_step": conv_ms / prof_steps,
