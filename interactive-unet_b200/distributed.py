@@ -43,6 +43,16 @@ def _all_to_all(recv, send, group):
         req.wait()
 
 
+def volumes_for_rank(files, group=None):
+    """Whole volumes are independent objects (`predict.py:163`: one loop iteration per store), so under `torchrun`
+    `predict_volumes` gives rank r the files r, r + G, r + 2G, ... of the sorted list and needs no collective; a single
+    process (or an uninitialised process group) keeps them all."""
+    files = list(files)
+    if not (dist.is_available() and dist.is_initialized()):
+        return files
+    return files[dist.get_rank(group)::dist.get_world_size(group)]
+
+
 def predict_volume_sharded(engine, volume, axes=(0, 1, 2), window=None, want_u8=True, want_labels=True,
                            want_mean=False, group=None):
     """Predict this rank's z-slab of a replicated cubic volume.

@@ -232,6 +232,7 @@ def predict_volumes(input_size=256, num_channels=1, num_classes=2, overlap=0.25,
     (`predict.py:181-198`) live in HBM instead, so no `temp/` directory is created (or removed, `predict.py:259`)."""
     import signal
     from . import utils, zarr3
+    from .distributed import volumes_for_rank
 
     if threading.current_thread() is threading.main_thread():
         def handle_sigint(sig, frame):                       # predict.py:118-122
@@ -241,7 +242,8 @@ def predict_volumes(input_size=256, num_channels=1, num_classes=2, overlap=0.25,
 
     device = _require_cuda()
     model = _load_model(num_channels, num_classes, device)
-    volume_files = np.sort(glob.glob('data/image_volumes/*.zarr'))
+    # one process per GPU under torchrun: every rank takes its share of the (independent) volumes, no collective
+    volume_files = volumes_for_rank(np.sort(glob.glob('data/image_volumes/*.zarr')))
 
     def open_and_stage(f):
         volume = zarr3.open(f, mode='r')['0']                # highest resolution (predict.py:167)

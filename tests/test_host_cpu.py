@@ -232,6 +232,37 @@ def _sharded_worker(rank, world, port, golden_path, result_dir):
         dist.destroy_process_group()
 
 
+def _volume_partition_worker(rank, world, port, result_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from interactive_unet_b200 import distributed as iud
+    files = [f"data/image_volumes/v{i}.zarr" for i in range(5)]
+    assert iud.volumes_for_rank(files) == files                      # no process group: everything
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        mine = iud.volumes_for_rank(files)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        if rank == 0:
+            with open(os.path.join(result_dir, "parts.txt"), "w") as f:
+                f.write(repr(everyone))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_volume_files_are_partitioned_across_ranks(tmp_path):
+    """`predict_volumes` under torchrun: world_size-2 gloo run, every store goes to exactly one rank."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_volume_partition_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    parts = eval(open(tmp_path / "parts.txt").read())
+    assert parts == [[f"data/image_volumes/v{i}.zarr" for i in (0, 2, 4)],
+                     [f"data/image_volumes/v{i}.zarr" for i in (1, 3)]]
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_prediction_matches_reference_golden(golden_dir, tmp_path, world):
     """world_size-N gloo run of the z-slab path reproduces the VERBATIM reference `predict_volumes`
