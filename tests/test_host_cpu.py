@@ -29,6 +29,21 @@ def test_library_exports_every_header_symbol(built_library):
     assert lib.iu_abi_version() == 1
 
 
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """The boundary is a C ABI: the header must compile on its own as C11 and as C++17 (no torch / CUDA types)."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "iunet_b200.h")
+    for compiler, std, ext in (("gcc", "-std=c11", "c"), ("g++", "-std=c++17", "cpp")):
+        if shutil.which(compiler) is None:
+            pytest.skip(f"{compiler} not installed")
+        src = tmp_path / f"use_header.{ext}"
+        src.write_text('#include "iunet_b200.h"\nint main(void) { return sizeof(&iu_engine_predict_volume) == 0; }\n')
+        r = subprocess.run([compiler, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
+                            "-I", os.path.dirname(hdr), str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_python_binding_mirrors_header(built_library):
     from interactive_unet_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _header_symbols()

@@ -264,3 +264,50 @@ def test_read_volume_clips_level(tmp_path):
     assert iu_utils.read_volume(tmp_path / "p.zarr", level=-3).shape == (16, 16, 16)
     with pytest.raises(KeyError):                       # utils.py:25 clips to num_scales, one past the last level
         iu_utils.read_volume(tmp_path / "p.zarr", level=9)
+
+
+def test_random_stores_round_trip_property(tmp_path_factory):
+    """Property test (hypothesis): any shape / chunking / shard multiple / region write sequence reads back as the
+    numpy model of the same assignments, through both the slicing and the chunk-major paths."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @st.composite
+    def stores(draw):
+        ndim = draw(st.integers(1, 4))
+        chunks = tuple(draw(st.integers(1, 5)) for _ in range(ndim))
+        mult = tuple(draw(st.integers(1, 3)) for _ in range(ndim))
+        shape = tuple(draw(st.integers(1, 13)) for _ in range(ndim))
+        sharded = draw(st.booleans())
+        dtype = draw(st.sampled_from(["uint8", "uint16", "float32", "int64"]))
+        writes = []
+        for _ in range(draw(st.integers(1, 4))):
+            region = []
+            for n in shape:
+                a = draw(st.integers(0, n - 1))
+                region.append(slice(a, draw(st.integers(a + 1, n))))
+            writes.append((tuple(region), draw(st.integers(0, 2 ** 31 - 1))))
+        return shape, chunks, tuple(c * m for c, m in zip(chunks, mult)) if sharded else None, dtype, writes
+
+    @hyp.settings(max_examples=40, deadline=None, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(stores())
+    def run(case):
+        shape, chunks, shards, dtype, writes = case
+        path = tmp_path_factory.mktemp("prop") / "s.zarr"
+        arr = zarr3.open(path, mode="w").create_array(name="0", shape=shape, chunks=chunks, shards=shards, dtype=dtype)
+        model = np.zeros(shape, dtype)
+        for region, seed in writes:
+            block = (np.random.default_rng(seed).random([r.stop - r.start for r in region]) * 3).astype(dtype)
+            arr[region] = block                       # mostly small values: some chunks stay equal to the fill value
+            model[region] = block
+        back = zarr3.open(path, mode="r")["0"]
+        assert np.array_equal(back[...], model)
+        for region, _ in writes:
+            assert np.array_equal(back[region], model[region])
+        staged = back.read_chunk_major()
+        other = zarr3.open(path, mode="r+").create_array(name="1", shape=shape, chunks=chunks, shards=shards,
+                                                         dtype=dtype)
+        other.write_chunk_major(staged)
+        assert np.array_equal(other[...], model)
+
+    run()
