@@ -130,7 +130,7 @@ template <int C>
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
   extern __shared__ float tile[];  // [32 x][32*C + 1]
   constexpr int pitch = 32 * C + 1;
-  const int z = blockIdx.z;
+  const int z = blockIdx.z + a.zoff;
   const int y0 = blockIdx.y * 32, x0 = blockIdx.x * 32;
   const int n = a.n, t = a.t;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -285,7 +285,8 @@ cudaError_t launch_finalise(const float* pred, const float* weight, size_t voxel
 
 cudaError_t launch_reduce(const ReduceArgs& args, cudaStream_t stream) {
   if (args.n_axes < 1 || args.n_axes > 3) return cudaErrorInvalidValue;
-  dim3 grid((args.n + 31) / 32, (args.n + 31) / 32, args.t);
+  if (args.zoff < 0 || args.zcount < 0 || args.zoff + args.zcount > args.t) return cudaErrorInvalidValue;
+  dim3 grid((args.n + 31) / 32, (args.n + 31) / 32, args.zcount ? args.zcount : args.t);
   const int c = args.num_classes;
   const size_t smem = (size_t)32 * (32 * c + 1) * sizeof(float);
 #define IU_REDUCE_CASE(C_)                                                                              \

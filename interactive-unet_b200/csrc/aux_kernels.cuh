@@ -31,6 +31,7 @@ struct ReduceArgs {
   int order[3];
   int n_axes;
   int n, t, z0, num_classes;
+  int zoff, zcount;     // planes [zoff, zoff + zcount) of the slab are reduced (zcount == 0: all t planes)
   const float* g1d;
   float gmax, lo;
   uint8_t* out_u8;

@@ -101,6 +101,7 @@ bool pick_tile(int cin_min, int cout_pad, int* kc, int* bn) {
 struct iu_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // result copies that overlap the last axis (predict_volume), created on first use
   std::string err;
   EncodeTiledFn encode = nullptr;
   int num_classes = 0;
@@ -885,7 +886,8 @@ int iu_engine_create(int device, iu_engine** out) {
   ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (ce != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
     g_create_error = "cuTensorMapEncodeTiled not available from the driver";
-    cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  cudaStreamDestroy(e->stream);
     delete e;
     return IU_ERR_CUDA;
   }
@@ -917,6 +919,7 @@ void iu_engine_destroy(iu_engine* e) {
     cudaEventDestroy(s.begin);
     cudaEventDestroy(s.end);
   }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1076,9 +1079,11 @@ int iu_engine_gather_slices(iu_engine* e, const void* volume_dev, int dtype, int
   return finish(e, flags);
 }
 
-int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, int axis, int slice_begin,
-                           int slice_count, float* probs_dev, int slice_offset, int slice_total, int row_block,
-                           unsigned flags) {
+// `plan_batch` > 0: run on the activation plan of that batch size even if `slice_count` is smaller (a partial batch),
+// so that a caller which interleaves short and long slice ranges does not re-plan (free + allocate) in between.
+static int predict_axis_impl(iu_engine* e, const void* volume, int dtype, int n, int axis, int slice_begin,
+                             int slice_count, float* probs_dev, int slice_offset, int slice_total, int row_block,
+                             unsigned flags, int plan_batch) {
   int rc;
   if (!check_engine(e, true, &rc)) return rc;
   if (!volume || !probs_dev || n < 32 || n % 32 || axis < 0 || axis > 2 || slice_begin < 0 || slice_count < 1 ||
@@ -1098,7 +1103,7 @@ int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, i
     }
     vol_dev = staged;
   }
-  const int bs = auto_batch(e, n, n, slice_count);
+  const int bs = plan_batch > 0 ? plan_batch : auto_batch(e, n, n, slice_count);
   rc = ensure_plan(e, bs, n, n);
   for (int s = 0; rc == IU_OK && s < slice_count; s += bs) {
     const int b = std::min(bs, slice_count - s);
@@ -1119,6 +1124,13 @@ int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, i
   }
   if (rc != IU_OK) return rc;
   return finish(e, flags);
+}
+
+int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, int axis, int slice_begin,
+                           int slice_count, float* probs_dev, int slice_offset, int slice_total, int row_block,
+                           unsigned flags) {
+  return predict_axis_impl(e, volume, dtype, n, axis, slice_begin, slice_count, probs_dev, slice_offset, slice_total,
+                           row_block, flags, 0);
 }
 
 int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float* p2, const int* order, int n_axes,
@@ -1213,10 +1225,6 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
   for (int i = 0; i < n_axes; ++i) {
     if ((rc = grab(vox * c * 4, (void**)&p[axes[i]])) != IU_OK) { release(); return rc; }
   }
-  for (int i = 0; i < n_axes; ++i) {
-    rc = iu_engine_predict_axis(e, vol_dev, dtype, n, axes[i], 0, n, p[axes[i]], 0, n, n, IU_FLAG_ASYNC);
-    if (rc != IU_OK) { release(); return rc; }
-  }
   const bool u8_dev = out_u8 && is_device_ptr(out_u8);
   const bool lab_dev = out_labels && is_device_ptr(out_labels);
   const bool mean_dev = out_mean && is_device_ptr(out_mean);
@@ -1226,6 +1234,93 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
   if (out_u8 && !u8_dev && (rc = grab(vox * c, (void**)&d_u8)) != IU_OK) { release(); return rc; }
   if (out_labels && !lab_dev && (rc = grab(vox, (void**)&d_lab)) != IU_OK) { release(); return rc; }
   if (out_mean && !mean_dev && (rc = grab(vox * c * 4, (void**)&d_mean)) != IU_OK) { release(); return rc; }
+  const bool to_host = (out_u8 && !u8_dev) || (out_labels && !lab_dev) || (out_mean && !mean_dev);
+
+  // Results for the host: the order in which the axes are COMPUTED does not enter the arithmetic (each axis has its
+  // own buffer; K4 adds them in the caller's order), so axis 0 runs last, in parts of the z range, and each part is
+  // reduced and copied out on a second stream while the next one is still in the network.
+  if (to_host && seen[0]) {
+    if (!e->copy_stream) {
+      cudaError_t ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+      if (ce != cudaSuccess) { release(); return e->cuda_fail(ce, "cudaStreamCreate(copy)"); }
+    }
+    for (int i = 0; i < n_axes; ++i) {
+      if (axes[i] == 0) continue;
+      rc = iu_engine_predict_axis(e, vol_dev, dtype, n, axes[i], 0, n, p[axes[i]], 0, n, n, IU_FLAG_ASYNC);
+      if (rc != IU_OK) { release(); return rc; }
+    }
+    float* g_dev = nullptr;
+    if (g1d_host) {
+      if ((rc = grab((size_t)n * 4, (void**)&g_dev)) != IU_OK) { release(); return rc; }
+      cudaError_t ce = cudaMemcpyAsync(g_dev, g1d_host, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream);
+      if (ce != cudaSuccess) { release(); return e->cuda_fail(ce, "cudaMemcpyAsync(window)"); }
+    }
+    ReduceArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 3; ++i) a.p[i] = p[i];
+    for (int i = 0; i < n_axes; ++i) a.order[i] = axes[i];
+    a.n_axes = n_axes;
+    a.n = n;
+    a.t = n;
+    a.num_classes = c;
+    a.g1d = g_dev;
+    a.gmax = gmax;
+    a.lo = lo;
+    a.out_u8 = out_u8 ? d_u8 : nullptr;
+    a.out_labels = out_labels ? d_lab : nullptr;
+    a.out_mean = out_mean ? d_mean : nullptr;
+    // parts of half an internal batch, run as partial batches on the same activation plan as the other axes
+    const int plan_batch = auto_batch(e, n, n, n);
+    const int zc = plan_batch >= 64 ? (plan_batch + 1) / 2 : plan_batch;
+    const int kParts = (n + zc - 1) / zc;
+    std::vector<cudaEvent_t> done((size_t)kParts, nullptr);
+    cudaError_t ce = cudaSuccess;
+    auto copy_part = [&](int k) {
+      const int zs = k * zc, cnt = (zs + zc > n ? n - zs : zc);
+      const size_t plane = (size_t)n * n, off = (size_t)zs * plane, len = (size_t)cnt * plane;
+      cudaError_t r = cudaStreamWaitEvent(e->copy_stream, done[k], 0);
+      if (r == cudaSuccess && out_u8 && !u8_dev)
+        r = cudaMemcpyAsync(out_u8 + off * c, d_u8 + off * c, len * c, cudaMemcpyDeviceToHost, e->copy_stream);
+      if (r == cudaSuccess && out_labels && !lab_dev)
+        r = cudaMemcpyAsync(out_labels + off, d_lab + off, len, cudaMemcpyDeviceToHost, e->copy_stream);
+      if (r == cudaSuccess && out_mean && !mean_dev)
+        r = cudaMemcpyAsync(out_mean + off * c, d_mean + off * c, len * c * 4, cudaMemcpyDeviceToHost, e->copy_stream);
+      return r;
+    };
+    int parts = 0;
+    for (int k = 0; k < kParts && k * zc < n && rc == IU_OK && ce == cudaSuccess; ++k, ++parts) {
+      const int zs = k * zc, cnt = (zs + zc > n ? n - zs : zc);
+      rc = predict_axis_impl(e, vol_dev, dtype, n, 0, zs, cnt, p[0], zs, n, n, IU_FLAG_ASYNC, plan_batch);
+      if (rc != IU_OK) break;
+      a.zoff = zs;
+      a.zcount = cnt;
+      prof_begin(e, IU_PROF_REDUCE);
+      ce = launch_reduce(a, e->stream);
+      prof_end(e);
+      e->launches += 1;
+      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
+      if (ce == cudaSuccess) ce = cudaEventRecord(done[k], e->stream);
+      // the copy of part k-1 is issued AFTER part k's kernels are queued: with pageable destinations the copy call
+      // blocks this thread, and the device then still has a part's worth of work
+      if (ce == cudaSuccess && k > 0) ce = copy_part(k - 1);
+    }
+    if (rc == IU_OK && ce == cudaSuccess && parts > 0) ce = copy_part(parts - 1);
+    cudaError_t ce2 = cudaStreamSynchronize(e->stream);
+    cudaError_t ce3 = cudaStreamSynchronize(e->copy_stream);
+    for (int k = 0; k < kParts; ++k)
+      if (done[k]) cudaEventDestroy(done[k]);
+    for (void* q : held) scratch_put(e, q);
+    if (rc != IU_OK) return rc;
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "predict_volume (pipelined results)");
+    if (ce2 != cudaSuccess) return e->cuda_fail(ce2, "predict_volume");
+    if (ce3 != cudaSuccess) return e->cuda_fail(ce3, "predict_volume (copy stream)");
+    return IU_OK;
+  }
+
+  for (int i = 0; i < n_axes; ++i) {
+    rc = iu_engine_predict_axis(e, vol_dev, dtype, n, axes[i], 0, n, p[axes[i]], 0, n, n, IU_FLAG_ASYNC);
+    if (rc != IU_OK) { release(); return rc; }
+  }
   rc = iu_engine_reduce(e, p[0], p[1], p[2], axes, n_axes, n, n, 0, c, g1d_host, gmax, lo, d_u8, d_lab, d_mean,
                         IU_FLAG_ASYNC);
   if (rc != IU_OK) { release(); return rc; }
