@@ -11,3 +11,5 @@ python tools/profile_forward.py --batch 74 --iters 2 > $O/pf_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_final.csv \
     python tools/profile_forward.py --batch 74 --iters 2 > $O/ncu_launch.log 2>&1
 timeout 600 python bench.py --edge 1024 --classes 4 --steps 2 --warmup 1 --no-cpu-baseline > $O/b_1024c4.json 2> $O/b_1024c4.err; echo "1024^3 C=4 rc=$?"
+timeout 300 python bench.py --encoder resnet18 --steps 5 --warmup 3 --no-cpu-baseline > $O/b_resnet18.json 2> $O/b_resnet18.err; echo "resnet18 rc=$?"
+timeout 300 python tools/zarr_bench.py > $O/zarr_bench.json 2> $O/zarr_bench.err; echo "zarr disk-to-disk rc=$?"
