@@ -67,9 +67,17 @@ __device__ __forceinline__ TileCoord mtile_coord(const ConvArgs& a, int m, int n
 // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5 / 6-9: epilogue groups 0 / 1
 constexpr int kThreads = 320;
 
-template <int KC, int BN, int BM>
+// CL = 2: the kernel runs as clusters of two CTAs that work on neighbouring pixel tiles of the SAME Cout tile; each CTA
+// fetches half of every weight box and multicasts it into both (the kernel is L2-bandwidth bound and the weight box is
+// a third to two thirds of its operand bytes).  A stage may be refilled once BOTH CTAs' MMAs have read it, so the
+// MMA issuer's commit arrives on the stage's empty barrier in both CTAs (count 2).  Launched with ntiles_n == 1 only.
+template <int KC, int BN, int BM, int CL>
 __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
   using Cfg = ConvCfg<KC, BN, BM>;
+  const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
+  // both CTAs of a cluster must run the same number of tiles: an odd total is rounded up with a tile beyond the batch
+  // (zero-filled operands, masked epilogue)
+  const int tiles_end = CL == 2 ? ((a.total_tiles + 1) & ~1) : a.total_tiles;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -90,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
     tma_prefetch_desc(BN == 256 ? &a.bmap256 : &a.bmap);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full_bar(b), 1);
@@ -104,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tiles_end; tile += gridDim.x) {
         const int ntile = tile % a.ntiles_n, m0 = (tile / a.ntiles_n) * BM;
         const TileCoord tc = mtile_coord(a, m0, ntile);
         const TileCoord tc1 = mtile_coord(a, m0 + BM - 1, ntile);  // second M tile (BM == 2)
@@ -125,7 +134,8 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
               for (int cc = 0; cc < chunks; ++cc, ++it) {
                 const int st = it % Cfg::STAGES;
                 const uint32_t ph = (it / Cfg::STAGES) & 1;
-                mbar_wait(empty_bar(st), ph ^ 1u);
+                if constexpr (CL == 2) mbar_wait_peer(empty_bar(st), ph ^ 1u);
+                else mbar_wait(empty_bar(st), ph ^ 1u);
                 mbar_arrive_expect_tx(full_bar(st), tps * (BM * Cfg::A_BYTES + Cfg::B_BYTES));
                 for (int j = 0; j < tps; ++j) {
                   const int q = q0 + j;
@@ -135,8 +145,14 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
                   if constexpr (BM == 2)
                     tma_load_4d(sa + Cfg::A_BYTES, &a.amap[s], full_bar(st), cc * KC, tc1.x0 * sg.stride - sg.pad + q,
                                 tc1.y0 * sg.stride - sg.pad + r, tc1.n0);
-                  tma_load_2d(sa + BM * Cfg::A_BYTES, BN == 256 ? &a.bmap256 : &a.bmap, full_bar(st),
-                              kbase + (r * sg.ksize + q) * sg.cin + cc * KC, tc.ntile * BN);
+                  if constexpr (CL == 2)
+                    tma_load_2d_multicast(sa + BM * Cfg::A_BYTES + crank * (Cfg::B_BYTES / 2),
+                                          BN == 256 ? &a.bmap : &a.bmap2, full_bar(st),
+                                          kbase + (r * sg.ksize + q) * sg.cin + cc * KC,
+                                          tc.ntile * BN + (int)crank * (BN / 2), (uint16_t)3);
+                  else
+                    tma_load_2d(sa + BM * Cfg::A_BYTES, BN == 256 ? &a.bmap256 : &a.bmap, full_bar(st),
+                                kbase + (r * sg.ksize + q) * sg.cin + cc * KC, tc.ntile * BN);
                 }
               }
             }
@@ -155,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
         iters_per_tile += a.seg[s].ksize * (a.seg[s].ksize / tps) * (a.seg[s].cin / KC);
       }
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile = blockIdx.x; tile < tiles_end; tile += gridDim.x, ++tcount) {
         const uint32_t buf = Cfg::NBUF == 2 ? (tcount & 1u) : 0u;
         const uint32_t use = Cfg::NBUF == 2 ? (tcount >> 1) : tcount;  // how often this buffer has been used before
         mbar_wait(acc_empty_bar(buf), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
@@ -187,7 +203,8 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
                 first = 0;
               }
             }
-            umma_commit(empty_bar(st));  // stage reusable once these MMAs have read it
+            if constexpr (CL == 2) umma_commit_multicast(empty_bar(st), (uint16_t)3);  // ... in both CTAs
+            else umma_commit(empty_bar(st));  // stage reusable once these MMAs have read it
           }
         }
         (void)iters_per_tile;
@@ -201,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
     const int quarter = warp & 3;  // TMEM lanes [32q, 32q+32) are the only ones this warp may read
     const int row = quarter * 32 + lane;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = blockIdx.x; tile < tiles_end; tile += gridDim.x, ++tcount) {
       const uint32_t buf = Cfg::NBUF == 2 ? (tcount & 1u) : 0u;
       const uint32_t use = Cfg::NBUF == 2 ? (tcount >> 1) : tcount;
       // BM == 1: group g drains the tiles of buffer g; BM == 2: group g drains M tile g of every CTA tile
@@ -227,10 +244,11 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int KC, int BN, int BM = 1>
+template <int KC, int BN, int BM = 1, int CL = 1>
 static cudaError_t launch_one(const ConvArgs& args_in, cudaStream_t stream) {
   using Cfg = ConvCfg<KC, BN, BM>;
   static int configured_dev = -1;  // per kernel instantiation; the attribute is per device
@@ -238,7 +256,7 @@ static cudaError_t launch_one(const ConvArgs& args_in, cudaStream_t stream) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, BN, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, BN, BM, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -252,15 +270,35 @@ static cudaError_t launch_one(const ConvArgs& args_in, cudaStream_t stream) {
   args.ntiles_n = cout_pad / BN;
   args.total_tiles = ((mtiles + BM - 1) / BM) * args.ntiles_n;
   const int slots = Cfg::CTAS_PER_SM * num_sms;
-  const int grid = args.total_tiles < slots ? args.total_tiles : slots;
-  conv_tc_kernel<KC, BN, BM><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(args);
+  int grid = args.total_tiles < slots ? args.total_tiles : slots;
+  if constexpr (CL == 2) {
+    if (args.ntiles_n != 1) return cudaErrorInvalidValue;  // the two CTAs of a cluster must share their weights
+    grid = (grid + 1) & ~1;
+    if (grid > slots) grid = slots & ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<KC, BN, BM, CL>, args);
+  }
+  conv_tc_kernel<KC, BN, BM, CL><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(args);
   return cudaGetLastError();
 }
 
 #define IU_CONV_DISPATCH(KC_, BN_) \
   if (kc == KC_ && bn == BN_) return launch_one<KC_, BN_>(args, stream);
 
-cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream, int bm) {
+cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream, int bm, int cluster) {
+  if (cluster == 2 && kc == 64 && bn == 256 && bm == 1) return launch_one<64, 256, 1, 2>(args, stream);
+  if (cluster == 2 && kc == 64 && bn == 128 && bm == 2) return launch_one<64, 128, 2, 2>(args, stream);
   if (bm == 2 && kc == 64 && bn == 256) return launch_one<64, 256, 2>(args, stream);
   if (bm == 2 && kc == 64 && bn == 128) return launch_one<64, 128, 2>(args, stream);
   IU_CONV_DISPATCH(64, 256)

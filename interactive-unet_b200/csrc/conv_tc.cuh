@@ -70,7 +70,9 @@ struct alignas(64) ConvArgs {
 
 // Launch on `stream`; KC = min(64, cin), BN = min(128, Cout_pad).  Returns cudaGetLastError().
 // bm = 2 (64-channel chunks, BN 128 / 256 only): CTA tiles of two M tiles that share every weight box.
-cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream, int bm = 1);
+// cluster = 2 (kc 64 with bn 256 / bm 1 or bn 128 / bm 2, layers with a single Cout tile): pairs of CTAs multicast the
+// weight boxes to each other; needs `bmap` (bn 256) / `bmap2` (bn 128) as the half-box maps.
+cudaError_t launch_conv_tc(const ConvArgs& args, int kc, int bn, cudaStream_t stream, int bm = 1, int cluster = 1);
 
 // Shared memory the kernel variant needs (for occupancy planning / tests).
 int conv_tc_smem_bytes(int kc, int bn);

@@ -113,6 +113,7 @@ struct iu_engine {
   int conv_variant = 0;  // 0 = auto (halo kernel where applicable), 1 = per-tap TMA kernel only (env IU_CONV_VARIANT)
   int conv_row = 1;  // env IU_CONV_ROW=0 keeps the narrow layers off the row-folded kernel
   int conv_bn256 = 1;  // env IU_CONV_BN256=0: per-tap kernel with 128-wide Cout tiles only
+  int conv_cluster = 0;  // env IU_CONV_CLUSTER=1: per-tap kernel in CTA pairs that multicast the weight boxes (single-Cout-tile layers)
   int conv_bm = 1;     // env IU_CONV_BM2: bit 0 = two-M-tile CTA tiles for BN 128, bit 1 = for BN 256 (per-tap kernel)
   __nv_bfloat16* d_ident = nullptr;  // [64][64] identity in the storage format: the residual segment of conv_row.cu
   unsigned long long* d_debug = nullptr;  // env IU_CONV_DEBUG=1: 16 cycle counters per conv layer (development aid)
@@ -780,8 +781,16 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
   else halo = has_up || (applicable && (kc <= 32 || bn <= 64) && a.out_h >= kHaloTile && a.out_w >= kHaloTile);
   if (halo) return launch_conv_halo(a, kc, bn, e->stream);
   const int bm = (kc == 64 && a.mode == kEpiBf16) ? e->conv_bm : 1;
-  if (a.use_bn256 && e->conv_bn256 && kc == 64) return launch_conv_tc(a, kc, 256, e->stream, (bm & 2) ? 2 : 1);
-  return launch_conv_tc(a, kc, bn, e->stream, (bn == 128 && (bm & 1)) ? 2 : 1);
+  // weight multicast across CTA pairs: layers whose Cout is ONE tile (Cout 256 with 256-wide tiles, Cout 128 with
+  // paired pixel tiles)
+  if (a.use_bn256 && e->conv_bn256 && kc == 64) {
+    const int bm256 = (bm & 2) ? 2 : 1;
+    const int cl = (e->conv_cluster && bm256 == 1 && a.cout == 256) ? 2 : 1;
+    return launch_conv_tc(a, kc, 256, e->stream, bm256, cl);
+  }
+  const int bm128 = (bn == 128 && (bm & 1)) ? 2 : 1;
+  const int cl = (e->conv_cluster && bm128 == 2 && a.cout == 128 && a.mode == kEpiBf16) ? 2 : 1;
+  return launch_conv_tc(a, kc, bn, e->stream, bm128, cl);
 }
 
 // Run the network on the `batch` slices already in plan.x_in; the head writes according to (mode, out, ...).
@@ -898,6 +907,7 @@ int iu_engine_create(int device, iu_engine** out) {
   if (const char* v = getenv("IU_CONV_ROW")) e->conv_row = atoi(v);
   if (const char* v = getenv("IU_CONV_BN256")) e->conv_bn256 = atoi(v);
   if (const char* v = getenv("IU_CONV_BM2")) e->conv_bm = atoi(v);
+  if (const char* v = getenv("IU_CONV_CLUSTER")) e->conv_cluster = atoi(v);
   if (const char* v = getenv("IU_CONV_DEBUG")) {
     if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(e->d_debug, 0, 64 * 16 * sizeof(unsigned long long));

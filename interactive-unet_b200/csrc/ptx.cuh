@@ -259,6 +259,42 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
+// ---- weight multicast inside a cluster of two ordinary (cta_group::1) CTAs
+// TMA load of one box into the SAME shared-memory offset of every CTA in `mask`, completing on the mbarrier at the
+// same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at offset `bar` in every CTA of `mask`.
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+// mbar_wait for a local barrier whose arrivals also come from the peer CTA (cluster-scope acquire, same back-off).
+__device__ __forceinline__ void mbar_wait_peer(uint32_t bar, uint32_t parity) {
+  uint32_t polls = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++polls > (1u << 28)) __trap();
+    if (IU_WAIT_BACKOFF > 0) __nanosleep(IU_WAIT_BACKOFF);
+  }
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor for a K-major operand whose rows are `SW` bytes long and stored
 // with the matching TMA swizzle (SW = 32, 64 or 128): 8-row groups are SW*8 bytes apart (SBO),

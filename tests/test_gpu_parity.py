@@ -97,7 +97,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", ["pertap", "pertap_bm2", "halo", "pair", "row"])
+@pytest.mark.parametrize("variant", ["pertap", "pertap_bm2", "pertap_cluster", "halo", "pair", "row"])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_matches_fp32_reference(dev, iu, case, precision, variant, monkeypatch):
@@ -107,7 +107,8 @@ def test_conv_matches_fp32_reference(dev, iu, case, precision, variant, monkeypa
     _, b, h, w, c0, c1, cout, k, stride, residual, relu, up2x = case
     act = torch.float16 if precision == "fp16" else torch.bfloat16
     monkeypatch.setenv("IU_CONV_VARIANT", "1" if variant.startswith("pertap") else "2")
-    monkeypatch.setenv("IU_CONV_BM2", "3" if variant == "pertap_bm2" else "0")
+    monkeypatch.setenv("IU_CONV_BM2", "3" if variant == "pertap_bm2" else ("1" if variant == "pertap_cluster" else "0"))
+    monkeypatch.setenv("IU_CONV_CLUSTER", "1" if variant == "pertap_cluster" else "0")
     monkeypatch.setenv("IU_CONV_PAIR", "1" if variant == "pair" else "0")
     monkeypatch.setenv("IU_CONV_ROW", "1" if variant == "row" else "0")
     eng = iu.Engine(0, precision=precision)
