@@ -91,6 +91,12 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // IU_CONV_DEBUG=1: per-role cycle counters, same slots as conv_halo.cu / conv_row.cu (0 MMA wait for a drained
+  // accumulator, 1 MMA wait for operands, 3 MMA thread total, 4 producer wait for a free stage, 7 producer total,
+  // 8 epilogue wait for a full accumulator, 9 epilogue body, 10 CTAs, 11 CTA life)
+  // (only in the one-CTA-per-SM shapes: the two-CTA shapes have no registers to spare for the counters)
+  const bool dbg_on = Cfg::CTAS_PER_SM == 1 && a.debug != nullptr;
+  const long long t_cta = (dbg_on && threadIdx.x == 0) ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.amap[0]);
@@ -120,6 +126,8 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
+      long long p_empty = 0, p_t0 = 0;
+      const long long p_begin = dbg_on ? clock64() : 0;
       for (int tile = blockIdx.x; tile < tiles_end; tile += gridDim.x) {
         const int ntile = tile % a.ntiles_n, m0 = (tile / a.ntiles_n) * BM;
         const TileCoord tc = mtile_coord(a, m0, ntile);
@@ -134,8 +142,10 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
               for (int cc = 0; cc < chunks; ++cc, ++it) {
                 const int st = it % Cfg::STAGES;
                 const uint32_t ph = (it / Cfg::STAGES) & 1;
+                if (dbg_on) p_t0 = clock64();
                 if constexpr (CL == 2) mbar_wait_peer(empty_bar(st), ph ^ 1u);
                 else mbar_wait(empty_bar(st), ph ^ 1u);
+                if (dbg_on) p_empty += clock64() - p_t0;
                 mbar_arrive_expect_tx(full_bar(st), tps * (BM * Cfg::A_BYTES + Cfg::B_BYTES));
                 for (int j = 0; j < tps; ++j) {
                   const int q = q0 + j;
@@ -160,6 +170,10 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
           kbase += sg.ksize * sg.ksize * sg.cin;
         }
       }
+      if (dbg_on) {
+        atomicAdd(a.debug + 4, (unsigned long long)p_empty);
+        atomicAdd(a.debug + 7, (unsigned long long)(clock64() - p_begin));
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
@@ -171,10 +185,14 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
         iters_per_tile += a.seg[s].ksize * (a.seg[s].ksize / tps) * (a.seg[s].cin / KC);
       }
       uint32_t it = 0, tcount = 0;
+      long long w_acc = 0, w_op = 0, m_t0 = 0;
+      const long long m_begin = dbg_on ? clock64() : 0;
       for (int tile = blockIdx.x; tile < tiles_end; tile += gridDim.x, ++tcount) {
         const uint32_t buf = Cfg::NBUF == 2 ? (tcount & 1u) : 0u;
         const uint32_t use = Cfg::NBUF == 2 ? (tcount >> 1) : tcount;  // how often this buffer has been used before
+        if (dbg_on) m_t0 = clock64();
         mbar_wait(acc_empty_bar(buf), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+        if (dbg_on) w_acc += clock64() - m_t0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * Cfg::ACC_COLS;
         uint32_t first = 1;
@@ -186,7 +204,9 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
           for (int i = 0; i < n_it; ++i, ++it, ++local) {
             const int st = it % Cfg::STAGES;
             const uint32_t ph = (it / Cfg::STAGES) & 1;
+            if (dbg_on) m_t0 = clock64();
             mbar_wait(full_bar(st), ph);
+            if (dbg_on) w_op += clock64() - m_t0;
             operand_ready_fence();
             for (int j = 0; j < tps; ++j) {
               const uint32_t sa = base + st * Cfg::STAGE_BYTES + j * Cfg::TAP_BYTES;
@@ -211,6 +231,12 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
         (void)local;
         umma_commit(acc_full_bar(buf));  // accumulator complete
       }
+      if (dbg_on) {
+        atomicAdd(a.debug + 0, (unsigned long long)w_acc);
+        atomicAdd(a.debug + 1, (unsigned long long)w_op);
+        atomicAdd(a.debug + 3, (unsigned long long)(clock64() - m_begin));
+        atomicAdd(a.debug + 10, 1ull);
+      }
     }
   } else {
     // ------------------------------------------------------------ epilogue groups (warps 2-5 and 6-9)
@@ -218,6 +244,8 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
     const int quarter = warp & 3;  // TMEM lanes [32q, 32q+32) are the only ones this warp may read
     const int row = quarter * 32 + lane;
     uint32_t tcount = 0;
+    const bool edbg = dbg_on && warp == 2 && lane == 0;
+    long long e_wait = 0, e_body = 0, e_t0 = 0;
     for (int tile = blockIdx.x; tile < tiles_end; tile += gridDim.x, ++tcount) {
       const uint32_t buf = Cfg::NBUF == 2 ? (tcount & 1u) : 0u;
       const uint32_t use = Cfg::NBUF == 2 ? (tcount >> 1) : tcount;
@@ -231,7 +259,9 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
       const bool valid = (n < a.batch) && (y < a.out_h) && (x < a.out_w);
       uint4 res[EpiCfg<BN>::RV];
       residual_prefetch<BN>(a, tc.ntile, n, y, x, valid, res);
+      if (edbg) e_t0 = clock64();
       mbar_wait(acc_full_bar(buf), use & 1u);
+      if (edbg) { const long long t1 = clock64(); e_wait += t1 - e_t0; e_t0 = t1; }
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * Cfg::ACC_COLS + (BM == 2 ? group * Cfg::TILE_COLS : 0) +
                              ((uint32_t)(quarter * 32) << 16);
@@ -239,6 +269,11 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty_bar(buf));
+      if (edbg) e_body += clock64() - e_t0;
+    }
+    if (edbg) {
+      atomicAdd(a.debug + 8, (unsigned long long)e_wait);
+      atomicAdd(a.debug + 9, (unsigned long long)e_body);
     }
   }
 
@@ -246,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, ConvCfg<KC, BN, BM>::CTAS_PER_SM) co
   __syncthreads();
   if constexpr (CL == 2) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (dbg_on && threadIdx.x == 0) atomicAdd(a.debug + 11, (unsigned long long)(clock64() - t_cta));
 }
 
 template <int KC, int BN, int BM = 1, int CL = 1>
