@@ -103,6 +103,41 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------- synthetic inputs
+def synthetic_model(classes, encoder, seed=1234, calib_size=64):
+    """Random-init weights of the named architecture in the product's own parameter container (no checkpoint can be
+    downloaded here): BN affine parameters randomised, BN statistics calibrated on noise and then jittered, so that
+    BN folding is exercised and activations stay O(1) through the 47 layers.  The CPU arm
+    loads the same state_dict into the oracle network."""
+    import interactive_unet_b200 as iu
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    model = iu.UNet(num_classes=classes, encoder_name=encoder)
+    net = model.model
+    bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    with torch.no_grad():
+        for m in bns:
+            m.weight.copy_(0.5 + torch.rand(m.num_features, generator=gen))
+            m.bias.copy_(-0.2 + 0.4 * torch.rand(m.num_features, generator=gen))
+            m.reset_running_stats()
+            m.momentum = None                       # cumulative average over the calibration batches
+        net.train()
+        for _ in range(2):
+            net(torch.rand(4, 1, calib_size, calib_size, generator=gen))
+        net.eval()
+        for m in bns:
+            m.momentum = 0.1
+            m.running_mean += 0.1 * m.running_var.sqrt() * torch.randn(m.num_features, generator=gen)
+            m.running_var *= 0.75 + 0.5 * torch.rand(m.num_features, generator=gen)
+        net.segmentation_head[0].bias.copy_(0.1 * torch.randn(classes, generator=gen))
+    return model.eval()
+
+
+def noise_volume(n, seed):
+    """Uniform uint8 noise [n,n,n] (the value distribution does not affect timing)."""
+    return np.random.default_rng(seed).integers(0, 256, (n, n, n), dtype=np.uint8)
+
+
 # ------------------------------------------------------------------------------------------- CPU arm
 _CPU_SETUP = {}
 
@@ -112,11 +147,13 @@ def cpu_reference_sample(edge, classes, slices_per_axis, threads, repeats=1):
     volume through the fp32 network + the port's scatter / average / quantise.  Returns voxels/s where one
     voxel = one 3-axis prediction (3 slice-pixels), and the seconds of the best repeat."""
     from oracle import predict_port as pp
-    from oracle import synth
+    from oracle.smp_unet_resnet34 import RefUNet
     torch.set_num_threads(threads)
     key = (edge, classes)
     if key not in _CPU_SETUP:                       # weights / volume are set-up, not part of the timed sample
-        _CPU_SETUP[key] = (synth.make_model(classes, encoder_name=ENCODER), synth.noise_volume(edge, 1))
+        oracle_net = RefUNet(1, classes, ENCODER)
+        oracle_net.load_state_dict(synthetic_model(classes, ENCODER).state_dict())
+        _CPU_SETUP[key] = (oracle_net.eval(), noise_volume(edge, 1))
     model, vol = _CPU_SETUP[key]
     best = None
     for _ in range(repeats):
@@ -168,7 +205,6 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import interactive_unet_b200 as iu
     from interactive_unet_b200 import distributed as iud
-    from oracle import synth                      # seeded synthetic weights / volume generators only
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -177,15 +213,13 @@ def run_ours(args, rank, world, local_rank):
     if edge % world or edge % 32:
         raise SystemExit(f"edge {edge} must be divisible by 32 and by the number of GPUs {world}")
     t_slab = edge // world
-    ref = synth.make_model(classes, encoder_name=ENCODER)             # random-init weights of the named architecture
-    model = iu.UNet(num_classes=classes, encoder_name=ENCODER)
+    model = synthetic_model(classes, ENCODER)                         # random-init weights of the named architecture
     model.precision = args.precision
-    model.load_state_dict(ref.state_dict())
     model = model.to(dev).eval()
     eng = model.engine()
     window = iu.gaussian_window_1d(edge)
 
-    vol_host = torch.from_numpy(synth.noise_volume(edge, 1)).pin_memory()
+    vol_host = torch.from_numpy(noise_volume(edge, 1)).pin_memory()
     vol_dev = vol_host.to(dev)
     stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
 

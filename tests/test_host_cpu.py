@@ -66,6 +66,24 @@ def test_product_package_never_touches_the_oracle():
                 f"{name} reads the reference tree"
 
 
+def test_bench_uses_the_oracle_only_in_its_cpu_arm():
+    """`bench.py` may execute `oracle/` only in the CPU-baseline / reference-arm leg: every `oracle` import must sit
+    inside `cpu_reference_sample` (which both of those call), never at module level or in the GPU arm."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    where = []
+    for fn in [n for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.Module))]:
+        for node in (fn.body if isinstance(fn, ast.Module) else ast.walk(fn)):
+            names = []
+            if isinstance(node, ast.ImportFrom) and node.module:
+                names = [node.module]
+            elif isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                where.append(getattr(fn, "name", "<module>"))
+    assert where and set(where) == {"cpu_reference_sample"}, where
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback(built_library):
     import interactive_unet_b200 as iu
