@@ -16,7 +16,6 @@ axis is zoomed too (4-D blocks): C = 2 -> 1 keeps class 0, C = 4 -> 2 keeps clas
 Shapes where numpy cannot assign the zoomed block (`round(n*scale) != int(i1*scale) - int(i0*scale)`, e.g. odd
 extents, C = 3) raise the same `ValueError` as the reference.
 """
-import os
 import threading
 
 import numpy as np

@@ -11,7 +11,7 @@ import struct
 import numpy as np
 import pytest
 
-import interactive_unet_b200 as iu
+import interactive_unet_b200  # noqa: F401  (registers the package alias)
 from interactive_unet_b200 import utils as iu_utils
 from interactive_unet_b200 import zarr3
 from oracle import predict_port
