@@ -311,3 +311,26 @@ def test_random_stores_round_trip_property(tmp_path_factory):
         assert np.array_equal(other[...], model)
 
     run()
+
+
+def test_bulk_path_layout_rules():
+    """Host-side argument rules of the device staging kernels (no GPU needed): which arrays take the bulk path and how
+    a voxel is sized inside the volume and inside a chunk."""
+    from interactive_unet_b200.engine import Engine
+    assert Engine._voxel_layout((512, 512, 512, 2), (128, 128, 128, 2), 1) == (512, 512, 512, 2, 2, 128, 128, 128)
+    assert Engine._voxel_layout((256, 256, 256, 1), (128, 128, 128, 2), 1) == (256, 256, 256, 1, 2, 128, 128, 128)
+    assert Engine._voxel_layout((40, 36, 44), (16, 16, 16), 2) == (40, 36, 44, 2, 2, 16, 16, 16)
+    assert Engine._voxel_layout((8, 8, 8, 3), (4, 4, 4, 3), 4) == (8, 8, 8, 12, 12, 4, 4, 4)
+    for shape, chunks in [((8, 8, 8, 4), (4, 4, 4, 2)), ((8, 8), (4, 4)), ((8, 8, 8), (4, 4)), ((8, 8, 8, 2, 2), (4, 4, 4, 2, 4))]:
+        with pytest.raises(ValueError):
+            Engine._voxel_layout(shape, chunks, 1)
+
+    class A:
+        def __init__(self, shape, chunks):
+            self.shape, self.chunks, self.ndim = shape, chunks, len(shape)
+            self.chunk_grid = tuple(-(-n // c) for n, c in zip(shape, chunks))
+    assert iu_utils._chunked_on_three_axes(A((512, 512, 512, 2), (128, 128, 128, 2)))
+    assert iu_utils._chunked_on_three_axes(A((256, 256, 256, 1), (128, 128, 128, 2)))      # pyramid level, class axis halved
+    assert iu_utils._chunked_on_three_axes(A((40, 36, 44), (16, 16, 16)))
+    assert not iu_utils._chunked_on_three_axes(A((8, 8, 8, 4), (4, 4, 4, 2)))              # class axis chunked
+    assert not iu_utils._chunked_on_three_axes(A((8, 8), (4, 4)))
