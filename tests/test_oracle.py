@@ -133,3 +133,23 @@ def test_port_matches_verbatim_reference():
     assert np.array_equal(ref.gaussian_3d(24), pp.gaussian_3d(24))
     for a, b in zip(ref.get_block_coordinates(np.array((50, 70, 90)), 32, 0.25), pp.block_coordinates((50, 70, 90), 32)):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("shape,chunk,shard", [((48, 32, 64, 2), 8, 16), ((40, 24, 56), 8, 16), ((34, 32, 32, 4), 8, 16)])
+def test_pyramid_port_matches_verbatim_reference(shape, chunk, shard):
+    """`predict_port.multiscale_levels` vs the verbatim `utils.add_multiscales` (`utils.py:50-80`) on fresh data,
+    including a shape the reference fails on part-way (34 -> 17 -> 8: the error must be the same one)."""
+    from oracle.make_golden import run_reference_add_multiscales
+    rng = np.random.default_rng(11)
+    vol = rng.integers(1, 255, shape, dtype=np.uint8)
+    tail = shape[3:]
+    want, err = run_reference_add_multiscales(vol, (chunk,) * 3 + tail, (shard,) * 3 + tail)
+    try:
+        got = pp.multiscale_levels(vol, (chunk,) * 3 + tail, (shard,) * 3 + tail)
+    except ValueError as e:
+        assert err is not None and err[0] == "ValueError" and err[1] == str(e)
+    else:
+        assert err is None and len(got) == len(want)
+        for k, lv in enumerate(got):
+            assert np.array_equal(lv, want[str(k + 1)])
