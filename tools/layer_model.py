@@ -73,7 +73,7 @@ def model(layer, ghz):
     w_bytes = sum(k * k * cin * cout * 2 for cin, k, _ in segs)
     hbm = in_bytes + out_bytes + w_bytes
     # ---- MMAs and shared-memory traffic
-    n_mma = smem = 0.0
+    n_mma = smem = cyc = 0.0
     if kind == "row":
         rows = {64: 4, 32: 8, 16: 8}[cout]
         for cin, k, up in segs:
@@ -81,17 +81,13 @@ def model(layer, ghz):
             in_rows = (rows / 2 + 2) if up else (rows + 2)   # MMAs per row block and kx and 16 channels
             m = mtiles / rows * in_rows * 3 * (cin / 16.0)
             n_mma += m
-            t = MMA_CYC[min(MMA_CYC, key=lambda v: abs(v - n))]
+            cyc += m * MMA_CYC[min(MMA_CYC, key=lambda v: abs(v - n))]
             smem += m * (4096 + n * 32)
-            layer_cyc = m * t
-            model.cyc = getattr(model, "cyc", 0.0) + layer_cyc
         if residual:
             m = mtiles * (cout / 16.0)                       # identity K segment
             n_mma += m
+            cyc += m * MMA_CYC[cout if cout in MMA_CYC else 64]
             smem += m * (4096 + cout * 32)
-            model.cyc = getattr(model, "cyc", 0.0) + m * MMA_CYC[cout if cout in MMA_CYC else 64]
-        cyc = model.cyc
-        model.cyc = 0.0
         smem += in_bytes                                      # gather writes (weights resident / streamed: small)
     else:
         n = 256 if kind == "tap256" else 128
