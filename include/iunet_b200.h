@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define IU_ABI_VERSION 1
+#define IU_ABI_VERSION 2
 
 #define IU_OK 0
 #define IU_ERR_INVALID 1 /* bad argument / unsupported configuration            */
@@ -79,6 +79,9 @@ int iu_engine_precision(const iu_engine* e);
 
 /* Upper bound on the slices per internal batch (0 = automatic).  Results do not depend on it. */
 int iu_engine_set_max_batch(iu_engine* e, int max_batch);
+/* Slices the engine runs per network pass when asked for `count` slices of h x w (the automatic choice, capped by
+ * iu_engine_set_max_batch): callers that pipeline work against the engine (the multi-GPU exchange) chunk by it. */
+int iu_engine_auto_batch(const iu_engine* e, int h, int w, int count);
 /* Device bytes the engine would hold for `batch` slices of h x w (weights + workspace). */
 int64_t iu_engine_workspace_bytes(iu_engine* e, int batch, int h, int w);
 
@@ -96,6 +99,16 @@ int iu_engine_forward(iu_engine* e, const float* x, int batch, int h, int w, flo
 int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, int axis, int slice_begin,
                            int slice_count, float* probs_dev, int slice_offset, int slice_total, int row_block,
                            unsigned flags);
+
+/* The same for slices of ANY strided device source (uint8 or fp32): element (slice i, row r, col c) of the `count`
+ * h x w images is base_dev[i*stride_slice + r*stride_row + c*stride_col] (strides in elements; h, w multiples of 32,
+ * row_block divides h).  A cubic volume [z][y][x] of edge n is (n*n, n, 1) | (n, n*n, 1) | (1, n*n, n) for axis
+ * 0 | 1 | 2; the multi-GPU path reads its z-slab and the two exchanged strips this way
+ * (`np.moveaxis` + batch slicing of predict.py:91-97 for a source that is not the whole cube).  Output layout as
+ * for iu_engine_predict_axis with n replaced by w. */
+int iu_engine_predict_slices(iu_engine* e, const void* base_dev, int dtype, int count, int h, int w,
+                             int64_t stride_slice, int64_t stride_row, int64_t stride_col, float* probs_dev,
+                             int slice_offset, int slice_total, int row_block, unsigned flags);
 
 /* K1 alone (predict.py:91,95,97,237): gather + normalise slices into fp32 [count][n][n] (device). */
 int iu_engine_gather_slices(iu_engine* e, const void* volume_dev, int dtype, int n, int axis, int start, int count,
@@ -177,6 +190,14 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
 
 /* Number of kernels the engine has launched since creation (bench.py's `gpu_launches`). */
 int64_t iu_engine_launch_count(const iu_engine* e);
+
+/* Device memory the engine keeps between calls: packed weights, the activation plans of the last few (batch, h, w)
+ * shapes (cached so that `predict_slice` and `predict_volumes` can alternate without re-allocating) and pooled
+ * scratch buffers.  iu_engine_release_workspace drains the stream and frees everything but the weights -- the
+ * drop-in `predict_volumes` calls it when it is done (the reference frees its tensors per volume, predict.py:257-259,
+ * and the trainer shares the GPU); iu_engine_held_bytes reports the current total. */
+int iu_engine_release_workspace(iu_engine* e);
+int64_t iu_engine_held_bytes(const iu_engine* e);
 
 /* Per-kernel-class device timing: while enabled every launch is bracketed by CUDA events recorded on
  * the engine's stream.  iu_engine_profile_read drains the stream and returns, per class, the summed

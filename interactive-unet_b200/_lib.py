@@ -11,7 +11,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # IU_LIB: development override (kernel-variant A/B runs built by tools/build_variant.py)
 LIB_PATH = os.environ.get("IU_LIB") or os.path.join(_PKG_DIR, "libiunet_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 IU_OK, IU_ERR_INVALID, IU_ERR_CUDA, IU_ERR_OOM, IU_ERR_STATE = 0, 1, 2, 3, 4
 FLAG_ASYNC = 1
 DTYPE_U8, DTYPE_F32 = 0, 1
@@ -34,10 +34,13 @@ SIGNATURES = {
     "iu_engine_set_precision": (_c.c_int, [_engine_p, _c.c_int]),
     "iu_engine_precision": (_c.c_int, [_engine_p]),
     "iu_engine_set_max_batch": (_c.c_int, [_engine_p, _c.c_int]),
+    "iu_engine_auto_batch": (_c.c_int, [_engine_p, _c.c_int, _c.c_int, _c.c_int]),
     "iu_engine_workspace_bytes": (_c.c_int64, [_engine_p, _c.c_int, _c.c_int, _c.c_int]),
     "iu_engine_forward": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint]),
     "iu_engine_predict_axis": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                           _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_uint]),
+    "iu_engine_predict_slices": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int64,
+                                            _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_uint]),
     "iu_engine_gather_slices": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                            _c.c_void_p, _c.c_uint]),
     "iu_engine_reduce": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_int), _c.c_int,
@@ -67,6 +70,8 @@ SIGNATURES = {
                                        _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,
                                        _c.c_int, _c.c_int, _c.c_void_p]),
     "iu_engine_launch_count": (_c.c_int64, [_engine_p]),
+    "iu_engine_release_workspace": (_c.c_int, [_engine_p]),
+    "iu_engine_held_bytes": (_c.c_int64, [_engine_p]),
     "iu_engine_debug_counters": (_c.c_int, [_engine_p, _c.POINTER(_c.c_uint64), _c.c_int, _c.c_int]),
     "iu_engine_profile": (_c.c_int, [_engine_p, _c.c_int]),
     "iu_engine_profile_read": (_c.c_int, [_engine_p, _c.POINTER(_c.c_double), _c.POINTER(_c.c_int64), _c.c_int]),

@@ -10,19 +10,28 @@ namespace iu {
 __device__ __forceinline__ float norm_val(uint8_t v) { return __fdiv_rn((float)v, 255.0f); }
 __device__ __forceinline__ float norm_val(float v) { return v; }
 
-// axes 0 and 1: image rows are contiguous in the volume -> 16-element vector copy per thread
+// A slice source is described by strides (in elements): element (slice b, row r, col c) lives at
+//   base[b * s_slice + r * s_row + c * s_col].
+// Cubic volume [z][y][x] of edge n: axis 0 -> (n*n, n, 1), axis 1 -> (n, n*n, 1), axis 2 -> (1, n*n, n); the z-slab /
+// strip buffers of the multi-GPU path (distributed.py) use the same three shapes with other extents.
+struct SliceSrc {
+  const void* base;
+  long long s_slice, s_row, s_col;
+  int count, h, w;
+};
+
+// rows contiguous in the source (s_col == 1): 16-element vector copy per thread
 template <typename T>
-__global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ vol, int n, int axis, int start,
-                                                          int count, float* __restrict__ out) {
-  const int groups_per_row = n / 16;
-  const size_t total = (size_t)count * n * groups_per_row;
+__global__ void __launch_bounds__(256) gather_rows_kernel(const SliceSrc s, float* __restrict__ out) {
+  const T* __restrict__ vol = static_cast<const T*>(s.base);
+  const int groups_per_row = s.w / 16;
+  const size_t total = (size_t)s.count * s.h * groups_per_row;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
     const int cg = (int)(g % groups_per_row);
-    const int r = (int)((g / groups_per_row) % n);
-    const int b = (int)(g / ((size_t)groups_per_row * n));
-    const size_t src_row = (axis == 0) ? ((size_t)(start + b) * n + r) : ((size_t)r * n + (start + b));
-    const T* src = vol + src_row * n + cg * 16;
-    float* dst = out + ((size_t)b * n + r) * n + cg * 16;
+    const int r = (int)((g / groups_per_row) % s.h);
+    const int b = (int)(g / ((size_t)groups_per_row * s.h));
+    const T* src = vol + (size_t)b * s.s_slice + (size_t)r * s.s_row + cg * 16;
+    float* dst = out + ((size_t)b * s.h + r) * s.w + cg * 16;
     float v[16];
     if constexpr (sizeof(T) == 1) {
       const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
@@ -42,46 +51,73 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ 
   }
 }
 
-// axis 2: slice index is the volume's fastest dimension -> transpose a [64 cols][32 slices] tile in smem
+// slices contiguous in the source (s_slice == 1): transpose a [64 cols][32 slices] tile in smem
 template <typename T>
-__global__ void __launch_bounds__(256) gather_cols_kernel(const T* __restrict__ vol, int n, int start, int count,
-                                                          float* __restrict__ out) {
+__global__ void __launch_bounds__(256) gather_cols_kernel(const SliceSrc s, float* __restrict__ out) {
   __shared__ float tile[64][33];
+  const T* __restrict__ vol = static_cast<const T*>(s.base);
   const int c0 = blockIdx.x * 64;
   const int r = blockIdx.y;
-  for (int b0 = 0; b0 < count; b0 += 32) {
+  for (int b0 = 0; b0 < s.count; b0 += 32) {
     const int bl = threadIdx.x & 31;
     for (int cl = threadIdx.x >> 5; cl < 64; cl += 8) {
-      if (b0 + bl < count && c0 + cl < n)
-        tile[cl][bl] = norm_val(vol[((size_t)r * n + c0 + cl) * n + start + b0 + bl]);
+      if (b0 + bl < s.count && c0 + cl < s.w)
+        tile[cl][bl] = norm_val(vol[(size_t)r * s.s_row + (size_t)(c0 + cl) * s.s_col + b0 + bl]);
     }
     __syncthreads();
     const int cl = threadIdx.x & 63;
     for (int b = threadIdx.x >> 6; b < 32; b += 4) {
-      if (b0 + b < count && c0 + cl < n) out[((size_t)(b0 + b) * n + r) * n + c0 + cl] = tile[cl][b];
+      if (b0 + b < s.count && c0 + cl < s.w) out[((size_t)(b0 + b) * s.h + r) * s.w + c0 + cl] = tile[cl][b];
     }
     __syncthreads();
   }
 }
 
+// any other stride pattern: one element per thread (correct for every source, fast for none)
+template <typename T>
+__global__ void __launch_bounds__(256) gather_any_kernel(const SliceSrc s, float* __restrict__ out) {
+  const T* __restrict__ vol = static_cast<const T*>(s.base);
+  const size_t total = (size_t)s.count * s.h * s.w;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % s.w);
+    const int r = (int)((i / s.w) % s.h);
+    const size_t b = i / ((size_t)s.w * s.h);
+    out[i] = norm_val(vol[b * s.s_slice + (size_t)r * s.s_row + (size_t)c * s.s_col]);
+  }
+}
+
+cudaError_t launch_gather_strided(const void* base, int is_f32, int count, int h, int w, long long s_slice,
+                                  long long s_row, long long s_col, float* out, cudaStream_t stream) {
+  if (count <= 0 || h <= 0 || w <= 0 || s_slice < 0 || s_row < 0 || s_col < 0) return cudaErrorInvalidValue;
+  SliceSrc s{base, s_slice, s_row, s_col, count, h, w};
+  const size_t esz = is_f32 ? 4 : 1;
+  const bool vec_ok = s_col == 1 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(base) % 16) == 0 &&
+                      ((size_t)s_slice * esz) % 16 == 0 && ((size_t)s_row * esz) % 16 == 0;
+  if (vec_ok) {
+    const size_t groups = (size_t)count * h * (w / 16);
+    const int blocks = (int)((groups + 255) / 256 < 148 * 16 ? (groups + 255) / 256 : 148 * 16);
+    if (is_f32) gather_rows_kernel<float><<<blocks, 256, 0, stream>>>(s, out);
+    else gather_rows_kernel<uint8_t><<<blocks, 256, 0, stream>>>(s, out);
+  } else if (s_slice == 1 && h <= 65535) {
+    dim3 grid((w + 63) / 64, h);
+    if (is_f32) gather_cols_kernel<float><<<grid, 256, 0, stream>>>(s, out);
+    else gather_cols_kernel<uint8_t><<<grid, 256, 0, stream>>>(s, out);
+  } else {
+    const size_t total = (size_t)count * h * w;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    if (is_f32) gather_any_kernel<float><<<blocks, 256, 0, stream>>>(s, out);
+    else gather_any_kernel<uint8_t><<<blocks, 256, 0, stream>>>(s, out);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_gather_slices(const void* vol, int vol_is_f32, int n, int axis, int start, int count, float* out,
                                  cudaStream_t stream) {
   if (n % 16 != 0 || axis < 0 || axis > 2 || count <= 0) return cudaErrorInvalidValue;
-  if (axis < 2) {
-    const size_t groups = (size_t)count * n * (n / 16);
-    const int blocks = (int)((groups + 255) / 256 < 148 * 16 ? (groups + 255) / 256 : 148 * 16);
-    if (vol_is_f32)
-      gather_rows_kernel<float><<<blocks, 256, 0, stream>>>((const float*)vol, n, axis, start, count, out);
-    else
-      gather_rows_kernel<uint8_t><<<blocks, 256, 0, stream>>>((const uint8_t*)vol, n, axis, start, count, out);
-  } else {
-    dim3 grid((n + 63) / 64, n);
-    if (vol_is_f32)
-      gather_cols_kernel<float><<<grid, 256, 0, stream>>>((const float*)vol, n, start, count, out);
-    else
-      gather_cols_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)vol, n, start, count, out);
-  }
-  return cudaGetLastError();
+  const long long nn = (long long)n * n;
+  const long long ss = axis == 0 ? nn : (axis == 1 ? n : 1), sr = axis == 0 ? n : nn, sc = axis == 2 ? n : 1;
+  const char* base = static_cast<const char*>(vol) + (size_t)start * ss * (vol_is_f32 ? 4 : 1);
+  return launch_gather_strided(base, vol_is_f32, count, n, n, ss, sr, sc, out, stream);
 }
 
 // =========================================================================== max-pool 3x3/s2/p1 (NHWC 16-bit, values >= 0)
@@ -126,7 +162,44 @@ cudaError_t launch_maxpool(const __nv_bfloat16* in, int batch, int h, int w, int
 // =========================================================================== K4 reduce + quantise + argmax
 // Block = one z, a 32(y) x 32(x) tile.  The axis-2 operand is x-major in memory, so its tile is staged
 // through shared memory (coalesced along y) and read back transposed; axes 0 and 1 are read directly.
-template <int C>
+// VEC (C = 2 / 4, 16-byte aligned buffers): one 8- / 16-byte load per voxel and operand, packed uint8 stores.
+template <int C, bool VEC>
+__device__ __forceinline__ void load_classes(const float* __restrict__ s, float (&p)[C]) {
+  if constexpr (VEC && C == 2) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(s));
+    p[0] = v.x; p[1] = v.y;
+  } else if constexpr (VEC && C == 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(s));
+    p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) p[c] = __ldg(s + c);
+  }
+}
+template <int C, bool VEC>
+__device__ __forceinline__ void store_classes(float* __restrict__ d, const float (&p)[C]) {
+  if constexpr (VEC && C == 2) {
+    *reinterpret_cast<float2*>(d) = make_float2(p[0], p[1]);
+  } else if constexpr (VEC && C == 4) {
+    *reinterpret_cast<float4*>(d) = make_float4(p[0], p[1], p[2], p[3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[c] = p[c];
+  }
+}
+template <int C, bool VEC>
+__device__ __forceinline__ void store_bytes(uint8_t* __restrict__ d, const uint8_t (&q)[C]) {
+  if constexpr (VEC && C == 2) {
+    *reinterpret_cast<uchar2*>(d) = make_uchar2(q[0], q[1]);
+  } else if constexpr (VEC && C == 4) {
+    *reinterpret_cast<uchar4*>(d) = make_uchar4(q[0], q[1], q[2], q[3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[c] = q[c];
+  }
+}
+
+template <int C, bool VEC>
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
   extern __shared__ float tile[];  // [32 x][32*C + 1]
   constexpr int pitch = 32 * C + 1;
@@ -140,7 +213,16 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
       if (x0 + xl < n) {
         const float* src = a.p[2] + (((size_t)(x0 + xl) * t + z) * n + y0) * C;
         const int lim = min(32, n - y0) * C;
-        for (int j = lane; j < lim; j += 32) tile[xl * pitch + j] = __ldg(src + j);
+        if (VEC && lim == 32 * C) {
+          // full tile row: 32*C floats as 16-byte loads (8*C lanes), scattered into the odd-pitch tile
+          if (lane < 8 * C) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + lane);
+            float* d = tile + xl * pitch + 4 * lane;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+          }
+        } else {
+          for (int j = lane; j < lim; j += 32) tile[xl * pitch + j] = __ldg(src + j);
+        }
       }
     }
   }
@@ -148,20 +230,20 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
 
   const int x = x0 + lane;
   if (x >= n) return;
+  // window = clip((g[z]*g[y])*g[x] / gmax, lo, 1) (predict.py:327-347); gmax is 1.0f for every window the host builds
+  // (g is normalised to a maximum of exactly 1), and x / 1.0f == x bit for bit, so that division is skipped then
+  const bool windowed = a.g1d != nullptr;
+  const float gz = windowed ? __ldg(a.g1d + a.z0 + z) : 0.0f;
+  const float gx = windowed ? __ldg(a.g1d + x) : 0.0f;
+  const bool unit_gmax = a.gmax == 1.0f;
+  const float axes_f = (float)a.n_axes;
+#pragma unroll 2
   for (int yl = wrp; yl < 32; yl += 8) {
     const int y = y0 + yl;
     if (y >= n) break;
     float p[3][C];
-    if (a.p[0] != nullptr) {
-      const float* s = a.p[0] + (((size_t)z * n + y) * n + x) * C;
-#pragma unroll
-      for (int c = 0; c < C; ++c) p[0][c] = __ldg(s + c);
-    }
-    if (a.p[1] != nullptr) {
-      const float* s = a.p[1] + (((size_t)y * t + z) * n + x) * C;
-#pragma unroll
-      for (int c = 0; c < C; ++c) p[1][c] = __ldg(s + c);
-    }
+    if (a.p[0] != nullptr) load_classes<C, VEC>(a.p[0] + (((size_t)z * n + y) * n + x) * C, p[0]);
+    if (a.p[1] != nullptr) load_classes<C, VEC>(a.p[1] + (((size_t)y * t + z) * n + x) * C, p[1]);
     if (a.p[2] != nullptr) {
 #pragma unroll
       for (int c = 0; c < C; ++c) p[2][c] = tile[lane * pitch + yl * C + c];
@@ -175,13 +257,10 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
         const float v = ax == 0 ? p[0][c] : (ax == 1 ? p[1][c] : p[2][c]);
         acc = __fadd_rn(acc, v);                       // predict.py:101-106, in the caller's axis order
       }
-      m[c] = __fdiv_rn(acc, (float)a.n_axes);          // predict.py:110
+      m[c] = __fdiv_rn(acc, axes_f);               // predict.py:110
     }
     const size_t vox = ((size_t)z * n + y) * n + x;
-    if (a.out_mean != nullptr) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) a.out_mean[vox * C + c] = m[c];
-    }
+    if (a.out_mean != nullptr) store_classes<C, VEC>(a.out_mean + vox * C, m);
     if (a.out_labels != nullptr) {
       int best = 0;
 #pragma unroll
@@ -189,24 +268,26 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
         if (m[c] > m[best]) best = c;                  // first maximum wins (np.argmax, predict.py:38)
       a.out_labels[vox] = (uint8_t)best;
     }
+    float wgt = 0.0f;
+    if (windowed) {
+      wgt = __fmul_rn(__fmul_rn(gz, __ldg(a.g1d + y)), gx);
+      if (!unit_gmax) wgt = __fdiv_rn(wgt, a.gmax);
+      wgt = fminf(fmaxf(wgt, a.lo), 1.0f);             // predict.py:345
+    }
     if (a.blend_pred != nullptr) {
       if (z >= a.l0[0] && z < a.l1[0] && y >= a.l0[1] && y < a.l1[1] && x >= a.l0[2] && x < a.l1[2]) {
-        float wgt = __fmul_rn(__fmul_rn(__ldg(a.g1d + a.z0 + z), __ldg(a.g1d + y)), __ldg(a.g1d + x));
-        wgt = __fdiv_rn(wgt, a.gmax);
-        wgt = fminf(fmaxf(wgt, a.lo), 1.0f);           // predict.py:345
         const size_t g = ((size_t)(a.b0[0] + z) * a.gh + (a.b0[1] + y)) * a.gw + (a.b0[2] + x);
+        float acc[C];
+        load_classes<C, false>(a.blend_pred + g * C, acc);
 #pragma unroll
-        for (int c = 0; c < C; ++c)                    // predict.py:244
-          a.blend_pred[g * C + c] = __fadd_rn(a.blend_pred[g * C + c], __fmul_rn(m[c], wgt));
-        a.blend_weight[g] = __fadd_rn(a.blend_weight[g], wgt);   // predict.py:245
+        for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(m[c], wgt));   // predict.py:244
+        store_classes<C, false>(a.blend_pred + g * C, acc);
+        a.blend_weight[g] = __fadd_rn(a.blend_weight[g], wgt);                          // predict.py:245
       }
     }
     if (a.out_u8 != nullptr) {
       uint8_t q[C];
-      if (a.g1d != nullptr) {
-        float wgt = __fmul_rn(__fmul_rn(__ldg(a.g1d + a.z0 + z), __ldg(a.g1d + y)), __ldg(a.g1d + x));
-        wgt = __fdiv_rn(wgt, a.gmax);
-        wgt = fminf(fmaxf(wgt, a.lo), 1.0f);           // predict.py:345
+      if (windowed) {
         const float den = fmaxf(wgt, 1e-3f);           // predict.py:253,255
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -217,8 +298,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
 #pragma unroll
         for (int c = 0; c < C; ++c) q[c] = (uint8_t)(int)__fmul_rn(255.0f, m[c]);
       }
-#pragma unroll
-      for (int c = 0; c < C; ++c) a.out_u8[vox * C + c] = q[c];
+      store_bytes<C, VEC>(a.out_u8 + vox * C, q);
     }
   }
 }
@@ -289,16 +369,25 @@ cudaError_t launch_reduce(const ReduceArgs& args, cudaStream_t stream) {
   dim3 grid((args.n + 31) / 32, (args.n + 31) / 32, args.zcount ? args.zcount : args.t);
   const int c = args.num_classes;
   const size_t smem = (size_t)32 * (32 * c + 1) * sizeof(float);
-#define IU_REDUCE_CASE(C_)                                                                              \
-  case C_:                                                                                              \
-    cudaFuncSetAttribute(reduce_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    reduce_kernel<C_><<<grid, 256, smem, stream>>>(args);                                               \
-    break;
+  // vector path: 2 / 4 classes with every buffer aligned to its widest access
+  auto aligned = [](const void* p, size_t a) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % a == 0; };
+  const bool vec = (c == 2 || c == 4) && aligned(args.p[0], 16) && aligned(args.p[1], 16) && aligned(args.p[2], 16) &&
+                   aligned(args.out_mean, 16) && aligned(args.out_u8, 4);
+#define IU_REDUCE_LAUNCH(C_, V_)                                                                         \
+  cudaFuncSetAttribute(reduce_kernel<C_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  reduce_kernel<C_, V_><<<grid, 256, smem, stream>>>(args);
+#define IU_REDUCE_CASE(C_) \
+  case C_:                 \
+    IU_REDUCE_LAUNCH(C_, false) break;
   switch (c) {
     IU_REDUCE_CASE(1)
-    IU_REDUCE_CASE(2)
+    case 2:
+      if (vec) { IU_REDUCE_LAUNCH(2, true) } else { IU_REDUCE_LAUNCH(2, false) }
+      break;
     IU_REDUCE_CASE(3)
-    IU_REDUCE_CASE(4)
+    case 4:
+      if (vec) { IU_REDUCE_LAUNCH(4, true) } else { IU_REDUCE_LAUNCH(4, false) }
+      break;
     IU_REDUCE_CASE(5)
     IU_REDUCE_CASE(6)
     IU_REDUCE_CASE(7)
@@ -308,6 +397,8 @@ cudaError_t launch_reduce(const ReduceArgs& args, cudaStream_t stream) {
     default:
       return cudaErrorInvalidValue;
   }
+#undef IU_REDUCE_CASE
+#undef IU_REDUCE_LAUNCH
   return cudaGetLastError();
 }
 

@@ -12,6 +12,11 @@ namespace iu {
 // (`predict.py:237` / `:30`), float input is copied.  Image (row,col) = (y,x) | (z,x) | (z,y).
 cudaError_t launch_gather_slices(const void* vol, int vol_is_f32, int n, int axis, int start, int count, float* out,
                                  cudaStream_t stream);
+// The same for any slice source given by element strides: element (slice b, row r, col c) of the `count` h x w
+// images is base[b*s_slice + r*s_row + c*s_col] (uint8 or fp32).  Vector path when rows are contiguous (s_col == 1,
+// 16-byte aligned), smem transpose when slices are (s_slice == 1), scalar gather otherwise.
+cudaError_t launch_gather_strided(const void* base, int is_f32, int count, int h, int w, long long s_slice,
+                                  long long s_row, long long s_col, float* out, cudaStream_t stream);
 
 // 3x3 stride-2 pad-1 max pool on NHWC 16-bit NON-NEGATIVE values (post-ReLU): for those the unsigned
 // integer order of the bit patterns equals the numeric order in both fp16 and bf16.

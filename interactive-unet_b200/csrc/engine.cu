@@ -59,6 +59,13 @@ struct Plan {
   ConvArgs stem_epi;
   CUtensorMap stem_omap;
   size_t bytes = 0;
+  uint64_t last_use = 0;  // LRU stamp while the plan sits in the cache
+  // latency path (`predict_slice`, predict.py:16-47): the 46 launches of one single-batch forward captured as a CUDA
+  // graph.  The graph reads plan.x_in and writes plan.fwd_out, so its kernel arguments never change.
+  float* fwd_out = nullptr;  // [batch][C][h][w] fp32
+  cudaGraphExec_t graph = nullptr;
+  int fwd_calls = 0;
+  int graph_launches = 0;  // kernels inside the graph
 };
 
 struct Scratch {
@@ -126,8 +133,15 @@ struct iu_engine {
   std::vector<TensorSpec> tensors;
   std::vector<ConvLayer> convs;
   int t_f1 = -1, t_p1 = -1;
-  Plan plan;
+  Plan plan;                 // the current activation plan
+  std::vector<Plan> cached;  // other (batch, h, w) plans kept allocated: the app alternates predict_slice / predict_volumes
+  int plan_cache = 3;        // env IU_PLAN_CACHE: plans kept besides none in use (0 = re-plan on every shape change)
+  uint64_t use_clock = 0;
+  int use_graph = 1;         // env IU_GRAPH=0: never capture the single-batch forward
   std::vector<Scratch> scratch;
+  size_t scratch_keep = ~(size_t)0;  // env IU_SCRATCH_KEEP_MB: idle scratch above this is returned to the driver when a
+                                     // volume call returns (default: keep everything for the next call of the same
+                                     // size; `iu_engine_release_workspace` is the explicit hand-back)
 
   // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers)
   bool prof = false;
@@ -228,6 +242,41 @@ void scratch_put(iu_engine* e, void* p) {
   for (auto& s : e->scratch)
     if (s.ptr == p) s.used = false;
 }
+// Idle scratch beyond `scratch_keep` bytes goes back to the driver (largest blocks first): after a tiled volume the
+// fp32 accumulators would otherwise stay allocated for the engine's lifetime, outside torch's caching allocator, and
+// the trainer / suggestor in the same process would see that much less free HBM.
+void scratch_trim(iu_engine* e) {
+  size_t idle = 0;
+  for (auto& s : e->scratch)
+    if (!s.used && s.ptr) idle += s.bytes;
+  while (idle > e->scratch_keep) {
+    int big = -1;
+    for (size_t i = 0; i < e->scratch.size(); ++i)
+      if (!e->scratch[i].used && e->scratch[i].ptr && (big < 0 || e->scratch[i].bytes > e->scratch[big].bytes)) big = (int)i;
+    if (big < 0) break;
+    cudaFree(e->scratch[big].ptr);
+    idle -= e->scratch[big].bytes;
+    e->scratch.erase(e->scratch.begin() + big);
+  }
+}
+// Every ABI call runs on the engine's device and puts the caller's current device back on return (a multi-GPU
+// process -- torch -- must not find its current device changed by a prediction call).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(int device) {
+    cudaError_t ce = cudaGetDevice(&prev);
+    if (ce != cudaSuccess) return ce;
+    if (prev != device) {
+      ce = cudaSetDevice(device);
+      switched = ce == cudaSuccess;
+    }
+    return ce;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
 bool is_device_ptr(const void* p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -373,11 +422,22 @@ void free_weights(iu_engine* e) {
   e->weight_bytes = 0;
 }
 
-void free_plan(iu_engine* e) {
-  for (auto p : e->plan.bufs)
-    if (p) cudaFree(p);
-  if (e->plan.x_in) cudaFree(e->plan.x_in);
-  e->plan = Plan();
+void release_plan(Plan& p) {
+  for (auto b : p.bufs)
+    if (b) cudaFree(b);
+  if (p.x_in) cudaFree(p.x_in);
+  if (p.fwd_out) cudaFree(p.fwd_out);
+  if (p.graph) cudaGraphExecDestroy(p.graph);
+  p = Plan();
+}
+void free_plan(iu_engine* e) { release_plan(e->plan); }
+void free_cached_plans(iu_engine* e) {
+  for (auto& p : e->cached) release_plan(p);
+  e->cached.clear();
+}
+void free_all_plans(iu_engine* e) {
+  free_plan(e);
+  free_cached_plans(e);
 }
 
 int new_tensor(iu_engine* e, int c, int hdiv) {
@@ -628,9 +688,8 @@ size_t plan_bytes(const iu_engine* e, int batch_pad, int h, int w) {
   return total;
 }
 
-int ensure_plan(iu_engine* e, int batch, int h, int w) {
-  if (e->plan.batch == batch && e->plan.h == h && e->plan.w == w) return IU_OK;
-  free_plan(e);
+// Allocate and describe the workspace of (batch, h, w) in e->plan (which must be empty).
+int build_plan(iu_engine* e, int batch, int h, int w) {
   Plan& p = e->plan;
   const int bp = (batch + 7) / 8 * 8;  // images are tiled in groups of up to 8: keep every TMA box inside the tensor
   p.bufs.assign(e->tensors.size(), nullptr);
@@ -742,6 +801,53 @@ int ensure_plan(iu_engine* e, int batch, int h, int w) {
   return IU_OK;
 }
 
+// Make (batch, h, w) the current plan.  Plans are cached (the app alternates `predict_slice` on one slice with
+// `predict_volumes` on batches: re-planning would free and re-allocate gigabytes on every switch); the least recently
+// used ones are dropped beyond `plan_cache` entries, and all of them when an allocation fails.
+int ensure_plan(iu_engine* e, int batch, int h, int w) {
+  e->use_clock += 1;
+  if (e->plan.batch == batch && e->plan.h == h && e->plan.w == w) return IU_OK;
+  if (e->plan.batch != 0) {
+    if (e->plan_cache > 0) {
+      e->plan.last_use = e->use_clock - 1;
+      e->cached.push_back(std::move(e->plan));
+      e->plan = Plan();
+    } else {
+      cudaStreamSynchronize(e->stream);
+      free_plan(e);
+    }
+  }
+  for (size_t i = 0; i < e->cached.size(); ++i)
+    if (e->cached[i].batch == batch && e->cached[i].h == h && e->cached[i].w == w) {
+      e->plan = std::move(e->cached[i]);
+      e->cached.erase(e->cached.begin() + i);
+      return IU_OK;
+    }
+  while ((int)e->cached.size() > std::max(0, e->plan_cache - 1)) {
+    size_t lru = 0;
+    for (size_t i = 1; i < e->cached.size(); ++i)
+      if (e->cached[i].last_use < e->cached[lru].last_use) lru = i;
+    cudaStreamSynchronize(e->stream);
+    release_plan(e->cached[lru]);
+    e->cached.erase(e->cached.begin() + lru);
+  }
+  int rc = build_plan(e, batch, h, w);
+  if (rc == IU_ERR_OOM && (!e->cached.empty() || !e->scratch.empty())) {
+    // give everything idle back to the driver and try once more
+    cudaStreamSynchronize(e->stream);
+    free_cached_plans(e);
+    for (auto& sc : e->scratch)
+      if (!sc.used && sc.ptr) {
+        cudaFree(sc.ptr);
+        sc.ptr = nullptr;
+        sc.bytes = 0;
+      }
+    cudaGetLastError();
+    rc = build_plan(e, batch, h, w);
+  }
+  return rc;
+}
+
 // Slices per internal batch.  Bigger batches amortise the 46 launches per pass and their prologues (weight tiles,
 // TMEM allocation); measured on B200 at 512^2: 37 / 74 / 148 / 256 slices -> 141.4 / 136.5 / 135.4 / 133.9 ms per
 // 512^3 volume (keeping producer -> consumer tensors inside L2 with small batches does NOT pay).  Target 256 slices
@@ -829,12 +935,12 @@ int finish(iu_engine* e, unsigned flags) {
   return IU_OK;
 }
 
-bool check_engine(iu_engine* e, bool need_weights, int* rc) {
+bool check_engine(iu_engine* e, bool need_weights, int* rc, DeviceGuard* guard) {
   if (!e) {
     *rc = IU_ERR_INVALID;
     return false;
   }
-  cudaError_t ce = cudaSetDevice(e->device);
+  cudaError_t ce = guard->enter(e->device);
   if (ce != cudaSuccess) {
     *rc = e->cuda_fail(ce, "cudaSetDevice");
     return false;
@@ -877,7 +983,8 @@ int iu_engine_create(int device, iu_engine** out) {
                      std::to_string(prop.minor) + "; iunet_b200 kernels are built for sm_100a only";
     return IU_ERR_CUDA;
   }
-  ce = cudaSetDevice(device);
+  DeviceGuard guard;
+  ce = guard.enter(device);
   if (ce != cudaSuccess) {
     g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(ce);
     return IU_ERR_CUDA;
@@ -908,6 +1015,9 @@ int iu_engine_create(int device, iu_engine** out) {
   if (const char* v = getenv("IU_CONV_BN256")) e->conv_bn256 = atoi(v);
   if (const char* v = getenv("IU_CONV_BM2")) e->conv_bm = atoi(v);
   if (const char* v = getenv("IU_CONV_CLUSTER")) e->conv_cluster = atoi(v);
+  if (const char* v = getenv("IU_PLAN_CACHE")) e->plan_cache = std::max(0, atoi(v));
+  if (const char* v = getenv("IU_GRAPH")) e->use_graph = atoi(v);
+  if (const char* v = getenv("IU_SCRATCH_KEEP_MB")) e->scratch_keep = (size_t)std::max(0, atoi(v)) << 20;
   if (const char* v = getenv("IU_CONV_DEBUG")) {
     if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(e->d_debug, 0, 64 * 16 * sizeof(unsigned long long));
@@ -918,9 +1028,10 @@ int iu_engine_create(int device, iu_engine** out) {
 
 void iu_engine_destroy(iu_engine* e) {
   if (!e) return;
-  cudaSetDevice(e->device);
+  DeviceGuard guard;
+  guard.enter(e->device);
   cudaStreamSynchronize(e->stream);
-  free_plan(e);
+  free_all_plans(e);
   free_weights(e);
   for (auto& s : e->scratch)
     if (s.ptr) cudaFree(s.ptr);
@@ -938,7 +1049,8 @@ void* iu_engine_stream(iu_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 int iu_engine_synchronize(iu_engine* e) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   IU_CUDA(e, cudaStreamSynchronize(e->stream));
   return IU_OK;
 }
@@ -946,11 +1058,12 @@ int iu_engine_synchronize(iu_engine* e) {
 int iu_engine_load_weights(iu_engine* e, int num_classes, int n_tensors, const char* const* names,
                            const float* const* data, const int64_t* numel) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (num_classes < 1 || num_classes > 16) return e->fail(IU_ERR_INVALID, "num_classes must be in [1, 16]");
   if (!names || !data || !numel) return e->fail(IU_ERR_INVALID, "null tensor table");
   cudaStreamSynchronize(e->stream);
-  free_plan(e);
+  free_all_plans(e);
   free_weights(e);
   HostTensors ht;
   for (int i = 0; i < n_tensors; ++i) ht.t[names[i]] = {data[i], numel[i]};
@@ -973,10 +1086,11 @@ int iu_engine_set_precision(iu_engine* e, int precision) {
   if (precision != IU_PRECISION_FP16 && precision != IU_PRECISION_BF16)
     return e->fail(IU_ERR_INVALID, "precision must be IU_PRECISION_FP16 or IU_PRECISION_BF16");
   const int fp16 = precision == IU_PRECISION_FP16;
+  DeviceGuard guard;
   if (fp16 != e->fp16 && e->loaded) {
-    cudaSetDevice(e->device);
+    guard.enter(e->device);
     cudaStreamSynchronize(e->stream);
-    free_plan(e);
+    free_all_plans(e);
     free_weights(e);  // packed weights are format specific: the caller must load them again
   }
   e->fp16 = fp16;
@@ -997,9 +1111,37 @@ int64_t iu_engine_workspace_bytes(iu_engine* e, int batch, int h, int w) {
 
 int64_t iu_engine_launch_count(const iu_engine* e) { return e ? e->launches : 0; }
 
+int iu_engine_auto_batch(const iu_engine* e, int h, int w, int count) {
+  if (!e || h < 1 || w < 1 || count < 1) return 0;
+  return auto_batch(e, h, w, count);
+}
+
+int iu_engine_release_workspace(iu_engine* e) {
+  int rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
+  IU_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (e->copy_stream) IU_CUDA(e, cudaStreamSynchronize(e->copy_stream));
+  free_all_plans(e);
+  const size_t keep = e->scratch_keep;
+  e->scratch_keep = 0;
+  scratch_trim(e);
+  e->scratch_keep = keep;
+  return IU_OK;
+}
+
+int64_t iu_engine_held_bytes(const iu_engine* e) {
+  if (!e) return -1;
+  size_t total = e->weight_bytes + e->plan.bytes;
+  for (const auto& p : e->cached) total += p.bytes;
+  for (const auto& sc : e->scratch) total += sc.bytes;
+  return (int64_t)total;
+}
+
 int iu_engine_debug_counters(iu_engine* e, unsigned long long* out, int n_values, int reset) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!e->d_debug) return e->fail(IU_ERR_STATE, "debug counters are off (set IU_CONV_DEBUG=1 before creating the engine)");
   if (!out || n_values < 1 || n_values > 64 * 16) return e->fail(IU_ERR_INVALID, "debug_counters: bad arguments");
   IU_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1010,7 +1152,8 @@ int iu_engine_debug_counters(iu_engine* e, unsigned long long* out, int n_values
 
 int iu_engine_profile(iu_engine* e, int enable) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   prof_flush(e);
   e->prof = enable != 0;
   return IU_OK;
@@ -1018,7 +1161,8 @@ int iu_engine_profile(iu_engine* e, int enable) {
 
 int iu_engine_profile_read(iu_engine* e, double* ms, int64_t* count, int reset) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!ms || !count) return e->fail(IU_ERR_INVALID, "profile_read: null output");
   prof_flush(e);
   for (int i = 0; i < IU_PROF_CLASSES; ++i) {
@@ -1034,7 +1178,8 @@ int iu_engine_profile_read(iu_engine* e, double* ms, int64_t* count, int reset) 
 
 int iu_engine_forward(iu_engine* e, const float* x, int batch, int h, int w, float* probs, unsigned flags) {
   int rc;
-  if (!check_engine(e, true, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, true, &rc, &guard)) return rc;
   if (!x || !probs || batch < 1) return e->fail(IU_ERR_INVALID, "forward: null pointer or empty batch");
   if (h < 32 || w < 32 || h % 32 || w % 32)
     return e->fail(IU_ERR_INVALID, "Wrong input shape height=" + std::to_string(h) + ", width=" + std::to_string(w) +
@@ -1045,6 +1190,57 @@ int iu_engine_forward(iu_engine* e, const float* x, int batch, int h, int w, flo
   if (rc != IU_OK) return rc;
   const bool x_dev = is_device_ptr(x), out_dev = is_device_ptr(probs);
   const size_t img = (size_t)h * w;
+  // Latency path (one internal batch of at most 64 slices of 512^2, e.g. `predict_slice` on one 256^2 slice): from
+  // the second call on a plan its launches run as ONE CUDA graph reading plan.x_in and writing plan.fwd_out.
+  if (e->use_graph && bs == batch && !e->prof && !e->d_debug && (size_t)batch * img <= (size_t)64 * 512 * 512) {
+    Plan& p = e->plan;
+    const size_t out_bytes = (size_t)batch * c * img * 4;
+    if (!p.fwd_out) {
+      cudaError_t ce = cudaMalloc(&p.fwd_out, out_bytes);
+      if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaMalloc(forward output)");
+    }
+    cudaError_t ce = cudaMemcpyAsync(p.x_in, x, (size_t)batch * img * 4,
+                                     x_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaMemcpyAsync(x)");
+    p.fwd_calls += 1;
+    if (p.graph == nullptr && p.fwd_calls >= 2) {
+      // the first call ran eagerly (it also configured every kernel's attributes); capture this one
+      const int64_t before = e->launches;
+      cudaGraph_t g = nullptr;
+      ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+      if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaStreamBeginCapture");
+      rc = run_network(e, batch, kEpiSoftmaxNCHW, p.fwd_out, 0, batch, h);
+      ce = cudaStreamEndCapture(e->stream, &g);
+      p.graph_launches = (int)(e->launches - before);
+      e->launches = before;
+      if (rc != IU_OK) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+      }
+      if (ce == cudaSuccess) ce = cudaGraphInstantiate(&p.graph, g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (ce != cudaSuccess) {
+        p.graph = nullptr;
+        return e->cuda_fail(ce, "capture of the forward graph");
+      }
+    }
+    if (p.graph) {
+      ce = cudaGraphLaunch(p.graph, e->stream);
+      if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaGraphLaunch");
+      e->launches += p.graph_launches;
+    } else {
+      rc = run_network(e, batch, kEpiSoftmaxNCHW, p.fwd_out, 0, batch, h);
+      if (rc != IU_OK) return rc;
+    }
+    ce = cudaMemcpyAsync(probs, p.fwd_out, out_bytes, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                         e->stream);
+    if (ce != cudaSuccess) return e->cuda_fail(ce, "copy probabilities");
+    if (!out_dev) {
+      IU_CUDA(e, cudaStreamSynchronize(e->stream));
+      return IU_OK;
+    }
+    return finish(e, flags);
+  }
   float* stage = nullptr;
   if (!out_dev) {
     rc = scratch_get(e, (size_t)batch * c * img * 4, (void**)&stage);
@@ -1078,7 +1274,8 @@ int iu_engine_forward(iu_engine* e, const float* x, int batch, int h, int w, flo
 int iu_engine_gather_slices(iu_engine* e, const void* volume_dev, int dtype, int n, int axis, int start, int count,
                             float* out_dev, unsigned flags) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!volume_dev || !out_dev || n < 16 || n % 16 || axis < 0 || axis > 2 || start < 0 || count < 1 ||
       start + count > n || (dtype != IU_DTYPE_U8 && dtype != IU_DTYPE_F32))
     return e->fail(IU_ERR_INVALID, "gather_slices: bad arguments");
@@ -1089,13 +1286,56 @@ int iu_engine_gather_slices(iu_engine* e, const void* volume_dev, int dtype, int
   return finish(e, flags);
 }
 
-// `plan_batch` > 0: run on the activation plan of that batch size even if `slice_count` is smaller (a partial batch),
-// so that a caller which interleaves short and long slice ranges does not re-plan (free + allocate) in between.
+// Slices from any strided source (device): element (slice i, row r, col c) = base[i*ss + r*sr + c*sc].
+// `plan_batch` > 0: run on the activation plan of that batch size even if `count` is smaller (a partial batch), so that
+// a caller which interleaves short and long slice ranges does not re-plan in between.
+static int predict_slices_impl(iu_engine* e, const void* base_dev, int dtype, int count, int h, int w, long long ss,
+                               long long sr, long long sc, float* probs_dev, int slice_offset, int slice_total,
+                               int row_block, unsigned flags, int plan_batch) {
+  const size_t esz = dtype == IU_DTYPE_F32 ? 4 : 1;
+  const int bs = plan_batch > 0 ? plan_batch : auto_batch(e, h, w, count);
+  int rc = ensure_plan(e, bs, h, w);
+  for (int s = 0; rc == IU_OK && s < count; s += bs) {
+    const int b = std::min(bs, count - s);
+    prof_begin(e, IU_PROF_GATHER);
+    cudaError_t ce = launch_gather_strided(static_cast<const char*>(base_dev) + (size_t)s * ss * esz,
+                                           dtype == IU_DTYPE_F32, b, h, w, ss, sr, sc, e->plan.x_in, e->stream);
+    prof_end(e);
+    if (ce != cudaSuccess) {
+      rc = e->cuda_fail(ce, "launch gather_slices");
+      break;
+    }
+    e->launches += 1;
+    rc = run_network(e, b, kEpiSoftmaxNHWC, probs_dev, slice_offset + s, slice_total, row_block);
+  }
+  if (rc != IU_OK) return rc;
+  return finish(e, flags);
+}
+
+int iu_engine_predict_slices(iu_engine* e, const void* base_dev, int dtype, int count, int h, int w,
+                             int64_t stride_slice, int64_t stride_row, int64_t stride_col, float* probs_dev,
+                             int slice_offset, int slice_total, int row_block, unsigned flags) {
+  int rc;
+  DeviceGuard guard;
+  if (!check_engine(e, true, &rc, &guard)) return rc;
+  if (!base_dev || !probs_dev || count < 1 || (dtype != IU_DTYPE_U8 && dtype != IU_DTYPE_F32) || stride_slice < 0 ||
+      stride_row < 0 || stride_col < 0 || row_block < 1 || slice_offset < 0 || slice_offset + count > slice_total)
+    return e->fail(IU_ERR_INVALID, "predict_slices: bad arguments");
+  if (h < 32 || w < 32 || h % 32 || w % 32)
+    return e->fail(IU_ERR_INVALID, "Wrong input shape height=" + std::to_string(h) + ", width=" + std::to_string(w) +
+                                       ". Expected image height and width divisible by 32.");
+  if (h % row_block) return e->fail(IU_ERR_INVALID, "predict_slices: row_block must divide the image height");
+  if (!is_device_ptr(base_dev)) return e->fail(IU_ERR_INVALID, "predict_slices: the slice source must be device memory");
+  return predict_slices_impl(e, base_dev, dtype, count, h, w, stride_slice, stride_row, stride_col, probs_dev,
+                             slice_offset, slice_total, row_block, flags, 0);
+}
+
 static int predict_axis_impl(iu_engine* e, const void* volume, int dtype, int n, int axis, int slice_begin,
                              int slice_count, float* probs_dev, int slice_offset, int slice_total, int row_block,
                              unsigned flags, int plan_batch) {
   int rc;
-  if (!check_engine(e, true, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, true, &rc, &guard)) return rc;
   if (!volume || !probs_dev || n < 32 || n % 32 || axis < 0 || axis > 2 || slice_begin < 0 || slice_count < 1 ||
       slice_begin + slice_count > n || (dtype != IU_DTYPE_U8 && dtype != IU_DTYPE_F32) || row_block < 1 ||
       n % row_block || slice_offset < 0 || slice_offset + slice_count > slice_total)
@@ -1113,27 +1353,17 @@ static int predict_axis_impl(iu_engine* e, const void* volume, int dtype, int n,
     }
     vol_dev = staged;
   }
-  const int bs = plan_batch > 0 ? plan_batch : auto_batch(e, n, n, slice_count);
-  rc = ensure_plan(e, bs, n, n);
-  for (int s = 0; rc == IU_OK && s < slice_count; s += bs) {
-    const int b = std::min(bs, slice_count - s);
-    prof_begin(e, IU_PROF_GATHER);
-    cudaError_t ce =
-        launch_gather_slices(vol_dev, dtype == IU_DTYPE_F32, n, axis, slice_begin + s, b, e->plan.x_in, e->stream);
-    prof_end(e);
-    if (ce != cudaSuccess) {
-      rc = e->cuda_fail(ce, "launch gather_slices");
-      break;
-    }
-    e->launches += 1;
-    rc = run_network(e, b, kEpiSoftmaxNHWC, probs_dev, slice_offset + s, slice_total, row_block);
-  }
+  // volume [z][y][x]: a slice along axis a is image (y,x) | (z,x) | (z,y)
+  const long long nn = (long long)n * n;
+  const long long ss = axis == 0 ? nn : (axis == 1 ? n : 1), sr = axis == 0 ? n : nn, sc = axis == 2 ? n : 1;
+  rc = predict_slices_impl(e, static_cast<const char*>(vol_dev) + (size_t)slice_begin * ss * esz, dtype, slice_count, n,
+                           n, ss, sr, sc, probs_dev, slice_offset, slice_total, row_block,
+                           staged ? (flags | IU_FLAG_ASYNC) : flags, plan_batch);
   if (staged) {
     cudaStreamSynchronize(e->stream);
     scratch_put(e, staged);
   }
-  if (rc != IU_OK) return rc;
-  return finish(e, flags);
+  return rc;
 }
 
 int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, int axis, int slice_begin,
@@ -1147,7 +1377,8 @@ int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float
                      int n, int t, int z0, int num_classes, const float* g1d_host, float gmax, float lo,
                      uint8_t* out_u8, uint8_t* out_labels, float* out_mean, unsigned flags) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!order || n_axes < 1 || n_axes > 3 || n < 1 || t < 1 || z0 < 0 || z0 + t > n || num_classes < 1 ||
       num_classes > 10)
     return e->fail(IU_ERR_INVALID, "reduce: bad arguments");
@@ -1200,7 +1431,8 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
                              const float* g1d_host, float gmax, float lo, uint8_t* out_u8, uint8_t* out_labels,
                              float* out_mean, unsigned flags) {
   int rc;
-  if (!check_engine(e, true, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, true, &rc, &guard)) return rc;
   if (!volume || !axes || n_axes < 1 || n_axes > 3 || n < 32 || n % 32 ||
       (dtype != IU_DTYPE_U8 && dtype != IU_DTYPE_F32))
     return e->fail(IU_ERR_INVALID, "predict_volume: bad arguments");
@@ -1320,6 +1552,7 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
     for (int k = 0; k < kParts; ++k)
       if (done[k]) cudaEventDestroy(done[k]);
     for (void* q : held) scratch_put(e, q);
+    scratch_trim(e);
     if (rc != IU_OK) return rc;
     if (ce != cudaSuccess) return e->cuda_fail(ce, "predict_volume (pipelined results)");
     if (ce2 != cudaSuccess) return e->cuda_fail(ce2, "predict_volume");
@@ -1343,6 +1576,7 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
   if (ce != cudaSuccess) { release(); return e->cuda_fail(ce, "copy results to host"); }
   ce = cudaStreamSynchronize(e->stream);
   for (void* q : held) scratch_put(e, q);
+  scratch_trim(e);
   if (ce != cudaSuccess) return e->cuda_fail(ce, "predict_volume");
   return IU_OK;
 }
@@ -1350,7 +1584,8 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
 int iu_engine_extract_block(iu_engine* e, const uint8_t* volume_dev, int d, int h, int w, int i0, int j0, int k0, int s,
                             uint8_t* out_dev, unsigned flags) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!volume_dev || !out_dev || d < 1 || h < 1 || w < 1 || s < 1)
     return e->fail(IU_ERR_INVALID, "extract_block: bad arguments");
   cudaError_t ce = launch_extract_block(volume_dev, d, h, w, i0, j0, k0, s, out_dev, e->stream);
@@ -1363,7 +1598,8 @@ int iu_engine_predict_tiled(iu_engine* e, const uint8_t* volume, int d, int h, i
                             const int* origins, const int* axes, int n_axes, const float* g1d_host, float gmax,
                             float lo, uint8_t* out_u8, uint8_t* out_labels, unsigned flags) {
   int rc;
-  if (!check_engine(e, true, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, true, &rc, &guard)) return rc;
   if (!volume || !origins || !axes || !g1d_host || n_blocks < 1 || d < 1 || h < 1 || w < 1 || s < 32 || s % 32 ||
       n_axes < 1 || n_axes > 3 || (!out_u8 && !out_labels))
     return e->fail(IU_ERR_INVALID, "predict_tiled: bad arguments (block edge must be a multiple of 32)");
@@ -1464,6 +1700,7 @@ int iu_engine_predict_tiled(iu_engine* e, const uint8_t* volume, int d, int h, i
   (void)flags;  // host outputs and the scratch hand-back need the stream drained: always synchronous
   cudaError_t ce = cudaStreamSynchronize(e->stream);
   for (void* q : held) scratch_put(e, q);
+  scratch_trim(e);
   if (ce != cudaSuccess) return e->cuda_fail(ce, "predict_tiled");
   return IU_OK;
 }
@@ -1472,7 +1709,8 @@ int iu_engine_blend_block(iu_engine* e, const float* p0, const float* p1, const 
                           int s, int num_classes, const float* g1d_host, float gmax, float lo, float* pred_dev,
                           float* weight_dev, int d, int h, int w, const int* origin, unsigned flags) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!order || n_axes < 1 || n_axes > 3 || s < 1 || num_classes < 1 || num_classes > 10 || !g1d_host || !pred_dev ||
       !weight_dev || !origin)
     return e->fail(IU_ERR_INVALID, "blend_block: bad arguments");
@@ -1518,7 +1756,8 @@ int iu_engine_blend_block(iu_engine* e, const float* p0, const float* p1, const 
 int iu_engine_finalise(iu_engine* e, const float* pred_dev, const float* weight_dev, int64_t voxels, int num_classes,
                        uint8_t* out_u8_dev, uint8_t* out_labels_dev, unsigned flags) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!pred_dev || !weight_dev || voxels < 1 || num_classes < 1 || (!out_u8_dev && !out_labels_dev))
     return e->fail(IU_ERR_INVALID, "finalise: bad arguments");
   cudaError_t ce = launch_finalise(pred_dev, weight_dev, (size_t)voxels, num_classes, out_u8_dev, out_labels_dev, e->stream);
@@ -1530,7 +1769,8 @@ int iu_engine_finalise(iu_engine* e, const float* pred_dev, const float* weight_
 int iu_engine_to_chunks(iu_engine* e, const void* volume_dev, int d, int h, int w, int elem, int chunk_elem, int cz,
                         int cy, int cx, void* staged_dev, unsigned flags) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!volume_dev || !staged_dev) return e->fail(IU_ERR_INVALID, "to_chunks: null buffer");
   cudaError_t ce = launch_chunk_layout((const uint8_t*)volume_dev, (uint8_t*)staged_dev, d, h, w, elem, chunk_elem, cz, cy, cx, true,
                                        e->stream);
@@ -1542,7 +1782,8 @@ int iu_engine_to_chunks(iu_engine* e, const void* volume_dev, int d, int h, int 
 int iu_engine_from_chunks(iu_engine* e, const void* staged_dev, int d, int h, int w, int elem, int chunk_elem, int cz,
                           int cy, int cx, void* volume_dev, unsigned flags) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!volume_dev || !staged_dev) return e->fail(IU_ERR_INVALID, "from_chunks: null buffer");
   cudaError_t ce = launch_chunk_layout((const uint8_t*)staged_dev, (uint8_t*)volume_dev, d, h, w, elem, chunk_elem, cz,
                                        cy, cx, false, e->stream);
@@ -1554,7 +1795,8 @@ int iu_engine_from_chunks(iu_engine* e, const void* staged_dev, int d, int h, in
 int iu_engine_zoom_nearest(iu_engine* e, const void* src_dev, const int* src_dims, void* dst_dev, const int* dst_dims,
                            const int* t0, const int* t1, const int* t2, const int* t3, int item_bytes, unsigned flags) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!src_dev || !src_dims || !dst_dims || !t0 || !t1 || !t2 || !t3)
     return e->fail(IU_ERR_INVALID, "zoom_nearest: null argument");
   size_t n = 0, total = 1;
@@ -1599,7 +1841,8 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
                         int w_in, int ksize, int stride, const float* weight, const float* bias, int cout,
                         const void* residual, int relu, int up2x, void* out) {
   int rc;
-  if (!check_engine(e, false, &rc)) return rc;
+  DeviceGuard guard;
+  if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!src0 || !weight || !bias || !out || batch < 1 || (ksize != 1 && ksize != 3) || (stride != 1 && stride != 2) ||
       cin0 < 16 || cout % 16 || (src1 == nullptr) != (cin1 == 0) || batch % 8)
     return e->fail(IU_ERR_INVALID, "conv_test: bad arguments (batch must be a multiple of 8)");

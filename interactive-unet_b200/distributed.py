@@ -5,42 +5,64 @@ one whole block per GPU, results gathered on the host).  Here the partition foll
 section 8e: the unit of work is a 2-D slice, so every rank runs N/G slices per axis, and only the
 cross-axis average couples ranks.
 
-    rank r owns the z-slab  z in [r*T, (r+1)*T),  T = N / G   (its part of the OUTPUT)
+    rank r owns the z-slab  z in [r*T, (r+1)*T),  T = N / G   (its part of the INPUT and of the OUTPUT)
     axis 0 (slices indexed by z): rank r runs its own slab's slices -> no exchange
     axis 1 (indexed by y, image (z,x)) and axis 2 (indexed by x, image (z,y)): rank r runs the slices
-        y (resp. x) in [r*T, (r+1)*T); each image row is a z, so the engine's head epilogue writes the
-        probabilities destination-major  [dest rank h][slice][z in slab h][col][C]  (row_block = T) and ONE
-        all-to-all per off-slab axis delivers to rank h exactly its slab: [y or x][z local][col][C].
+        y (resp. x) in [r*T, (r+1)*T).
+        input : each rank holds (and, end to end, uploads) only its slab; the two uint8 strips
+                vol[:, rT:(r+1)T, :] and vol[:, :, rT:(r+1)T] it needs are assembled by one uint8 all-to-all
+                each (N^3/G bytes per rank) and read in place through the engine's strided slice source;
+        output: each image row is a z, so the engine's head epilogue writes the probabilities
+                destination-major  [dest rank h][slice][z in slab h][col][C]  (row_block = T); they travel
+                in chunks of one network pass (`Engine.auto_batch` slices): the all-to-all of chunk k runs
+                on NCCL's stream while the network computes chunk k+1, and lands directly in rank h's
+                [y or x][z local][col][C] buffer.  No whole-axis send / receive staging exists, which is
+                what lets 2048^3 fit on two GPUs.
     then K4 (reduce / blend / quantise / argmax) runs locally on each slab.
 
 The per-voxel arithmetic and its order (axis order of `axes`) are identical to the single-GPU path, so
-the sharded result is bit-identical to it.  The exchange is `torch.distributed.all_to_all_single`
-(NCCL over NVLink on GPUs; gloo in the CPU tests), T*T*N*C*4 bytes per ordered pair per axis.
+the sharded result is bit-identical to it.  Streams are ordered with events (engine stream <-> torch's
+current stream <-> NCCL's stream); the host never waits inside the loop.
 """
 import torch
 import torch.distributed as dist
 
 
-def _all_to_all(recv, send, group):
-    """all_to_all_single, with a send/recv fallback for backends that lack it."""
-    try:
-        dist.all_to_all_single(recv, send, group=group)
-        return
-    except (RuntimeError, NotImplementedError):
-        pass
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    sends = list(send.chunk(world))
-    recvs = list(recv.chunk(world))
-    recvs[rank].copy_(sends[rank])
+_tag = [0]
+
+
+def _exchange(outs, ins, group, rank, world):
+    """All-to-all over tensor lists: `ins[h]` goes to rank h, `outs[g]` is filled by rank g.  Returns the pending
+    work handles (NCCL: one grouped send/recv; other backends: isend / irecv pairs, one tag per exchange so that
+    several exchanges can be in flight between the same pair of ranks)."""
+    _tag[0] = (_tag[0] + 1) % 30000
+    if world == 1:
+        outs[0].copy_(ins[0])
+        return []
+    if dist.get_backend(group) == "nccl":
+        return [dist.all_to_all(outs, ins, group=group, async_op=True)]
+    outs[rank].copy_(ins[rank])
     ops = []
     for peer in range(world):
         if peer == rank:
             continue
-        ops.append(dist.P2POp(dist.isend, sends[peer], dist.get_global_rank(group, peer) if group else peer, group))
-        ops.append(dist.P2POp(dist.irecv, recvs[peer], dist.get_global_rank(group, peer) if group else peer, group))
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
+        gp = dist.get_global_rank(group, peer) if group is not None else peer
+        ops.append(dist.P2POp(dist.isend, ins[peer], gp, group, _tag[0]))
+        ops.append(dist.P2POp(dist.irecv, outs[peer], gp, group, _tag[0]))
+    return list(dist.batch_isend_irecv(ops))
+
+
+def _wait(works):
+    """Wait for the handles and drop them: a gloo send / recv handle must not be waited on twice."""
+    while works:
+        works.pop().wait()
+
+
+def _order(engine, name):
+    """Stream-ordering hooks of the native engine (`wait_torch`, `torch_wait`); CPU test doubles have none."""
+    fn = getattr(engine, name, None)
+    if fn is not None:
+        fn()
 
 
 def volumes_for_rank(files, group=None):
@@ -53,36 +75,104 @@ def volumes_for_rank(files, group=None):
     return files[dist.get_rank(group)::dist.get_world_size(group)]
 
 
-def predict_volume_sharded(engine, volume, axes=(0, 1, 2), window=None, want_u8=True, want_labels=True,
-                           want_mean=False, group=None):
-    """Predict this rank's z-slab of a replicated cubic volume.
+def exchange_strips(slab, axes, group=None):
+    """From every rank's z-slab `[T,N,N]` (uint8 / fp32 device tensor) assemble the strips this rank predicts along the
+    off-slab axes: {1: vol[:, rT:(r+1)T, :] as `[N,T,N]`, 2: vol[:, :, rT:(r+1)T] as `[N,N,T]`}."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    t, n = int(slab.shape[0]), int(slab.shape[1])
+    strips, works, keep = {}, [], []
+    if 1 in axes:
+        send = slab.view(t, world, t, n).permute(1, 0, 2, 3).contiguous()            # [dest][z local][y local][x]
+        recv = torch.empty((world, t, t, n), dtype=slab.dtype, device=slab.device)     # [src][z local][y local][x]
+        works += _exchange(list(recv.unbind(0)), list(send.unbind(0)), group, rank, world)
+        strips[1] = recv.view(n, t, n)
+        keep.append(send)
+    if 2 in axes:
+        send = slab.view(t, n, world, t).permute(2, 0, 1, 3).contiguous()            # [dest][z local][y][x local]
+        recv = torch.empty((world, t, n, t), dtype=slab.dtype, device=slab.device)
+        works += _exchange(list(recv.unbind(0)), list(send.unbind(0)), group, rank, world)
+        strips[2] = recv.view(n, n, t)
+        keep.append(send)
+    _wait(works)
+    return strips
 
-    engine : an `Engine` (or any object with `predict_axis`, `reduce`, `num_classes`, `device`)
-    volume : the WHOLE uint8 / fp32 volume `[N,N,N]`, identical on every rank (device tensor or numpy)
+
+def predict_volume_sharded(engine, volume=None, axes=(0, 1, 2), window=None, want_u8=True, want_labels=True,
+                           want_mean=False, group=None, slab=None):
+    """Predict this rank's z-slab of a cubic volume of edge N.
+
+    engine : an `Engine` (or any object with `predict_slices`, `reduce`, `auto_batch`, `num_classes`, `device`)
+    slab   : this rank's part `volume[rT:(r+1)T]` as a `[T,N,N]` device tensor -- the sharded input: strips for the
+             off-slab axes are exchanged between the ranks (uint8 all-to-all);
+    volume : alternatively the WHOLE volume `[N,N,N]`, identical on every rank (device tensor or numpy): every rank
+             reads its slab and strips out of it in place, no input exchange.
     Returns dict(z0, t, u8=[T,N,N,C] uint8, labels=[T,N,N] uint8, mean=[T,N,N,C] fp32) of device tensors.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    n = volume.shape[0]
-    if n % world:
-        raise ValueError(f"volume edge {n} is not divisible by the number of ranks {world}")
-    t = n // world
-    z0 = rank * t
-    c = engine.num_classes
     dev = engine.device
-    probs = {}
-    for axis in axes:
+    c = engine.num_classes
+    axes = [int(a) for a in axes]
+    if (volume is None) == (slab is None):
+        raise ValueError("give either the replicated `volume` or this rank's `slab`")
+    if slab is not None:
+        slab = torch.as_tensor(slab).to(dev).contiguous()
+        t, n = int(slab.shape[0]), int(slab.shape[1])
+        if tuple(slab.shape) != (t, n, n) or t * world != n:
+            raise ValueError(f"slab shape {tuple(slab.shape)} is not [N/{world}, N, N]")
+        strips = exchange_strips(slab, axes, group)
+        sources = {0: (slab, 0, (n * n, n, 1))}
+        if 1 in strips:
+            sources[1] = (strips[1], 0, (n, t * n, 1))           # [z][y local][x]: slice y, image (z, x)
+        if 2 in strips:
+            sources[2] = (strips[2], 0, (1, n * t, t))           # [z][y][x local]: slice x, image (z, y)
+    else:
+        volume = torch.as_tensor(volume).to(dev).contiguous()
+        n = int(volume.shape[0])
+        if tuple(volume.shape) != (n, n, n):
+            raise ValueError("the sharded path predicts cubic volumes (predict.py:81)")
+        if n % world:
+            raise ValueError(f"volume edge {n} is not divisible by the number of ranks {world}")
+        t = n // world
+        z0 = rank * t
+        sources = {0: (volume, z0 * n * n, (n * n, n, 1)), 1: (volume, z0 * n, (n, n * n, 1)),
+                   2: (volume, z0, (1, n * n, n))}
+    z0 = rank * t
+
+    probs, in_flight, keep = {}, [], []
+    _order(engine, "wait_torch")                  # uploads / strip exchange queued on torch's stream come first
+    # the off-slab axes run first so that their last exchanges overlap with axis 0's network passes; the order in
+    # which axes are COMPUTED does not enter the arithmetic (K4 adds the buffers in the caller's order)
+    for axis in [a for a in axes if a != 0] + [a for a in axes if a == 0]:
+        src, off, strides = sources[axis]
         if axis == 0:
-            probs[0] = engine.predict_axis(volume, 0, slice_begin=z0, slice_count=t)
-        else:
-            send = torch.empty((world, t, t, n, c), dtype=torch.float32, device=dev)
-            engine.predict_axis(volume, axis, slice_begin=z0, slice_count=t, out=send, slice_total=t, row_block=t)
-            recv = torch.empty_like(send)
-            if world > 1:
-                _all_to_all(recv.view(-1), send.view(-1), group)
-            else:
-                recv = send
-            probs[axis] = recv           # [source rank g][slice in strip g][z local][col][C] == [y|x][z local][col][C]
+            probs[0] = torch.empty((t, n, n, c), dtype=torch.float32, device=dev)
+            engine.predict_slices(src, off, t, n, n, strides, probs[0], asynchronous=True, sync=False)
+            continue
+        dst = torch.empty((n, t, n, c), dtype=torch.float32, device=dev)     # [y | x][z local][col][C]
+        probs[axis] = dst
+        if world == 1:
+            engine.predict_slices(src, off, t, n, n, strides, dst, row_block=t, asynchronous=True, sync=False)
+            continue
+        chunk = max(1, min(t, int(engine.auto_batch(n, n, t))))
+        send = [torch.empty((world * chunk * t * n * c,), dtype=torch.float32, device=dev) for _ in range(2)]
+        keep.append(send)
+        pending = [None, None]
+        for k, s0 in enumerate(range(0, t, chunk)):
+            cnt = min(chunk, t - s0)
+            if pending[k % 2] is not None:        # this buffer's previous exchange must have read it
+                _wait(pending[k % 2])
+                _order(engine, "wait_torch")
+            buf = send[k % 2][:world * cnt * t * n * c].view(world, cnt, t, n, c)
+            engine.predict_slices(src, off + s0 * strides[0], cnt, n, n, strides, buf, slice_offset=0, slice_total=cnt,
+                                  row_block=t, asynchronous=True, sync=False)
+            _order(engine, "torch_wait")          # the collective is queued behind this chunk's head kernel
+            outs = [dst[g * t + s0:g * t + s0 + cnt] for g in range(world)]
+            pending[k % 2] = _exchange(outs, list(buf.unbind(0)), group, rank, world)
+            in_flight.append(pending[k % 2])
+    for w in in_flight:
+        _wait(w)
+    _order(engine, "wait_torch")
     out = dict(z0=z0, t=t)
     out["u8"] = torch.empty((t, n, n, c), dtype=torch.uint8, device=dev) if want_u8 else None
     out["labels"] = torch.empty((t, n, n), dtype=torch.uint8, device=dev) if want_labels else None

@@ -55,6 +55,26 @@ def _dtype_code(a):
     raise TypeError(f"volume dtype must be uint8 or float32, got {dt}")
 
 
+class _BatchLimit:
+    def __init__(self, engine, max_batch):
+        self.engine, self.max_batch = engine, max_batch
+
+    def __enter__(self):
+        self.engine._lock.acquire()
+        try:
+            self.engine.set_max_batch(self.max_batch or 0)
+        except BaseException:
+            self.engine._lock.release()
+            raise
+        return self.engine
+
+    def __exit__(self, *exc):
+        try:
+            self.engine.set_max_batch(0)
+        finally:
+            self.engine._lock.release()
+
+
 class Engine:
     """One native engine bound to one CUDA device.  Calls are serialised with a lock because
     the reference calls the prediction entry points from worker threads (`app.py:737-739`)."""
@@ -122,6 +142,38 @@ class Engine:
 
     def set_max_batch(self, max_batch):
         self._check(self._lib.iu_engine_set_max_batch(self._h, int(max_batch or 0)))
+
+    def limit_batch(self, max_batch):
+        """Context manager: hold the engine for the caller's thread with `max_batch` as the cap on slices per network
+        pass, and lift the cap on exit.  The app calls `predict_slice` and `predict_volumes` from different worker
+        threads on one cached model (`app.py:737-739`); set / predict / reset must not interleave between them."""
+        return _BatchLimit(self, max_batch)
+
+    def auto_batch(self, h, w, count):
+        """Slices per network pass the engine would choose for `count` slices of h x w."""
+        return int(self._lib.iu_engine_auto_batch(self._h, int(h), int(w), int(count)))
+
+    def release_workspace(self):
+        """Give activation plans and pooled scratch back to the driver (weights stay)."""
+        with self._lock:
+            self._check(self._lib.iu_engine_release_workspace(self._h))
+
+    def held_bytes(self):
+        return int(self._lib.iu_engine_held_bytes(self._h))
+
+    # ---- stream ordering against torch (no host synchronisation)
+    def _ext_stream(self):
+        if getattr(self, "_ext", None) is None:
+            self._ext = torch.cuda.ExternalStream(self.stream_handle(), device=self.device)
+        return self._ext
+
+    def wait_torch(self):
+        """The engine's stream waits for everything queued so far on torch's current stream."""
+        self._ext_stream().wait_event(torch.cuda.current_stream(self.device).record_event())
+
+    def torch_wait(self):
+        """torch's current stream waits for everything queued so far on the engine's stream."""
+        torch.cuda.current_stream(self.device).wait_event(self._ext_stream().record_event())
 
     def workspace_bytes(self, batch, h, w):
         return int(self._lib.iu_engine_workspace_bytes(self._h, batch, h, w))
@@ -201,6 +253,23 @@ class Engine:
             self._check(self._lib.iu_engine_predict_axis(
                 self._h, vp, _dtype_code(volume), n, int(axis), int(slice_begin), int(slice_count),
                 ctypes.c_void_p(out.data_ptr()), int(slice_offset), int(slice_total), int(row_block),
+                _lib.FLAG_ASYNC if asynchronous else 0))
+        return out
+
+    def predict_slices(self, source, offset, count, h, w, strides, out, slice_offset=0, slice_total=None,
+                       row_block=None, asynchronous=False, sync=True):
+        """Probabilities of `count` slices of h x w read from a CUDA tensor through element strides:
+        pixel (slice i, row r, col c) = source.view(-1)[offset + i*strides[0] + r*strides[1] + c*strides[2]].
+        `sync=False`: the caller orders the streams itself (`wait_torch` / `torch_wait`)."""
+        slice_total = count if slice_total is None else slice_total
+        row_block = h if row_block is None else row_block
+        base = ctypes.c_void_p(source.data_ptr() + int(offset) * source.element_size())
+        with self._lock:
+            if sync:
+                self._sync_torch(source, out)
+            self._check(self._lib.iu_engine_predict_slices(
+                self._h, base, _dtype_code(source), int(count), int(h), int(w), int(strides[0]), int(strides[1]),
+                int(strides[2]), ctypes.c_void_p(out.data_ptr()), int(slice_offset), int(slice_total), int(row_block),
                 _lib.FLAG_ASYNC if asynchronous else 0))
         return out
 
