@@ -34,9 +34,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_VOXEL_AXIS = {2: 235.62e3, 4: 236.19e3}          # BASELINE.md section 3 (dense conv FLOPs per pixel per axis)
-WEAK_EDGES = {1: 512, 2: 640, 4: 800, 8: 1024}             # ~512^3 voxels per GPU (edge % 32 == 0, edge % G == 0)
+STEM_FLOP_PER_VOXEL_AXIS = 2 * 49 * 64 / 4.0               # the 7x7/s2 stem's share of the figure above (its own kernel class)
+# N = 1 is BASELINE.json configs[1] (512^3 on one B200); N = 2 / 4 / 8 run configs[2]'s 1024^3 volume z-slab sharded
+# (512 / 256 / 128 slices of 1024^2 per GPU and axis).  The per-voxel work is the same at every N, so value(N) / N is
+# comparable across the row; the edges between 512 and 1024 that would keep the voxel count per GPU exactly constant
+# (640, 800) have feature maps that tile badly (20x20, 25x25) and would measure that instead of the sharding.
+WEAK_EDGES = {1: 512, 2: 1024, 4: 1024, 8: 1024}
 AXES = (0, 1, 2)
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 228.7e6
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_conv_dram.json")   # written by tools/ncu_dram.py from an ncu capture
 
 
 ENCODER = "resnet34"                                       # --encoder
@@ -138,6 +143,87 @@ def noise_volume(n, seed):
     return np.random.default_rng(seed).integers(0, 256, (n, n, n), dtype=np.uint8)
 
 
+def noise_slab(n, z0, t, seed):
+    """Planes [z0, z0 + t) of a uint8 noise volume that is the same whatever the number of ranks (one generator per
+    plane): every rank makes only its own slab."""
+    out = np.empty((t, n, n), dtype=np.uint8)
+    for i in range(t):
+        out[i] = np.random.default_rng([seed, z0 + i]).integers(0, 256, (n, n), dtype=np.uint8)
+    return out
+
+
+def conv_dram_traffic(edge, world):
+    """`roofline.traffic`: DRAM bytes per conv launch from the committed ncu capture (tools/ncu_dram.py), or None when
+    no capture of this workload is on file."""
+    try:
+        rec = json.load(open(NCU_TRAFFIC_FILE))
+    except (OSError, ValueError):
+        return None, None
+    if rec.get("edge") != edge or world != 1:
+        return None, rec.get("source")
+    return rec.get("dram_bytes_per_launch"), rec.get("source")
+
+
+def torch_gpu_baseline(model, dev, edge, classes, slices=32, repeats=3):
+    """The same network in PyTorch eager / cuDNN on this GPU (fp16, channels_last, BatchNorm in eval mode; network only:
+    no gather, accumulate or tail), as voxels/s-equivalent of a 3-axis prediction: context for `value`, timed with CUDA
+    events on torch's stream after a warm-up."""
+    net = model.model
+    half = torch.empty(0)
+    try:
+        import copy
+        half = copy.deepcopy(net).to(dev).half().to(memory_format=torch.channels_last).eval()
+        x = torch.rand(slices, 1, edge, edge, device=dev).half().contiguous(memory_format=torch.channels_last)
+        with torch.inference_mode():
+            for _ in range(2):
+                torch.softmax(half(x), 1)
+            torch.cuda.synchronize(dev)
+            best = None
+            for _ in range(repeats):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.softmax(half(x), 1)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+        return {"value": slices * edge * edge / 3.0 / (best * 1e-3), "unit": "voxels/s",
+                "kind": "PyTorch eager + cuDNN, fp16 channels_last, network only (no gather / reduce / tail)",
+                "sample": f"{slices} slices of {edge}x{edge} ({best:.1f} ms), best of {repeats}"}
+    except Exception as exc:            # context only: never fail the bench over it
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    finally:
+        del half
+        torch.cuda.empty_cache()
+
+
+def cpu_config0(threads, repeats=3):
+    """BASELINE.json configs[0], as specified: the reference path (port of predict.py:79-112 + the restated fp32
+    network) on a synthetic 128^3 uint8 volume, 2 classes, axes=[0], batch 128, on the host cores: one warm-up, best of
+    `repeats`."""
+    from oracle import predict_port as pp
+    from oracle.smp_unet_resnet34 import RefUNet
+    torch.set_num_threads(threads)
+    net = RefUNet(1, 2, "resnet34")
+    net.load_state_dict(synthetic_model(2, "resnet34").state_dict())
+    net.eval()
+    vol = np.random.default_rng(0).integers(0, 256, (128, 128, 128), dtype=np.uint8)
+
+    def fwd(x):
+        with torch.inference_mode():
+            return net(torch.from_numpy(x)).numpy()
+    best = None
+    for i in range(repeats + 1):
+        t0 = time.perf_counter()
+        pp.predict_block(fwd, pp.normalise_u8(vol), 2, 128, (0,))
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    return {"workload": "configs[0]: single-axis prediction of a synthetic 128^3 uint8 volume, 2 classes, CPU",
+            "value": 128 ** 3 / best, "unit": "voxels/s", "seconds": best, "cores": threads, "batch_size": 128,
+            "kind": "port"}
+
+
 # ------------------------------------------------------------------------------------------- CPU arm
 _CPU_SETUP = {}
 
@@ -185,7 +271,8 @@ def run_reference_arm(args, rank, world):
     vals = [cpu_reference_sample(edge, args.classes, spa, threads)[0] for _ in range(args.steps)]
     total = time.perf_counter() - t0
     value = float(np.mean(vals))
-    sample = f"{spa} slices of {edge}x{edge} per axis x 3 axes per step (of {edge} per axis), fp32, torch CPU"
+    sample = (f"{spa} slices of {edge}x{edge} per axis x 3 axes per step (of {edge} per axis): numpy port of predict.py "
+              f"+ restated fp32 network (oracle/), torch CPU, {threads} threads; ms_per_step is the SAMPLE's time")
     line = {
         "impl": "reference", "metric": "voxels/sec, full 3-axis volume prediction", "value": value, "unit": "voxels/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -197,6 +284,8 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_config0:
+        line["config0"] = cpu_config0(threads)
     print(json.dumps(line), flush=True)
 
 
@@ -219,7 +308,12 @@ def run_ours(args, rank, world, local_rank):
     eng = model.engine()
     window = iu.gaussian_window_1d(edge)
 
-    vol_host = torch.from_numpy(noise_volume(edge, 1)).pin_memory()
+    # one GPU: the whole volume; several: every rank makes, holds and uploads ONLY its z-slab (the strips it needs
+    # along the other two axes are exchanged between the GPUs, distributed.py)
+    if world == 1:
+        vol_host = torch.from_numpy(noise_volume(edge, 1)).pin_memory()
+    else:
+        vol_host = torch.from_numpy(noise_slab(edge, rank * t_slab, t_slab, 1)).pin_memory()
     vol_dev = vol_host.to(dev)
     stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
 
@@ -237,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
             eng.predict_volume(vol_dev, axes=AXES, window=window, out_u8=out_u8, out_labels=out_lab)
     else:
         def step():
-            return iud.predict_volume_sharded(eng, vol_dev, axes=AXES, window=window)
+            return iud.predict_volume_sharded(eng, slab=vol_dev, axes=AXES, window=window)
 
     for _ in range(args.warmup):
         step()
@@ -268,12 +362,8 @@ def run_ours(args, rank, world, local_rank):
         h_lab = torch.empty((t_slab, edge, edge), dtype=torch.uint8).pin_memory()
 
         def e2e_step():
-            v = vol_host.to(dev, non_blocking=True)
-            res = iud.predict_volume_sharded(eng, v, axes=AXES, window=window)
-            h_u8.copy_(res["u8"], non_blocking=True)
-            h_lab.copy_(res["labels"], non_blocking=True)
-            torch.cuda.synchronize(dev)
-        h2d, d2h = edge ** 3 * world, edge ** 3 * (classes + 1)       # volume replicated on every rank
+            iud.predict_slab_from_host(eng, vol_host, axes=AXES, window=window, out_u8=h_u8, out_labels=h_lab)
+        h2d, d2h = edge ** 3, edge ** 3 * (classes + 1)               # summed over the ranks: each moves its slab only
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -301,8 +391,15 @@ def run_ours(args, rank, world, local_rank):
     peaks = measured_peaks()
     value = voxels * args.steps / (dev_ms * 1e-3)
     conv_ms, conv_n = prof["conv"]
-    conv_flops = flops_per_voxel(classes, encoder=ENCODER) * voxels / world * prof_steps        # this rank's share
+    # the conv class is every tcgen05 3x3 / 1x1 conv and the head; the stem is its own kernel class, so its FLOPs are
+    # left out of this numerator (`network_tflops` below has every FLOP over every network kernel's time)
+    conv_fpv = flops_per_voxel(classes, encoder=ENCODER) - 3 * STEM_FLOP_PER_VOXEL_AXIS
+    conv_flops = conv_fpv * voxels / world * prof_steps                                        # this rank's share
     conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    net_ms = conv_ms + prof["stem"][0] + prof["pool"][0]
+    net_tflops = flops_per_voxel(classes, encoder=ENCODER) * voxels / world * prof_steps / (net_ms * 1e-3) / 1e12 \
+        if net_ms > 0 else 0.0
+    traffic, traffic_source = conv_dram_traffic(edge, world)
     gather_ms, gather_n = prof["gather"]
     reduce_ms, reduce_n = prof["reduce"]
     share = voxels / world * prof_steps
@@ -319,24 +416,28 @@ def run_ours(args, rank, world, local_rank):
                    "edge": edge, "classes": classes, "axes": list(AXES), "network": f"smp.Unet({ENCODER}), random init",
                    "storage": f"{args.precision} activations/weights, fp32 accumulate (TMEM), fp32 tail",
                    "l2": "inputs_exceed_l2 (per-step working set of several GB >> 126 MB L2; no explicit flush)",
-                   "slices_per_gpu_per_axis": t_slab},
+                   "slices_per_gpu_per_axis": t_slab,
+                   "input": "whole volume on the one GPU" if world == 1 else
+                            "each rank holds / uploads its z-slab; uint8 strips and fp32 partial probabilities of the "
+                            "off-slab axes exchanged with NCCL all-to-all"},
         "e2e": {"value": voxels * args.steps / (e2e_ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                 "api": "interactive_unet_b200.predict.predict_volume_array (pinned host buffers)" if world == 1
-                       else "interactive_unet_b200.distributed.predict_volume_sharded + pinned host copies"},
+                       else "interactive_unet_b200.distributed.predict_slab_from_host (pinned host buffers)"},
         "gpu_launches": int(launches),
         "algorithmic_tflops": flops_per_voxel(classes, encoder=ENCODER) * value / 1e12,
         "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM, all conv layers + head)", "bound": "tensor",
                      "achieved": conv_tflops, "peak": peaks["tc_tflops"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["tc_tflops"],
-                     # DRAM bytes per conv launch (read + write, mean over the 43 launches of one 74-slice pass at
-                     # 512^2) from the committed `ncu --set full` capture; activations only, weights are L2 resident
-                     "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH if (edge == 512 and world == 1) else None,
-                     "traffic_source": "profiles/r01_ncu_full_conv_pass_v12.txt (9.84 GB per 43-launch pass of 74 slices)",
+                     # DRAM bytes per conv launch (read + write) from the committed `ncu --set full` capture of this
+                     # workload (profiles/ncu_conv_dram.json, tools/ncu_dram.py); null when none is on file
+                     "traffic": traffic, "traffic_source": traffic_source,
                      "peak_source": peaks["source"],
-                     "flops_per_voxel": flops_per_voxel(classes, encoder=ENCODER), "launches": int(conv_n),
+                     "flops_per_voxel": conv_fpv, "launches": int(conv_n),
                      "kernel_ms_per_step": conv_ms / prof_steps,
-                     "share_of_step": conv_ms / total_prof_ms if total_prof_ms else None},
+                     "share_of_step": conv_ms / total_prof_ms if total_prof_ms else None,
+                     "network_tflops": net_tflops, "network_frac": net_tflops / peaks["tc_tflops"],
+                     "network_note": "all conv FLOPs incl. the stem over conv + stem + max-pool kernel time"},
         "roofline_hbm": {
             "gather": {"bound": "hbm", "achieved": gather_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": gather_gbs / peaks["hbm_gbs"], "bytes_per_voxel_per_axis": 5,
@@ -352,7 +453,12 @@ def run_ours(args, rank, world, local_rank):
         v, secs = cpu_reference_sample(edge, classes, args.cpu_slices, threads)
         line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.cpu_slices} slices of {edge}x{edge} per axis x 3 axes "
-                                          f"({secs:.1f} s), fp32 oracle network + port of predict.py, torch CPU"}
+                                          f"({secs:.1f} s): numpy port of predict.py (not the verbatim module) + "
+                                          f"restated fp32 network (oracle/), torch CPU"}
+        if not args.no_config0:
+            line["cpu_baseline"]["config0"] = cpu_config0(threads)
+    if world == 1 and not args.no_gpu_baseline:
+        line["gpu_baseline"] = torch_gpu_baseline(model, dev, edge, classes)
     print(json.dumps(line), flush=True)
 
 
@@ -370,6 +476,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("IU_PRECISION", "fp16"), choices=["fp16", "bf16"])
     ap.add_argument("--cpu-slices", type=int, default=32, help="slices per axis in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch/cuDNN-on-this-GPU context number")
+    ap.add_argument("--no-config0", action="store_true", help="skip timing BASELINE configs[0] (128^3, 1 axis, CPU)")
     args = ap.parse_args()
     ENCODER = args.encoder
 

@@ -182,6 +182,22 @@ def predict_volume_sharded(engine, volume=None, axes=(0, 1, 2), window=None, wan
     return out
 
 
+def predict_slab_from_host(engine, slab_host, axes=(0, 1, 2), window=None, out_u8=None, out_labels=None, group=None):
+    """End-to-end form of `predict_volume_sharded` for host data: `slab_host` is this rank's `[T,N,N]` part of the
+    volume in (pinned) host memory; the uint8 probabilities / labels of the slab are copied into the (pinned) host
+    tensors `out_u8` `[T,N,N,C]` / `out_labels` `[T,N,N]`.  Per rank N^3/G bytes go up and (C+1) N^3/G come back."""
+    dev = engine.device
+    slab = torch.as_tensor(slab_host).to(dev, non_blocking=True)
+    res = predict_volume_sharded(engine, slab=slab, axes=axes, window=window, want_u8=out_u8 is not None,
+                                 want_labels=out_labels is not None, group=group)
+    if out_u8 is not None:
+        out_u8.copy_(res["u8"], non_blocking=True)
+    if out_labels is not None:
+        out_labels.copy_(res["labels"], non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return res["z0"], res["t"]
+
+
 def gather_slabs(slab, group=None, dst=0):
     """Concatenate every rank's slab tensor along z on rank `dst` (None elsewhere)."""
     world = dist.get_world_size(group)

@@ -46,7 +46,13 @@ def _load_model(num_channels, num_classes, device):
         with _model_cache_lock:
             model = _model_cache.get(key)
             if model is None:
-                model = unet.UNet.load_from_checkpoint(checkpoint_path=model_path).to(device)
+                try:
+                    model = unet.UNet.load_from_checkpoint(checkpoint_path=model_path).to(device)
+                except NotImplementedError as e:
+                    raise NotImplementedError(
+                        f"{model_path} was trained with a configuration the B200 engine does not accelerate ({e}). "
+                        "Keep `from interactive_unet import predict` for this model, or train with "
+                        "architecture='U-Net' and encoder_name='resnet34' / 'resnet18' (INTEGRATION.md section 1).") from e
                 model.eval()
                 _model_cache.clear()
                 _model_cache[key] = model
@@ -85,21 +91,21 @@ def find_max_batch_size(model, input_size=256, start=4, max_limit=512):
     allocation probe per size instead of timed trial forwards."""
     batch_size, best = start, start
     device = model.device
+    eng = model.engine()
     while batch_size <= max_limit:
         try:
-            with torch.inference_mode():
+            with torch.inference_mode(), eng.limit_batch(batch_size):
                 test_batch = torch.zeros((batch_size, 1, input_size, input_size), dtype=torch.float32, device=device)
-                model.engine().set_max_batch(batch_size)
                 _ = model(test_batch)
             best = batch_size
             batch_size *= 2
             torch.cuda.empty_cache()
         except RuntimeError as e:
-            if "out of memory" in str(e):
+            if "out of memory" in str(e):                                # predict.py:67-72
                 torch.cuda.empty_cache()
                 break
             raise
-    model.engine().set_max_batch(0)
+    eng.release_workspace()              # the probe's plans (one per size tried) go back to the driver
     torch.cuda.empty_cache()
     return best
 
@@ -113,14 +119,11 @@ def predict_block(model, block, num_classes=2, batch_size=8, axes=[0, 1, 2]):
     eng = model.engine()
     if eng.num_classes != num_classes:
         raise ValueError(f"model has {eng.num_classes} classes, num_classes={num_classes} requested")
-    eng.set_max_batch(batch_size)
     out = np.empty((size, size, size, num_classes), dtype=np.float32)
     vol = block.to(torch.float32).contiguous()
     vol = vol if vol.is_cuda else vol.numpy()
-    try:
+    with eng.limit_batch(batch_size):
         eng.predict_volume(vol, axes=list(axes), window=None, out_mean=out)
-    finally:
-        eng.set_max_batch(0)
     return out
 
 
@@ -173,6 +176,35 @@ def get_shard_coordinates(volume_shape, shard_size=128):
     return np.concatenate([c, np.minimum(c + shard_size, volume_shape)], axis=1)
 
 
+def tiled_device_bytes(shape, input_size, num_classes, n_axes=3, volume_on_device=True, out_on_device=True):
+    """Device bytes the tiled mode holds for a `[D,H,W]` volume beyond what the caller already keeps there: the fp32
+    `pred` / `weight` accumulators of `predict.py:181-198` (in HBM here, on disk in the reference), the uint8 outputs
+    and the volume itself when they arrive from / go to the host, one block and its per-axis probabilities."""
+    vox = int(np.prod(shape, dtype=np.int64))
+    bvox = int(input_size) ** 3
+    total = vox * (4 * num_classes + 4) + bvox * (1 + 4 * num_classes * n_axes)
+    if not volume_on_device:
+        total += vox
+    if not out_on_device:
+        total += vox * (num_classes + 1)
+    return total
+
+
+def _check_tiled_fits(eng, shape, input_size, num_classes, n_axes, volume_on_device, out_on_device):
+    """The reference streams blocks through on-disk accumulators and handles any volume size; this engine keeps them
+    in HBM.  Fail before allocating anything, with the numbers, rather than with an allocator error half way."""
+    need = tiled_device_bytes(shape, input_size, num_classes, n_axes, volume_on_device, out_on_device)
+    need += eng.workspace_bytes(eng.auto_batch(input_size, input_size, input_size), input_size, input_size)
+    free, _total = torch.cuda.mem_get_info(eng.device)
+    avail = free + eng.held_bytes()                      # pooled scratch and cached plans are reused or released
+    if need > avail:
+        raise RuntimeError(
+            f"CUDA out of memory: predicting a {shape[0]}x{shape[1]}x{shape[2]} volume in the tiled mode keeps "
+            f"{need / 2**30:.1f} GiB on the device ({4 * num_classes + 4} B per voxel of fp32 accumulators), "
+            f"{avail / 2**30:.1f} GiB are available; split the volume (for example into z ranges that overlap by "
+            f"input_size * overlap) and predict the parts separately")
+
+
 def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=0.25, batch_size=None,
                          axes=[0, 1, 2], return_labels=False, out=None, out_labels=None):
     """In-memory core of `predict_volumes` (`predict.py:153,201,235-256`): uint8 volume `[D,H,W]` (numpy, or a CUDA
@@ -191,7 +223,6 @@ def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=
     eng = model.engine()
     if eng.num_classes != num_classes:
         raise ValueError(f"model has {eng.num_classes} classes, num_classes={num_classes} requested")
-    eng.set_max_batch(batch_size or 0)
     window = gaussian_window_1d(input_size, sigma=0.125)               # predict.py:153
     lab = out_labels
     if isinstance(volume, torch.Tensor):
@@ -206,16 +237,16 @@ def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=
             out = np.empty(shape + (num_classes,), dtype=np.uint8)
         if lab is None and return_labels:
             lab = np.empty(shape, dtype=np.uint8)
-    try:
+    with eng.limit_batch(batch_size):
         if shape == (input_size,) * 3:
             eng.predict_volume(volume, axes=list(axes), window=window, out_u8=out, out_labels=lab)
         else:
             if volume.dtype not in (np.uint8, torch.uint8):
                 raise TypeError("the tiled mode reads uint8 volumes (predict.py:237)")
+            _check_tiled_fits(eng, shape, input_size, num_classes, len(axes), isinstance(volume, torch.Tensor),
+                              isinstance(out, torch.Tensor))
             _, padded, _ = get_block_coordinates(np.array(shape), input_size=input_size, overlap=overlap)
             eng.predict_tiled(volume, input_size, padded[:, :3], axes=list(axes), window=window, out_u8=out, out_labels=lab)
-    finally:
-        eng.set_max_batch(0)
     return (out, lab) if return_labels else out
 
 
@@ -299,4 +330,6 @@ def predict_volumes(input_size=256, num_channels=1, num_classes=2, overlap=0.25,
                 except Exception:
                     pass
             prefetch.shutdown(wait=True)
+            # the engine is cached with the model: give its workspace back (the trainer shares this GPU)
+            model.engine().release_workspace()
     print('\nAll volumes segmented.\n')

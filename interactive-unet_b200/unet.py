@@ -2,12 +2,18 @@
 
 Same constructor arguments, same `forward` contract (fp32 `[B,1,H,W]` in `[0,1]` -> softmax
 probabilities fp32 `[B,C,H,W]`), same `state_dict()` keys (`model.<smp key>`), `.device`, `.eval()`,
-`.to()` and `load_from_checkpoint(checkpoint_path=...)`.  In eval mode `forward` runs entirely in the
+`.to()`, `load_from_checkpoint(checkpoint_path=...)`, `configure_optimizers`, `training_step`,
+`validation_step` and `_log_metrics` (`unet.py:71-116`).  In eval mode `forward` runs entirely in the
 native sm_100a engine; there is no PyTorch or CPU fallback for inference -- a missing library or a
-non-CUDA input raises.  Training mode keeps stock autograd so the reference's trainer still works.
+non-CUDA input raises.  Training mode runs the same parameters through stock autograd, so the
+reference's trainer (`trainer.py:37-49`) can fit this module; validation steps (eval mode) use the engine.
 
-Accelerated configuration: `architecture='U-Net'`, `encoder_name='resnet34'`, `num_channels=1`
-(SURVEY.md section 8a).  Other configurations raise `NotImplementedError`.
+Accelerated configurations: `architecture='U-Net'` with `encoder_name` `'resnet34'` or `'resnet18'`,
+`num_channels=1`.  DELIBERATE DIFFERENCE from `unet.py:15-20`: the
+defaults here are `encoder_name='resnet34', pretrained=False` (the reference's are `'mit_b0', True`: a
+transformer encoder and a weight download, neither of which this engine has).  Every other
+configuration raises `NotImplementedError` naming the stock module to use instead -- it is never run on
+another code path silently.
 """
 import sys
 import types
@@ -125,6 +131,36 @@ class UNet(_Base):
 
     def configure_optimizers(self):
         return torch.optim.AdamW(self.parameters(), lr=self.lr)      # unet.py:71-73
+
+    # ---- trainer hooks (unet.py:75-116).  `metrics_module` may be injected; by default the reference's own
+    #      `interactive_unet.metrics` is used (it is present wherever the reference's trainer runs).
+    metrics_module = None
+
+    def _metrics(self):
+        if self.metrics_module is not None:
+            return self.metrics_module
+        from interactive_unet import metrics
+        return metrics
+
+    def _log_metrics(self, set_name, loss, y_hat, y, w):
+        m = self._metrics()
+        y, y_hat = torch.round(y), torch.round(y_hat)
+        self.log(f"{set_name}/Loss", loss, prog_bar=True, on_step=False, on_epoch=True)
+        for label, fn in (("Dice", m.dice), ("IoU", m.iou), ("MCC", m.mcc)):
+            self.log(f"{set_name}/{label}", fn(y_hat, y, w, axes=[0, 2, 3]), on_step=False, on_epoch=True)
+
+    def _step(self, set_name, batch):
+        X, y, w = batch
+        y_hat = self(X)
+        loss = self.loss_function(y_hat, y, w, axes=[0, 2, 3])
+        self._log_metrics(set_name, loss, y_hat, y, w)
+        return loss
+
+    def training_step(self, batch, *args):
+        return self._step('train', batch)
+
+    def validation_step(self, batch, *args):
+        self._step('val', batch)
 
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, **kwargs):

@@ -666,3 +666,191 @@ def test_full_size_is_deterministic(big_run, iu):
     model, vol, u8, lab = big_run
     u8b, labb = iu.predict.predict_volume_array(model, vol, num_classes=2, return_labels=True)
     assert torch.equal(u8, u8b) and torch.equal(lab, labb)
+
+
+# --------------------------------------------------------------------------- slice sizes of BASELINE configs 3 and 5
+@pytest.mark.parametrize("size,c,batch", [(1024, 2, 2), (1024, 4, 2), (2048, 2, 1), (2048, 4, 1)])
+def test_forward_matches_fp32_oracle_large_slices(dev, fitted, size, c, batch):
+    """1024^2 (config 3) and 2048^2 (config 5) slices against the strict-fp32 oracle: same gates as the small sizes.
+    At these widths the full-resolution layers run 8 / 16 row segments per image row and the deepest maps are 32 / 64
+    wide, so every kernel variant sees tile counts it never meets at 512^2."""
+    from oracle import synth
+    ref, model = fitted[c]
+    vol, _ = synth.blob_volume(128, 5)
+    reps = size // 128
+    img = np.tile(vol[3:3 + batch], (1, reps, reps))
+    img = np.roll(img, (37, 91), (1, 2))                                    # no tile boundary on a period boundary
+    x = torch.from_numpy(img.astype(np.float32) / 255.0)[:, None].to(dev)
+    with torch.inference_mode():
+        want = ref(x)
+        got = model(x)
+    assert got.shape == want.shape == (batch, c, size, size)
+    _check_probs(got, want)
+
+
+def test_full_volume_voxel_parity_512(dev, fitted, iu):
+    """BASELINE config 2 (512^3, 2 classes, 3 axes) compared with the oracle AT VOXEL LEVEL on sampled z planes.
+    The oracle runs every slice of axes 1 and 2 (1024 fp32 forwards of 512^2, keeping the rows of the sampled planes)
+    plus the sampled axis-0 slices, and accumulates in the reference's order (predict.py:85-110)."""
+    from oracle import predict_port as pp
+    from oracle import synth
+    ref, model = fitted[2]
+    n, c = 512, 2
+    planes = [0, 1, 137, 255, 256, 300, 511]
+    vol = np.tile(synth.blob_volume(128, 23)[0], (4, 4, 4))
+    vol = np.ascontiguousarray(np.roll(vol, (11, 45, 77), (0, 1, 2)))
+    vol_d = torch.from_numpy(vol).to(dev)
+    zs = torch.tensor(planes, device=dev)
+
+    def probs_of(slices_u8):                                # [B,H,W] uint8 (device) -> [B,C,H,W] fp32
+        with torch.inference_mode():
+            return ref((slices_u8.to(torch.float32) / 255.0)[:, None])
+    acc = torch.zeros((len(planes), n, n, c), dtype=torch.float32, device=dev)
+    acc += probs_of(vol_d[zs]).permute(0, 2, 3, 1)                          # axis 0: image (y, x)
+    bs = 16
+    p1 = torch.empty((len(planes), n, n, c), dtype=torch.float32, device=dev)
+    p2 = torch.empty_like(p1)
+    for s in range(0, n, bs):
+        q = probs_of(vol_d[:, s:s + bs, :].permute(1, 0, 2).contiguous())   # axis 1: slice y, image (z, x)
+        p1[:, s:s + bs] = q[:, :, zs, :].permute(2, 0, 3, 1)                # -> [plane][y][x][c]
+        q = probs_of(vol_d[:, :, s:s + bs].permute(2, 0, 1).contiguous())   # axis 2: slice x, image (z, y)
+        p2[:, :, s:s + bs] = q[:, :, zs, :].permute(2, 3, 0, 1)             # -> [plane][y][x][c]
+    acc += p1
+    acc += p2
+    want = acc / np.float32(3)
+
+    eng = model.engine()
+    mean = torch.empty((n, n, n, c), dtype=torch.float32, device=dev)
+    eng.predict_volume(vol_d, axes=(0, 1, 2), window=None, out_mean=mean)
+    got = mean[zs]
+    err = (got - want).abs().max().item()
+    assert err <= PROB_TOL, f"max-abs probability error {err}"
+    dis = got.argmax(-1) != want.argmax(-1)
+    assert 1.0 - dis.float().mean().item() >= MIN_AGREEMENT
+    if dis.any():
+        s2 = want.sort(-1).values
+        assert (s2[..., -1] - s2[..., -2])[dis].max().item() <= NEAR_TIE
+    # the quantised outputs of the drop-in call are the reference's formulas applied to the engine's own means, bit for
+    # bit, and within 255 * tolerance of the oracle's
+    u8, lab = iu.predict.predict_volume_array(model, vol_d, num_classes=c, return_labels=True)
+    g, gmax, lo = iu.gaussian_window_1d(n)
+    for i, z in enumerate(planes):
+        w = np.clip(((g[z] * g[:, None]) * g[None, :]) / np.float32(gmax), np.float32(lo), np.float32(1.0))
+        m = got[i].cpu().numpy()
+        assert np.array_equal(u8[z].cpu().numpy(), pp.quantise(m * w[..., None], w))
+        assert np.array_equal(lab[z].cpu().numpy(), m.argmax(-1).astype(np.uint8))
+        want_u8 = pp.quantise(want[i].cpu().numpy() * w[..., None], w).astype(np.int32)
+        assert np.abs(u8[z].cpu().numpy().astype(np.int32) - want_u8).max() <= 3
+
+
+# --------------------------------------------------------------------------- strided slice sources (multi-GPU strips)
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+def test_predict_slices_strided_sources_bit_identical(dev, fitted, iu, dtype):
+    """`iu_engine_predict_slices` on the strip layouts of the sharded path -- `[N][T][N]` for axis 1, `[N][N][T]` for
+    axis 2, the z-slab for axis 0 -- equals `predict_axis` on the whole cube bit for bit, with and without the
+    destination-major output layout."""
+    from oracle import synth
+    _, model = fitted[2]
+    eng = model.engine()
+    n, t, y0, c = 96, 32, 32, 2
+    vol = torch.from_numpy(synth.blob_volume(n, 31)[0]).to(dev)
+    if dtype == "f32":
+        vol = vol.to(torch.float32) / 255.0
+    sources = {0: (vol[y0:y0 + t].contiguous(), (n * n, n, 1)),
+               1: (vol[:, y0:y0 + t, :].contiguous(), (n, t * n, 1)),
+               2: (vol[:, :, y0:y0 + t].contiguous(), (1, n * t, t))}
+    for axis, (src, strides) in sources.items():
+        for row_block in (n, t):
+            want = torch.zeros((t, n, n, c), dtype=torch.float32, device=dev)
+            eng.predict_axis(vol, axis, slice_begin=y0, slice_count=t, out=want, slice_total=t, row_block=row_block)
+            got = torch.zeros_like(want)
+            eng.predict_slices(src, 0, t, n, n, strides, got, slice_total=t, row_block=row_block)
+            assert torch.equal(got, want), f"axis {axis} row_block {row_block}"
+    # a generic stride pattern (neither rows nor slices contiguous) goes through the scalar gather
+    wide = torch.zeros((n, n, 2 * n), dtype=vol.dtype, device=dev)
+    wide[:, :, ::2] = vol
+    got = torch.zeros((t, n, n, c), dtype=torch.float32, device=dev)
+    eng.predict_slices(wide, y0 * n * 2 * n, t, n, n, (n * 2 * n, 2 * n, 2), got)
+    want = eng.predict_axis(vol, 0, slice_begin=y0, slice_count=t)
+    assert torch.equal(got, want)
+    with pytest.raises(RuntimeError, match="divisible by 32"):
+        eng.predict_slices(vol, 0, 4, 48, 96, (n * n, n, 1), got)
+
+
+# --------------------------------------------------------------------------- latency path: plan cache + CUDA graph
+def test_forward_graph_replay_is_bit_identical(dev, fitted, iu):
+    """The first forward on a plan runs eagerly, the second captures a CUDA graph, later ones replay it: all must
+    return the same bits, for changing inputs, and alternating shapes must come back from the plan cache."""
+    _, model = fitted[2]
+    eng = model.engine()
+    eng.release_workspace()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    xs = {(1, 256): [torch.rand(1, 1, 256, 256, generator=g).to(dev) for _ in range(3)],
+          (4, 96): [torch.rand(4, 1, 96, 160, generator=g).to(dev) for _ in range(3)]}
+    first = {k: [model(x).clone() for x in v] for k, v in xs.items()}        # call 1 eager, call 2 captures, 3 replays
+    held = eng.held_bytes()
+    for _ in range(3):
+        for k, v in xs.items():
+            for x, want in zip(v, first[k]):
+                assert torch.equal(model(x), want)
+    assert eng.held_bytes() == held                                          # no re-planning while alternating
+    n0 = eng.launch_count()
+    model(xs[(1, 256)][0])
+    replayed = eng.launch_count() - n0
+    eng.release_workspace()
+    assert eng.held_bytes() < held
+    n0 = eng.launch_count()
+    assert torch.equal(model(xs[(1, 256)][1]), first[(1, 256)][1])           # eager again after the release
+    assert replayed == eng.launch_count() - n0 >= 45                         # stem, pool, 42 convs, head
+
+
+def test_engine_keeps_callers_current_device(dev, iu):
+    """An ABI call must not change the CUDA device that is current for the calling thread (torch's)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    torch.cuda.set_device(0)
+    eng = iu.Engine(1)
+    assert torch.cuda.current_device() == 0
+    eng.synchronize()
+    assert torch.cuda.current_device() == 0
+
+
+# --------------------------------------------------------------------------- out-of-memory behaviour (predict.py:49-77)
+def test_out_of_memory_is_reported_and_survivable(dev, fitted, iu):
+    """With the device nearly full, a workspace that cannot fit raises RuntimeError('...out of memory...') (the text
+    `find_max_batch_size` matches, predict.py:67-72) and leaves the engine usable; `find_max_batch_size` stops at the
+    last size that fitted.  (On an empty B200 the probe cannot fail: the engine sub-batches internally and its
+    largest plan is 12 GB.)"""
+    _, model = fitted[2]
+    eng = model.engine()
+    eng.release_workspace()
+    torch.cuda.empty_cache()
+    free, _total = torch.cuda.mem_get_info(dev)
+    leave = 5 << 30
+    hog = torch.empty(free - leave, dtype=torch.uint8, device=dev)
+    try:
+        per_slice = eng.workspace_bytes(8, 1024, 1024) / 8                # ~0.19 GB of activations per 1024^2 slice
+        assert 32 * per_slice > leave > 16 * per_slice + (1 << 30)
+        x = torch.zeros((32, 1, 1024, 1024), dtype=torch.float32, device=dev)
+        with pytest.raises(RuntimeError, match="out of memory"):
+            with eng.limit_batch(32):
+                model(x)
+        del x
+        small = torch.rand(2, 1, 64, 64, device=dev)
+        assert model(small).shape == (2, 2, 64, 64)                       # engine still healthy
+        torch.cuda.empty_cache()
+        best = iu.predict.find_max_batch_size(model, input_size=1024, start=4, max_limit=64)
+        assert best in (8, 16)                                            # 32 slices (6.2 GB) cannot fit in 5 GB
+        assert model(small).shape == (2, 2, 64, 64)
+    finally:
+        del hog
+        torch.cuda.empty_cache()
+    assert iu.predict.find_max_batch_size(model, input_size=256, start=4, max_limit=64) == 64
+
+
+def test_tiled_mode_refuses_volumes_that_cannot_fit(dev, fitted, iu):
+    from interactive_unet_b200 import predict as P
+    _, model = fitted[2]
+    with pytest.raises(RuntimeError, match="out of memory.*split the volume"):
+        P._check_tiled_fits(model.engine(), (4096, 4096, 4096), 256, 2, 3, True, True)
+    P._check_tiled_fits(model.engine(), (512, 512, 384), 256, 2, 3, False, False)

@@ -68,7 +68,8 @@ def test_product_package_never_touches_the_oracle():
 
 def test_bench_uses_the_oracle_only_in_its_cpu_arm():
     """`bench.py` may execute `oracle/` only in the CPU-baseline / reference-arm leg: every `oracle` import must sit
-    inside `cpu_reference_sample` (which both of those call), never at module level or in the GPU arm."""
+    inside `cpu_reference_sample` or `cpu_config0` (the two CPU timers both of those legs call), never at module level
+    or in the GPU arm."""
     import ast
     tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
     where = []
@@ -81,7 +82,7 @@ def test_bench_uses_the_oracle_only_in_its_cpu_arm():
                 names = [a.name for a in node.names]
             if any(n == "oracle" or n.startswith("oracle.") for n in names):
                 where.append(getattr(fn, "name", "<module>"))
-    assert where and set(where) == {"cpu_reference_sample"}, where
+    assert where and set(where) == {"cpu_reference_sample", "cpu_config0"}, where
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

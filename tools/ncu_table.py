@@ -10,7 +10,8 @@ COLS = [
     ("us", "gpu__time_duration.sum"),
     ("rdMB", "dram__bytes_read.sum"),
     ("wrMB", "dram__bytes_write.sum"),
-    ("tens%", "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
+    # share of the kernel's active cycles in which the fp16/bf16 tensor sub-pipe (tcgen05 kind::f16) was busy
+    ("tens%", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"),
     ("lts%", "LTS.TriageCompute.lts__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("dram%", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
     ("sm%", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
