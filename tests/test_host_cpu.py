@@ -121,6 +121,47 @@ def test_state_dict_matches_oracle_and_training_forward():
     assert torch.equal(m(x), ref(x))                 # autograd path kept for the reference's trainer
 
 
+def test_state_dict_layout_matches_smp_key_fixture(golden_dir):
+    """Keys, order and shapes of the drop-in's `state_dict()` against the list assembled from torchvision's resnet34
+    (encoder) and smp 0.5.0's published decoder / head (tests/golden/make_smp_keys.py): a reference checkpoint
+    (`trainer.py:46-49`, keys `model.<smp key>`) loads with strict=True exactly when these agree."""
+    import json
+    import interactive_unet_b200 as iu
+    want = json.load(open(os.path.join(golden_dir, "smp_unet_resnet34_keys.json")))["keys"]
+    got = [[k, list(v.shape)] for k, v in iu.UNet(num_classes=2).state_dict().items()]
+    assert got == [["model." + k, shp] for k, shp in want]
+
+
+def test_trainer_hooks_fit_one_step():
+    """`training_step` / `validation_step` / `_log_metrics` (unet.py:75-116) exist and one optimiser step runs through
+    them with an injected metrics module (the reference's `interactive_unet.metrics` is used when it is importable)."""
+    import interactive_unet_b200 as iu
+
+    class Metrics:
+        calls = []
+
+        @staticmethod
+        def dice(y_hat, y, w, axes):
+            Metrics.calls.append(tuple(axes))
+            return (y_hat * y * w).sum() / ((y_hat + y) * w).sum().clamp_min(1e-6)
+        iou = mcc = dice
+
+    logged = {}
+    m = iu.UNet(num_classes=2, loss_function=lambda y_hat, y, w, axes: (((y_hat - y) ** 2) * w).mean(dim=axes).sum())
+    m.metrics_module = Metrics
+    m.log = lambda name, value, **kw: logged.__setitem__(name, float(value))
+    batch = (torch.rand(2, 1, 64, 64), torch.rand(2, 2, 64, 64).round(), torch.ones(2, 1, 64, 64))
+    m.train()
+    opt = m.configure_optimizers()
+    before = m.model.segmentation_head[0].weight.detach().clone()
+    loss = m.training_step(batch)
+    loss.backward()
+    opt.step()
+    assert not torch.equal(before, m.model.segmentation_head[0].weight)
+    assert {"train/Loss", "train/Dice", "train/IoU", "train/MCC"} <= set(logged) and Metrics.calls[0] == (0, 2, 3)
+    assert m.validation_step.__code__.co_argcount >= 2
+
+
 def test_resnet18_encoder_state_dict_and_checkpoint(tmp_path):
     """SURVEY section 8 row f3 (first step): the other BasicBlock ResNet behind the same kernels."""
     import interactive_unet_b200 as iu
