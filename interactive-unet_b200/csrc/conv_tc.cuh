@@ -98,6 +98,24 @@ int conv_row_kc(int cout_pad, int mode);
 int conv_row_store_rows(int cout_pad);  // output rows per TMA store box (the `omap` box height)
 cudaError_t launch_conv_row(const ConvArgs& args, cudaStream_t stream);
 
+// Fused decoder tail (conv_chain.cu): decoder block 4 conv1 (32 channels at half resolution, read through the 2x
+// nearest upsample, -> 16) -> conv2 (16 -> 16) -> head (16 -> classes, softmax, oriented fp32 store) in one kernel; the
+// two 16-channel full-resolution intermediates stay in shared-memory line buffers.
+struct alignas(64) ChainArgs {
+  CUtensorMap w1;   // conv1, four-slot fold (ConvArgs::bmapu of decoder block 4 conv1), box (16, 64)
+  CUtensorMap w2;   // conv2, three-slot fold (ConvArgs::bmapf), box (16, 48)
+  CUtensorMap w3;   // head, three-slot fold (ConvArgs::bmapf), box (16, 48)
+  const __nv_bfloat16* src;  // decoder block 3 output [batch][h/2][w/2][32]
+  const float* b1;  // [16] folded-BN shifts of conv1 / conv2
+  const float* b2;
+  int batch, h, w;  // full-resolution geometry
+  int strips, total_items, groups;  // filled by launch_conv_chain
+  int fp16;
+  ConvArgs head;    // the head's epilogue description (bias, mode, out, num_classes, slice0, slice_count, row_block)
+};
+bool conv_chain_applicable(int h, int w);
+cudaError_t launch_conv_chain(const ChainArgs& args, cudaStream_t stream);
+
 // Stem (conv_stem.cu): Conv2d(1, 64, 7, stride 2, padding 3) + bias + ReLU on the tensor cores.
 //   bmap: 2-D map over the packed 16-bit weights [64 cout][64 k], k = filter_row * 8 + filter_col (col 7 and
 //         k >= 56 are zero), box (64, 64), 128-byte swizzle;  x: fp32 [batch][h][w];

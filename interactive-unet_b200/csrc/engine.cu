@@ -58,6 +58,8 @@ struct Plan {
   std::vector<ConvArgs> args;
   ConvArgs stem_epi;
   CUtensorMap stem_omap;
+  ChainArgs chain;         // fused decoder block 4 conv1 -> conv2 -> head (conv_chain.cu), valid when use_chain
+  bool use_chain = false;
   size_t bytes = 0;
   uint64_t last_use = 0;  // LRU stamp while the plan sits in the cache
   // latency path (`predict_slice`, predict.py:16-47): the 46 launches of one single-batch forward captured as a CUDA
@@ -138,6 +140,7 @@ struct iu_engine {
   int plan_cache = 3;        // env IU_PLAN_CACHE: plans kept besides none in use (0 = re-plan on every shape change)
   uint64_t use_clock = 0;
   int use_graph = 1;         // env IU_GRAPH=0: never capture the single-batch forward
+  int conv_chain = 1;        // env IU_CONV_CHAIN=0: decoder block 4 + head as three separate row-folded launches
   std::vector<Scratch> scratch;
   size_t scratch_keep = ~(size_t)0;  // env IU_SCRATCH_KEEP_MB: idle scratch above this is returned to the driver when a
                                      // volume call returns (default: keep everything for the next call of the same
@@ -794,6 +797,33 @@ int build_plan(iu_engine* e, int batch, int h, int w) {
       return rc;
     }
   }
+  // fused tail: the last three convs are decoder block 4 conv1 (upsampled 32 -> 16), conv2 (16 -> 16) and the head
+  p.use_chain = false;
+  const size_t nc = e->convs.size();
+  if (e->conv_chain && e->conv_row && e->conv_variant != 1 && nc >= 3 && conv_chain_applicable(h, w)) {
+    const ConvLayer &l1 = e->convs[nc - 3], &l2 = e->convs[nc - 2], &l3 = e->convs[nc - 1];
+    const ConvArgs &a1 = p.args[nc - 3], &a2 = p.args[nc - 2], &a3 = p.args[nc - 1];
+    const bool shapes = l1.nseg == 1 && l1.seg[0].up && l1.seg[0].cin == 32 && l1.cout == 16 && l1.d_wu && l1.relu &&
+                        l1.residual < 0 && l1.out_hdiv == 1 && l2.nseg == 1 && !l2.seg[0].up && l2.seg[0].cin == 16 &&
+                        l2.cout == 16 && l2.relu && l2.residual < 0 && l2.src[0] == l1.out && l3.mode != kEpiBf16 &&
+                        l3.nseg == 1 && l3.seg[0].cin == 16 && l3.src[0] == l2.out && l3.cout_pad == 16;
+    if (shapes && a1.use_row && a2.use_row && a3.use_row) {
+      ChainArgs& c = p.chain;
+      memset(&c, 0, sizeof(c));
+      c.w1 = a1.bmapu;
+      c.w2 = a2.bmapf;
+      c.w3 = a3.bmapf;
+      c.src = p.bufs[l1.src[0]];
+      c.b1 = l1.d_b;
+      c.b2 = l2.d_b;
+      c.batch = batch;
+      c.h = h;
+      c.w = w;
+      c.fp16 = e->fp16;
+      c.head = a3;
+      p.use_chain = true;
+    }
+  }
   p.batch = batch;
   p.batch_pad = bp;
   p.h = h;
@@ -911,6 +941,22 @@ int run_network(iu_engine* e, int batch, int head_mode, float* head_out, int sli
   e->launches += 2;
   for (size_t i = 0; i < e->convs.size(); ++i) {
     const ConvLayer& L = e->convs[i];
+    if (p.use_chain && i + 3 == e->convs.size()) {
+      ChainArgs c = p.chain;
+      c.batch = batch;
+      c.head.batch = batch;
+      c.head.mode = head_mode;
+      c.head.out = head_out;
+      c.head.slice0 = slice0;
+      c.head.slice_count = slice_count;
+      c.head.row_block = row_block;
+      prof_begin(e, IU_PROF_CONV);
+      cudaError_t ce = launch_conv_chain(c, e->stream);
+      prof_end(e);
+      if (ce != cudaSuccess) return e->cuda_fail(ce, "launch decoder tail (conv_chain)");
+      e->launches += 1;
+      break;
+    }
     ConvArgs a = p.args[i];
     a.batch = batch;
     if (L.mode != kEpiBf16) {
@@ -1017,6 +1063,7 @@ int iu_engine_create(int device, iu_engine** out) {
   if (const char* v = getenv("IU_CONV_CLUSTER")) e->conv_cluster = atoi(v);
   if (const char* v = getenv("IU_PLAN_CACHE")) e->plan_cache = std::max(0, atoi(v));
   if (const char* v = getenv("IU_GRAPH")) e->use_graph = atoi(v);
+  if (const char* v = getenv("IU_CONV_CHAIN")) e->conv_chain = atoi(v);
   if (const char* v = getenv("IU_SCRATCH_KEEP_MB")) e->scratch_keep = (size_t)std::max(0, atoi(v)) << 20;
   if (const char* v = getenv("IU_CONV_DEBUG")) {
     if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)

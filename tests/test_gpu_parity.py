@@ -854,3 +854,49 @@ def test_tiled_mode_refuses_volumes_that_cannot_fit(dev, fitted, iu):
     with pytest.raises(RuntimeError, match="out of memory.*split the volume"):
         P._check_tiled_fits(model.engine(), (4096, 4096, 4096), 256, 2, 3, True, True)
     P._check_tiled_fits(model.engine(), (512, 512, 384), 256, 2, 3, False, False)
+
+
+# --------------------------------------------------------------------------- fused decoder tail (conv_chain.cu)
+@pytest.mark.parametrize("c,h,w,batch", [(2, 512, 512, 3), (4, 512, 512, 2), (3, 320, 640, 2), (5, 64, 512, 2),
+                                         (2, 1024, 1024, 1), (2, 512, 1504, 1)])
+def test_decoder_tail_fusion_matches_separate_layers(dev, iu, monkeypatch, c, h, w, batch):
+    """Decoder block 4 conv1 -> conv2 -> head as ONE kernel (line buffers in shared memory, 124-column strips) against
+    the same three layers as separate row-folded launches: both within tolerance of the fp32 oracle and within
+    accumulation-order noise of each other, on square, rectangular and ragged-last-strip images, for the 2 / 3 / 4 /
+    more-class head paths."""
+    from oracle import synth
+    ref = synth.make_model(c).to(dev).eval()
+    g = torch.Generator().manual_seed(c * 1000 + w)
+    x = torch.rand(batch, 1, h, w, generator=g).to(dev)
+    outs = {}
+    for chain in ("1", "0"):
+        monkeypatch.setenv("IU_CONV_CHAIN", chain)
+        model = iu.UNet(num_classes=c)
+        model.load_state_dict(ref.state_dict())
+        model = model.to(dev).eval()
+        n0 = model.engine().launch_count()
+        with torch.inference_mode():
+            outs[chain] = model(x).clone()
+        outs[chain + "_launches"] = model.engine().launch_count() - n0
+    assert outs["0_launches"] - outs["1_launches"] == 2                      # three launches became one
+    with torch.inference_mode():
+        want = ref(x)
+    assert (outs["1"] - want).abs().max().item() <= PROB_TOL
+    assert (outs["0"] - want).abs().max().item() <= PROB_TOL
+    assert (outs["1"] - outs["0"]).abs().max().item() <= 2e-3
+    assert torch.allclose(outs["1"].sum(1), torch.ones_like(outs["1"][:, 0]), atol=1e-5)
+
+
+def test_decoder_tail_fusion_oriented_store(dev, fitted, iu):
+    """The fused tail writes the head's probabilities through the same oriented / destination-major addressing as the
+    separate head launch: `predict_axis` with row_block = n/4 equals the plain layout re-arranged, bit for bit."""
+    from oracle import synth
+    _, model = fitted[2]
+    eng = model.engine()
+    n, t, cnt, c = 512, 128, 6, 2
+    vol = torch.from_numpy(synth.noise_volume(n, 5)).to(dev)
+    for axis in (1, 2):
+        plain = eng.predict_axis(vol, axis, slice_begin=100, slice_count=cnt)                     # [cnt][n][n][c]
+        major = torch.zeros((n // t, cnt, t, n, c), dtype=torch.float32, device=dev)
+        eng.predict_axis(vol, axis, slice_begin=100, slice_count=cnt, out=major, slice_total=cnt, row_block=t)
+        assert torch.equal(major.permute(1, 0, 2, 3, 4).reshape(cnt, n, n, c), plain)
