@@ -800,7 +800,9 @@ int build_plan(iu_engine* e, int batch, int h, int w) {
   // fused tail: the last three convs are decoder block 4 conv1 (upsampled 32 -> 16), conv2 (16 -> 16) and the head
   p.use_chain = false;
   const size_t nc = e->convs.size();
-  if (e->conv_chain && e->conv_row && e->conv_variant != 1 && nc >= 3 && conv_chain_applicable(h, w)) {
+  // IU_CONV_CHAIN=2 (development): also where the strip overhead makes the fused tail the slower choice
+  if (e->conv_chain && e->conv_row && e->conv_variant != 1 && nc >= 3 &&
+      (conv_chain_applicable(h, w) || (e->conv_chain == 2 && h >= 16 && h % 8 == 0 && w >= 128))) {
     const ConvLayer &l1 = e->convs[nc - 3], &l2 = e->convs[nc - 2], &l3 = e->convs[nc - 1];
     const ConvArgs &a1 = p.args[nc - 3], &a2 = p.args[nc - 2], &a3 = p.args[nc - 1];
     const bool shapes = l1.nseg == 1 && l1.seg[0].up && l1.seg[0].cin == 32 && l1.cout == 16 && l1.d_wu && l1.relu &&
