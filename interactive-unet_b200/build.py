@@ -15,7 +15,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libiunet_b200.so")
-SOURCES = ["conv_tc.cu", "conv_halo.cu", "conv_row.cu", "conv_chain.cu", "conv_stem.cu", "aux_kernels.cu", "engine.cu"]
+SOURCES = ["conv_tc.cu", "conv_tc2.cu", "conv_halo.cu", "conv_row.cu", "conv_chain.cu", "conv_stem.cu", "aux_kernels.cu", "engine.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

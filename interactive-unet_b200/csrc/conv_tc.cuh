@@ -89,6 +89,12 @@ cudaError_t launch_conv_halo(const ConvArgs& args, int kc, int bn, cudaStream_t 
 bool conv_pair_applicable(const ConvArgs& args);
 cudaError_t launch_conv_pair(const ConvArgs& args, cudaStream_t stream);
 
+// Per-tap TMA kernel on CTA pairs (conv_tc2.cu, tcgen05 cta_group::2, M = 256): 64-channel chunks, 16-bit outputs,
+// Cout a multiple of bn = 256 (one pixel tile per CTA) or 128 (two pixel tiles per CTA); each CTA holds half of every
+// weight tile.  Needs `bmap` (bn 256: half box (64, 128)) / `bmap2` (bn 128: half box (64, 64)).
+bool conv_tc2_applicable(const ConvArgs& args, int bn);
+cudaError_t launch_conv_tc2(const ConvArgs& args, int bn, cudaStream_t stream);
+
 // Row-folded variant (conv_row.cu) for stride-1 3x3 convs with Cout_pad in {16, 32, 64} on images whose width is a
 // multiple of 128: vertical taps folded into the MMA's N, residual as an identity K segment, TMA-store epilogue.
 // Needs `bmapf` / `omap` (and `bmapi` with a residual).  conv_row_kc: the K chunk its weight maps are boxed with.

@@ -141,6 +141,7 @@ struct iu_engine {
   uint64_t use_clock = 0;
   int use_graph = 1;         // env IU_GRAPH=0: never capture the single-batch forward
   int conv_chain = 1;        // env IU_CONV_CHAIN=0: decoder block 4 + head as three separate row-folded launches
+  int conv_pair2 = 0;        // env IU_CONV_PAIR2: per-tap kernel on CTA pairs; bit 0: Cout >= 256 layers, bit 1: Cout 128
   std::vector<Scratch> scratch;
   size_t scratch_keep = ~(size_t)0;  // env IU_SCRATCH_KEEP_MB: idle scratch above this is returned to the driver when a
                                      // volume call returns (default: keep everything for the next call of the same
@@ -918,6 +919,11 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
   else if (e->conv_variant == 2) halo = applicable;
   else halo = has_up || (applicable && (kc <= 32 || bn <= 64) && a.out_h >= kHaloTile && a.out_w >= kHaloTile);
   if (halo) return launch_conv_halo(a, kc, bn, e->stream);
+  if (e->conv_pair2 && kc == 64 && a.mode == kEpiBf16) {
+    const int bn2 = (a.use_bn256 && e->conv_bn256) ? 256 : bn;
+    if (((bn2 == 256 && (e->conv_pair2 & 1)) || (bn2 == 128 && (e->conv_pair2 & 2))) && conv_tc2_applicable(a, bn2))
+      return launch_conv_tc2(a, bn2, e->stream);
+  }
   const int bm = (kc == 64 && a.mode == kEpiBf16) ? e->conv_bm : 1;
   // weight multicast across CTA pairs: layers whose Cout is ONE tile (Cout 256 with 256-wide tiles, Cout 128 with
   // paired pixel tiles)
@@ -1066,6 +1072,7 @@ int iu_engine_create(int device, iu_engine** out) {
   if (const char* v = getenv("IU_PLAN_CACHE")) e->plan_cache = std::max(0, atoi(v));
   if (const char* v = getenv("IU_GRAPH")) e->use_graph = atoi(v);
   if (const char* v = getenv("IU_CONV_CHAIN")) e->conv_chain = atoi(v);
+  if (const char* v = getenv("IU_CONV_PAIR2")) e->conv_pair2 = atoi(v);
   if (const char* v = getenv("IU_SCRATCH_KEEP_MB")) e->scratch_keep = (size_t)std::max(0, atoi(v)) << 20;
   if (const char* v = getenv("IU_CONV_DEBUG")) {
     if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)

@@ -97,7 +97,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", ["pertap", "pertap_bm2", "pertap_cluster", "halo", "pair", "row"])
+@pytest.mark.parametrize("variant", ["pertap", "pertap_bm2", "pertap_cluster", "pertap_pair2", "halo", "pair", "row"])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_matches_fp32_reference(dev, iu, case, precision, variant, monkeypatch):
@@ -110,6 +110,7 @@ def test_conv_matches_fp32_reference(dev, iu, case, precision, variant, monkeypa
     monkeypatch.setenv("IU_CONV_BM2", "3" if variant == "pertap_bm2" else ("1" if variant == "pertap_cluster" else "0"))
     monkeypatch.setenv("IU_CONV_CLUSTER", "1" if variant == "pertap_cluster" else "0")
     monkeypatch.setenv("IU_CONV_PAIR", "1" if variant == "pair" else "0")
+    monkeypatch.setenv("IU_CONV_PAIR2", "3" if variant == "pertap_pair2" else "0")       # cta_group::2 per-tap kernel
     monkeypatch.setenv("IU_CONV_ROW", "1" if variant == "row" else "0")
     eng = iu.Engine(0, precision=precision)
     g = torch.Generator().manual_seed(hash(case[0]) % 1000)
@@ -941,10 +942,14 @@ def test_fp16_range_stress(dev, fitted, iu):
             h.remove()
         return peak[0], out
 
-    base, _ = largest_activation(ref)
-    factor = 3.0e4 / base
-    big = scaled(factor)
-    peak, want = largest_activation(big)
+    # the network is not exactly homogeneous in the stem's scale (BatchNorm shifts): home in on a ~3e4 peak
+    factor = 3.0e4 / largest_activation(ref)[0]
+    for _ in range(8):
+        big = scaled(factor)
+        peak, want = largest_activation(big)
+        if 2.0e4 <= peak <= 5.0e4:
+            break
+        factor *= (3.0e4 / peak) ** 0.8
     assert 1.0e4 <= peak <= 6.0e4, peak
     model = iu.UNet(num_classes=2)
     model.load_state_dict(big.state_dict())
