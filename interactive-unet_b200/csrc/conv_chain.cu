@@ -150,6 +150,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     operand_ready_fence();
     uint32_t n1 = 0, n2 = 0, n3 = 0;  // groups issued so far per layer (barrier phases)
     uint32_t r1 = 0, r2 = 0;          // line-buffer hand-offs waited for so far (conv1 -> A1, conv2 -> A2)
+    // IU_CONV_DEBUG=1: role cycle counters in the slots of ConvArgs::debug ([0] MMA waits for a drained accumulator,
+    // [1] for the gathered input, [2] for a line-buffer hand-off, [3] MMA warp total, [4] gather waits for a free stage,
+    // [5] gather issue, [6] gather landing, [7] gather total, [8] epilogue waits for an accumulator, [9] epilogue body)
+    unsigned long long* dbgp = c.head.debug;
+    const bool dbg = dbgp != nullptr;
+    long long w_acc = 0, w_in = 0, w_ready = 0, t0 = 0;
+    const long long t_begin = dbg ? clock64() : 0;
+#define IU_CHAIN_TIMED(acc_, stmt_)      \
+  do {                                   \
+    if (dbg) t0 = clock64();             \
+    stmt_;                               \
+    if (dbg) acc_ += clock64() - t0;     \
+  } while (0)
     // conv2 / head of the group whose first OUTPUT row is `orow0`: input rows orow0-1 .. orow0+8 from the line buffer
     auto issue_folded = [&](uint32_t dbase, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, int orow0) {
       uint32_t a_row[kChainR + 2];  // descriptor of every input row: its ring row, or the zero row outside the image
@@ -183,12 +196,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       for (int i = 0; i < NG + 3; ++i) {
         if (i < NG) {
           // ---- conv1 of group i: A1 rows [8i, 8i+8) from six source rows (four-slot pre-summed filters)
-          chain_warp_wait(acc_empty(0), (n1 & 1u) ^ 1u, lane);
+          IU_CHAIN_TIMED(w_acc, chain_warp_wait(acc_empty(0), (n1 & 1u) ^ 1u, lane));
           tc_fence_after();
           const uint32_t dbase = tmem_base;
 #pragma unroll
           for (int cb = 0; cb < 2; ++cb) {
-            chain_warp_wait(in_full(cb), n1 & 1u, lane);
+            IU_CHAIN_TIMED(w_in, chain_warp_wait(in_full(cb), n1 & 1u, lane));
             operand_ready_fence();
             if (elect_one()) {
               const uint32_t a_st = in_lo + (uint32_t)((cb * kChainInStage) >> 4);
@@ -223,8 +236,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         const int j2 = i - 1;
         if (j2 >= 0 && j2 <= NG) {
           // ---- conv2 of group j2: A2 rows [8*j2 - 1, 8*j2 + 7) from A1 rows [8*j2 - 2, 8*j2 + 8)
-          if (j2 < NG) chain_warp_wait(a_ready(0), r1++ & 1u, lane);  // conv1's rows of group j2 are in A1
-          chain_warp_wait(acc_empty(1), (n2 & 1u) ^ 1u, lane);
+          if (j2 < NG) IU_CHAIN_TIMED(w_ready, chain_warp_wait(a_ready(0), r1++ & 1u, lane));  // conv1's rows of group j2 are in A1
+          IU_CHAIN_TIMED(w_acc, chain_warp_wait(acc_empty(1), (n2 & 1u) ^ 1u, lane));
           tc_fence_after();
           if (elect_one()) {
             issue_folded(tmem_base + 128u, a1_lo, a1_hi, b_lo0 + (uint32_t)(kChainW1Bytes >> 4), kChainR * j2 - 1);
@@ -236,8 +249,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         const int j3 = i - 2;
         if (j3 >= 0 && j3 <= NG) {
           // ---- head of group j3: output rows [8*j3 - 2, 8*j3 + 6) from A2 rows [8*j3 - 3, 8*j3 + 7)
-          chain_warp_wait(a_ready(1), r2++ & 1u, lane);                // conv2's rows of group j3 are in A2
-          chain_warp_wait(acc_empty(2), (n3 & 1u) ^ 1u, lane);
+          IU_CHAIN_TIMED(w_ready, chain_warp_wait(a_ready(1), r2++ & 1u, lane));               // conv2's rows of group j3 are in A2
+          IU_CHAIN_TIMED(w_acc, chain_warp_wait(acc_empty(2), (n3 & 1u) ^ 1u, lane));
           tc_fence_after();
           if (elect_one()) {
             issue_folded(tmem_base + 256u, a2_lo, a2_hi, b_lo0 + (uint32_t)((kChainW1Bytes + kChainW2Bytes) >> 4),
@@ -249,6 +262,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         }
       }
     }
+    if (dbg && lane == 0) {
+      atomicAdd(dbgp + 0, (unsigned long long)w_acc);
+      atomicAdd(dbgp + 1, (unsigned long long)w_in);
+      atomicAdd(dbgp + 2, (unsigned long long)w_ready);
+      atomicAdd(dbgp + 3, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(dbgp + 10, 1ull);
+    }
   } else if (warp < 10) {
     // ------------------------------------------------------------ epilogue: set s owns rows [4s, 4s+4) of every group
     const int set = (warp - 2) >> 2;
@@ -256,6 +276,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
     const int p = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     uint32_t n1 = 0, n2 = 0, n3 = 0;
+    unsigned long long* dbgp = c.head.debug;
+    const bool dbg = dbgp != nullptr && warp == 2 && lane == 0;
+    long long e_wait = 0, e_t0 = 0;
+    const long long e_begin = dbg ? clock64() : 0;
+#define IU_CHAIN_EWAIT(stmt_)              \
+  do {                                     \
+    if (dbg) e_t0 = clock64();             \
+    stmt_;                                 \
+    if (dbg) e_wait += clock64() - e_t0;   \
+  } while (0)
     // One layer's rows [4*set, 4*set+4) of the group in accumulator `acc_col`: TMEM -> bias + ReLU + 16-bit pack (two
     // rows at a time), accumulator handed back, then the packed rows go into the line buffer in the layout the next
     // layer's A descriptor reads.  Rows outside the image are skipped (readers take the zero row instead); columns
@@ -305,21 +335,21 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
       const bool colok = x >= 0 && x < W;
       for (int i = 0; i < NG + 3; ++i) {
         if (i < NG) {
-          chain_warp_wait(acc_full(0), n1 & 1u, lane);
+          IU_CHAIN_EWAIT(chain_warp_wait(acc_full(0), n1 & 1u, lane));
           tc_fence_after();
           rows_to_line_buffer(0u, acc_empty(0), a_ready(0), bias_s, a1_base, kChainR * i, colok);
           ++n1;
         }
         const int j2 = i - 1;
         if (j2 >= 0 && j2 <= NG) {
-          chain_warp_wait(acc_full(1), n2 & 1u, lane);
+          IU_CHAIN_EWAIT(chain_warp_wait(acc_full(1), n2 & 1u, lane));
           tc_fence_after();
           rows_to_line_buffer(128u, acc_empty(1), a_ready(1), bias_s + 16, a2_base, kChainR * j2 - 1, colok);
           ++n2;
         }
         const int j3 = i - 2;
         if (j3 >= 0 && j3 <= NG) {
-          chain_warp_wait(acc_full(2), n3 & 1u, lane);
+          IU_CHAIN_EWAIT(chain_warp_wait(acc_full(2), n3 & 1u, lane));
           tc_fence_after();
           const bool mine = colok && p >= 2 && p < 2 + kChainValid;
           if (c.head.num_classes <= 4) {
@@ -356,32 +386,59 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
         }
       }
     }
+    if (dbg) {
+      atomicAdd(dbgp + 8, (unsigned long long)e_wait);
+      atomicAdd(dbgp + 9, (unsigned long long)(clock64() - e_begin - e_wait));
+    }
   } else if ((warp & 3) != 1) {
     // ------------------------------------------------------------ gather: six source rows x 130 slots x 16 channels per stage
     const int gw = warp - 10;
     const int t = (gw - (gw + 1) / 4) * 32 + lane;   // rank among the gather warps (ids 13 and 17 stay idle) * 32 + lane
     const int sh = H >> 1, sw = W >> 1;
     uint32_t n1 = 0;
+    unsigned long long* dbgp = c.head.debug;
+    const bool dbg = dbgp != nullptr && t == 0;
+    long long g_empty = 0, g_issue = 0, g_land = 0, g_t0 = 0;
+    const long long g_begin = dbg ? clock64() : 0;
+    // Thread t owns the (slot, plane) column t of a stage (130 slots x 2 planes = 260 columns: the last four are shared
+    // out as 24 single copies) and walks the six rows: per copy one bounds test and one pointer add.
+    const int my_slot = t >> 1, my_plane = t & 1;
+    const int x_slot = 128 + ((t % 4) >> 1), x_plane = t & 1, x_row = t >> 2;   // threads 0..23: slots 128 / 129, rows 0..5
+    const bool has_extra = t < 4 * kChainInRows;
+    const uint32_t my_dst = my_plane * kChainInPlane + my_slot * 16;
+    const uint32_t x_dst = x_plane * kChainInPlane + x_row * kChainPitch + x_slot * 16;
     for (int item = blockIdx.x; item < c.total_items; item += gridDim.x) {
       const int strip = item % c.strips, n = item / c.strips;
       const int ux0 = strip * kChainValid - 3;         // upsampled column of slot 0
       const __nv_bfloat16* img = c.src + (size_t)n * sh * sw * 32;
+      const int my_ux = ux0 + my_slot, x_ux = ux0 + x_slot;
+      const bool my_xok = (unsigned)my_ux < (unsigned)W, x_xok = (unsigned)x_ux < (unsigned)W;
+      const __nv_bfloat16* my_col = img + (size_t)(my_xok ? my_ux >> 1 : 0) * 32 + my_plane * 8;
+      const __nv_bfloat16* x_col = img + (size_t)(x_xok ? x_ux >> 1 : 0) * 32 + x_plane * 8;
+      const size_t row_stride = (size_t)sw * 32;
       for (int i = 0; i < NG; ++i, ++n1) {
         const int sy0 = 4 * i - 1;                     // source row of stage row 0
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
+          if (dbg) g_t0 = clock64();
           chain_warp_wait(in_empty(cb), (n1 & 1u) ^ 1u, lane);
+          if (dbg) { const long long t1 = clock64(); g_empty += t1 - g_t0; g_t0 = t1; }
           const uint32_t stage = in_base + cb * kChainInStage;
-          for (int idx = t; idx < kChainInRows * kChainSlots * 2; idx += kChainGatherThreads) {
-            const int js = idx / (2 * kChainSlots), rem = idx - js * (2 * kChainSlots);
-            const int slot = rem >> 1, plane = rem & 1;
-            const int sy = sy0 + js, ux = ux0 + slot;
-            const bool ok = (unsigned)sy < (unsigned)sh && (unsigned)ux < (unsigned)W;
-            const __nv_bfloat16* gp = ok ? img + ((size_t)sy * sw + (ux >> 1)) * 32 + cb * 16 + plane * 8 : c.src;
-            ccp_async_16(stage + plane * kChainInPlane + js * kChainPitch + slot * 16, gp, ok ? 16u : 0u);
+#pragma unroll
+          for (int js = 0; js < kChainInRows; ++js) {
+            const int sy = sy0 + js;
+            const bool ok = my_xok && (unsigned)sy < (unsigned)sh;
+            ccp_async_16(stage + my_dst + js * kChainPitch, ok ? my_col + (size_t)sy * row_stride + cb * 16 : c.src, ok ? 16u : 0u);
+          }
+          if (has_extra) {
+            const int sy = sy0 + x_row;
+            const bool ok = x_xok && (unsigned)sy < (unsigned)sh;
+            ccp_async_16(stage + x_dst, ok ? x_col + (size_t)sy * row_stride + cb * 16 : c.src, ok ? 16u : 0u);
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
+          if (dbg) g_issue += clock64() - g_t0;
         }
+        if (dbg) g_t0 = clock64();
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
@@ -394,7 +451,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) conv_chain_kernel(const __gr
           fence_proxy_async();
           mbar_arrive(in_full(1));
         }
+        if (dbg) g_land += clock64() - g_t0;
       }
+    }
+    if (dbg) {
+      atomicAdd(dbgp + 4, (unsigned long long)g_empty);
+      atomicAdd(dbgp + 5, (unsigned long long)g_issue);
+      atomicAdd(dbgp + 6, (unsigned long long)g_land);
+      atomicAdd(dbgp + 7, (unsigned long long)(clock64() - g_begin));
     }
   }
 

@@ -12,8 +12,11 @@ def load(path):
 
 
 def one_batch(names, which=1):
+    """Launches of network pass `which` (0-based): from its stem kernel up to the next pass's stem (or the end)."""
     idx = [i for i, (n, g, t) in enumerate(names) if "stem" in n]
-    return names[idx[which] - 1:idx[which + 1] - 1]
+    which = min(which, len(idx) - 1)
+    end = idx[which + 1] if which + 1 < len(idx) else len(names)
+    return names[idx[which]:end]
 
 
 if __name__ == "__main__":
