@@ -303,6 +303,127 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
   }
 }
 
+// Single-block mode (no blend accumulators), 2 or 4 classes, even n, 16-byte aligned buffers: a 32(y) x 64(x) tile per
+// block and TWO x-adjacent voxels per thread -- 16 / 32-byte loads per operand, packed 4 / 8-byte uint8 stores, 2-byte
+// label stores, half the address arithmetic per voxel.  Same per-voxel arithmetic (and bits) as reduce_kernel.
+template <int C>
+__global__ void __launch_bounds__(256) reduce_pair_kernel(const ReduceArgs a) {
+  extern __shared__ float tile[];  // [64 x][32*C + 1]
+  constexpr int pitch = 32 * C + 1;
+  const int z = blockIdx.z + a.zoff;
+  const int y0 = blockIdx.y * 32, x0 = blockIdx.x * 64;
+  const int n = a.n, t = a.t;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  if (a.p[2] != nullptr) {
+    const int ylim = min(32, n - y0);
+    for (int xl = wrp; xl < 64; xl += 8) {
+      if (x0 + xl < n) {
+        const float* src = a.p[2] + (((size_t)(x0 + xl) * t + z) * n + y0) * C;
+        if (ylim == 32) {
+          if (lane < 8 * C) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src) + lane);
+            float* d = tile + xl * pitch + 4 * lane;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+          }
+        } else {
+          for (int j = lane; j < ylim * C; j += 32) tile[xl * pitch + j] = __ldg(src + j);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int xl = 2 * lane, x = x0 + xl;
+  if (x >= n) return;                      // n is even: a pair is inside or outside as a whole
+  const bool windowed = a.g1d != nullptr;
+  const float gz = windowed ? __ldg(a.g1d + a.z0 + z) : 0.0f;
+  const float gx[2] = {windowed ? __ldg(a.g1d + x) : 0.0f, windowed ? __ldg(a.g1d + x + 1) : 0.0f};
+  const bool unit_gmax = a.gmax == 1.0f;
+  const float axes_f = (float)a.n_axes;
+#pragma unroll 2
+  for (int yl = wrp; yl < 32; yl += 8) {
+    const int y = y0 + yl;
+    if (y >= n) break;
+    float p[3][2][C];
+    if (a.p[0] != nullptr) {
+      const float4* s = reinterpret_cast<const float4*>(a.p[0] + (((size_t)z * n + y) * n + x) * C);
+#pragma unroll
+      for (int k = 0; k < C / 2; ++k) {
+        const float4 v = __ldg(s + k);
+        float* d = &p[0][0][0] + 4 * k;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+    if (a.p[1] != nullptr) {
+      const float4* s = reinterpret_cast<const float4*>(a.p[1] + (((size_t)y * t + z) * n + x) * C);
+#pragma unroll
+      for (int k = 0; k < C / 2; ++k) {
+        const float4 v = __ldg(s + k);
+        float* d = &p[1][0][0] + 4 * k;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+    if (a.p[2] != nullptr) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int c = 0; c < C; ++c) p[2][v][c] = tile[(xl + v) * pitch + yl * C + c];
+    }
+    const float gzy = windowed ? __fmul_rn(gz, __ldg(a.g1d + y)) : 0.0f;
+    float m[2][C];
+    uint8_t q[2][C];
+    uint8_t lab[2];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float acc = 0.0f;
+        for (int i = 0; i < a.n_axes; ++i) {
+          const int ax = a.order[i];
+          const float val = ax == 0 ? p[0][v][c] : (ax == 1 ? p[1][v][c] : p[2][v][c]);
+          acc = __fadd_rn(acc, val);                   // predict.py:101-106, in the caller's axis order
+        }
+        m[v][c] = __fdiv_rn(acc, axes_f);              // predict.py:110
+      }
+      int best = 0;
+#pragma unroll
+      for (int c = 1; c < C; ++c)
+        if (m[v][c] > m[v][best]) best = c;            // first maximum wins (np.argmax, predict.py:38)
+      lab[v] = (uint8_t)best;
+      if (windowed) {
+        float wgt = __fmul_rn(gzy, gx[v]);
+        if (!unit_gmax) wgt = __fdiv_rn(wgt, a.gmax);
+        wgt = fminf(fmaxf(wgt, a.lo), 1.0f);           // predict.py:345
+        const float den = fmaxf(wgt, 1e-3f);           // predict.py:253,255
+#pragma unroll
+        for (int c = 0; c < C; ++c) q[v][c] = (uint8_t)(int)__fdiv_rn(__fmul_rn(255.0f, __fmul_rn(m[v][c], wgt)), den);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) q[v][c] = (uint8_t)(int)__fmul_rn(255.0f, m[v][c]);
+      }
+    }
+    const size_t vox = ((size_t)z * n + y) * n + x;
+    if (a.out_mean != nullptr) {
+      float4* d = reinterpret_cast<float4*>(a.out_mean + vox * C);
+#pragma unroll
+      for (int k = 0; k < C / 2; ++k) {
+        const float* sm = &m[0][0] + 4 * k;
+        d[k] = make_float4(sm[0], sm[1], sm[2], sm[3]);
+      }
+    }
+    if (a.out_labels != nullptr) *reinterpret_cast<uchar2*>(a.out_labels + vox) = make_uchar2(lab[0], lab[1]);
+    if (a.out_u8 != nullptr) {
+      if constexpr (C == 2) {
+        *reinterpret_cast<uchar4*>(a.out_u8 + vox * C) = make_uchar4(q[0][0], q[0][1], q[1][0], q[1][1]);
+      } else {
+        uint2 w;
+        w.x = q[0][0] | (q[0][1] << 8) | (q[0][2] << 16) | ((uint32_t)q[0][3] << 24);
+        w.y = q[1][0] | (q[1][1] << 8) | (q[1][2] << 16) | ((uint32_t)q[1][3] << 24);
+        *reinterpret_cast<uint2*>(a.out_u8 + vox * C) = w;
+      }
+    }
+  }
+}
+
 // =========================================================================== tiled mode: block extraction / finalise
 // numpy 'reflect' of index i against a run of length len (period 2*(len-1), the edge sample is not repeated)
 __device__ __forceinline__ int reflect_index(int i, int len) {
@@ -373,6 +494,18 @@ cudaError_t launch_reduce(const ReduceArgs& args, cudaStream_t stream) {
   auto aligned = [](const void* p, size_t a) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % a == 0; };
   const bool vec = (c == 2 || c == 4) && aligned(args.p[0], 16) && aligned(args.p[1], 16) && aligned(args.p[2], 16) &&
                    aligned(args.out_mean, 16) && aligned(args.out_u8, 4);
+  // two voxels per thread: single-block mode, even edge, every buffer aligned to its widest access
+  if (vec && args.blend_pred == nullptr && args.n % 2 == 0 && aligned(args.out_u8, 8) && aligned(args.out_labels, 2)) {
+    dim3 grid2((args.n + 63) / 64, (args.n + 31) / 32, args.zcount ? args.zcount : args.t);
+    const size_t smem2 = (size_t)64 * (32 * c + 1) * sizeof(float);
+    if (c == 2) {
+      reduce_pair_kernel<2><<<grid2, 256, smem2, stream>>>(args);
+    } else {
+      cudaFuncSetAttribute(reduce_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      reduce_pair_kernel<4><<<grid2, 256, smem2, stream>>>(args);
+    }
+    return cudaGetLastError();
+  }
 #define IU_REDUCE_LAUNCH(C_, V_)                                                                         \
   cudaFuncSetAttribute(reduce_kernel<C_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   reduce_kernel<C_, V_><<<grid, 256, smem, stream>>>(args);

@@ -200,8 +200,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
       *reinterpret_cast<uint4*>(a_ptr + st * kStemAStage + row_off + ((7 ^ (m & 7)) << 4)) = make_uint4(0, 0, 0, 0);
     constexpr int kPatchElems = kStemPatchRows * kStemPatchCols;
     constexpr int kPerThread = (kPatchElems + kStemBuilders - 1) / kStemBuilders;
-    float pre[kPerThread];
-    auto load_patch = [&](int tile) {
+    // Patches are fetched TWO tiles ahead into registers (`pre` = the next tile's, `pre2` = the one after): the global
+    // latency of a fetch then hides under a whole tile's expansion instead of being waited for in store_patch.
+    float pre[kPerThread], pre2[kPerThread];
+    auto load_patch = [&](int tile, float (&dst)[kPerThread]) {
       const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
       const int iy0 = 2 * ty * kStemTileEdge - 3, ix0 = 2 * tx * kStemTileEdge - 3;
       const float* img = s.x + (size_t)n * s.h * s.w;
@@ -211,32 +213,33 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
         const int r = e / kStemPatchCols, c = e - r * kStemPatchCols;
         const int iy = iy0 + r, ix = ix0 + c;
         const bool ok = e < kPatchElems && (unsigned)iy < (unsigned)s.h && (unsigned)ix < (unsigned)s.w;
-        pre[i] = ok ? __ldg(img + (size_t)iy * s.w + ix) : 0.0f;
+        dst[i] = ok ? __ldg(img + (size_t)iy * s.w + ix) : 0.0f;
       }
     };
-    auto store_patch = [&](int which) {
+    auto store_patch = [&](int which, const float (&src)[kPerThread]) {
       uint16_t* p = patch_ptr + which * (kStemPatchBytes / 2);
 #pragma unroll
       for (int i = 0; i < kPerThread; ++i) {
         const int e = t + i * kStemBuilders;
         const int r = e / kStemPatchCols, c = e - r * kStemPatchCols;
         if (e < kPatchElems)
-          p[r * kStemPitch + c] = a.fp16 ? __half_as_ushort(__float2half_rn(pre[i]))
-                                         : __bfloat16_as_ushort(__float2bfloat16_rn(pre[i]));
+          p[r * kStemPitch + c] = a.fp16 ? __half_as_ushort(__float2half_rn(src[i]))
+                                         : __bfloat16_as_ushort(__float2bfloat16_rn(src[i]));
       }
     };
     auto builders_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kStemBuilders) : "memory"); };
     uint32_t it = 0;
     int tile = blockIdx.x;
     if (tile < total_tiles) {
-      load_patch(tile);
-      store_patch(0);
+      load_patch(tile, pre);
+      store_patch(0, pre);
+      if (tile + (int)gridDim.x < total_tiles) load_patch(tile + gridDim.x, pre);
     }
     builders_sync();
     for (; tile < total_tiles; tile += gridDim.x, ++it) {
       const int st = it % kStemAStages;
-      const int next = tile + gridDim.x;
-      if (next < total_tiles) load_patch(next);  // global latency hides under this tile's expansion
+      const int next = tile + gridDim.x, next2 = tile + 2 * gridDim.x;
+      if (next2 < total_tiles) load_patch(next2, pre2);  // lands during this tile's and the next tile's expansion
       if (lane == 0) mbar_wait(a_empty(st), ((it / kStemAStages) & 1) ^ 1u);
       __syncwarp();
       const uint32_t* prow =
@@ -252,7 +255,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
         fence_proxy_async();  // generic-proxy writes (ordered by the warp sync) -> visible to the tensor core's reads
         mbar_arrive(a_full(st));
       }
-      if (next < total_tiles) store_patch((it + 1) & 1u);
+      if (next < total_tiles) store_patch((it + 1) & 1u, pre);  // fetched one iteration ago
+#pragma unroll
+      for (int i = 0; i < kPerThread; ++i) pre[i] = pre2[i];
       builders_sync();  // next patch complete; everyone is done reading the current one
     }
   }
