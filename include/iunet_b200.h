@@ -125,6 +125,12 @@ int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float
                      int n, int t, int z0, int num_classes, const float* g1d_host, float gmax, float lo,
                      uint8_t* out_u8, uint8_t* out_labels, float* out_mean, unsigned flags);
 
+/* The same for the planes [zoff, zoff + zcount) of the slab only (outputs stay indexed by the slab's z): lets a caller
+ * reduce a z range as soon as its last axis has been predicted and copy it out while the next range is in the network. */
+int iu_engine_reduce_planes(iu_engine* e, const float* p0, const float* p1, const float* p2, const int* order, int n_axes,
+                            int n, int t, int z0, int zoff, int zcount, int num_classes, const float* g1d_host,
+                            float gmax, float lo, uint8_t* out_u8, uint8_t* out_labels, float* out_mean, unsigned flags);
+
 /* Whole single-GPU path (predict.py:79-112 + 244-245,255): volume (uint8 or fp32, host or device,
  * cubic edge n) -> uint8 probabilities [n][n][n][C], uint8 labels [n][n][n], fp32 mean probabilities
  * [n][n][n][C]; each output host or device, any may be NULL.  `axes`: n_axes entries from {0,1,2}. */

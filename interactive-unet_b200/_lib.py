@@ -46,6 +46,9 @@ SIGNATURES = {
     "iu_engine_reduce": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_int), _c.c_int,
                                     _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_float, _c.c_float,
                                     _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint]),
+    "iu_engine_reduce_planes": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_int), _c.c_int,
+                                           _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+                                           _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint]),
     "iu_engine_predict_volume": (_c.c_int, [_engine_p, _c.c_void_p, _c.c_int, _c.c_int, _c.POINTER(_c.c_int),
                                             _c.c_int, _c.c_void_p, _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p,
                                             _c.c_void_p, _c.c_uint]),

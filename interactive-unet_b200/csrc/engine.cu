@@ -135,6 +135,8 @@ struct iu_engine {
   std::vector<TensorSpec> tensors;
   std::vector<ConvLayer> convs;
   int t_f1 = -1, t_p1 = -1;
+  float* d_window = nullptr;        // device copy of the last 1-D window factor given to iu_engine_reduce(_planes)
+  std::vector<float> window_host;   // ... and its host values: re-uploaded only when they change
   Plan plan;                 // the current activation plan
   std::vector<Plan> cached;  // other (batch, h, w) plans kept allocated: the app alternates predict_slice / predict_volumes
   int plan_cache = 3;        // env IU_PLAN_CACHE: plans kept besides none in use (0 = re-plan on every shape change)
@@ -1092,6 +1094,7 @@ void iu_engine_destroy(iu_engine* e) {
   for (auto& s : e->scratch)
     if (s.ptr) cudaFree(s.ptr);
   if (e->d_debug) cudaFree(e->d_debug);
+  if (e->d_window) cudaFree(e->d_window);
   for (auto& s : e->spans) {
     cudaEventDestroy(s.begin);
     cudaEventDestroy(s.end);
@@ -1429,14 +1432,37 @@ int iu_engine_predict_axis(iu_engine* e, const void* volume, int dtype, int n, i
                            row_block, flags, 0);
 }
 
-int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float* p2, const int* order, int n_axes,
-                     int n, int t, int z0, int num_classes, const float* g1d_host, float gmax, float lo,
-                     uint8_t* out_u8, uint8_t* out_labels, float* out_mean, unsigned flags) {
+// The window factor lives in a device buffer the engine keeps (uploaded again only when its values change), so a
+// reduce call neither allocates nor has to drain the stream to give a staging block back.
+static int window_on_device(iu_engine* e, const float* g1d_host, int n, const float** out) {
+  *out = nullptr;
+  if (!g1d_host) return IU_OK;
+  const bool same = e->d_window && (int)e->window_host.size() == n &&
+                    memcmp(e->window_host.data(), g1d_host, (size_t)n * 4) == 0;
+  if (!same) {
+    if ((int)e->window_host.size() != n || !e->d_window) {
+      IU_CUDA(e, cudaStreamSynchronize(e->stream));  // kernels that still read the old table
+      if (e->d_window) cudaFree(e->d_window);
+      e->d_window = nullptr;
+      IU_CUDA(e, cudaMalloc(&e->d_window, (size_t)n * 4));
+    } else {
+      IU_CUDA(e, cudaStreamSynchronize(e->stream));
+    }
+    e->window_host.assign(g1d_host, g1d_host + n);
+    IU_CUDA(e, cudaMemcpyAsync(e->d_window, e->window_host.data(), (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  *out = e->d_window;
+  return IU_OK;
+}
+
+int iu_engine_reduce_planes(iu_engine* e, const float* p0, const float* p1, const float* p2, const int* order, int n_axes,
+                            int n, int t, int z0, int zoff, int zcount, int num_classes, const float* g1d_host,
+                            float gmax, float lo, uint8_t* out_u8, uint8_t* out_labels, float* out_mean, unsigned flags) {
   int rc;
   DeviceGuard guard;
   if (!check_engine(e, false, &rc, &guard)) return rc;
   if (!order || n_axes < 1 || n_axes > 3 || n < 1 || t < 1 || z0 < 0 || z0 + t > n || num_classes < 1 ||
-      num_classes > 10)
+      num_classes > 10 || zoff < 0 || zcount < 1 || zoff + zcount > t)
     return e->fail(IU_ERR_INVALID, "reduce: bad arguments");
   ReduceArgs a;
   memset(&a, 0, sizeof(a));
@@ -1453,34 +1479,28 @@ int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float
   a.n = n;
   a.t = t;
   a.z0 = z0;
+  a.zoff = zoff;
+  a.zcount = zcount;
   a.num_classes = num_classes;
   a.gmax = gmax;
   a.lo = lo;
   a.out_u8 = out_u8;
   a.out_labels = out_labels;
   a.out_mean = out_mean;
-  float* g_dev = nullptr;
-  if (g1d_host) {
-    rc = scratch_get(e, (size_t)n * 4, (void**)&g_dev);
-    if (rc != IU_OK) return rc;
-    cudaError_t ce = cudaMemcpyAsync(g_dev, g1d_host, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream);
-    if (ce != cudaSuccess) {
-      scratch_put(e, g_dev);
-      return e->cuda_fail(ce, "cudaMemcpyAsync(window)");
-    }
-  }
-  a.g1d = g_dev;
+  if ((rc = window_on_device(e, g1d_host, n, &a.g1d)) != IU_OK) return rc;
   prof_begin(e, IU_PROF_REDUCE);
   cudaError_t ce = launch_reduce(a, e->stream);
   prof_end(e);
   e->launches += 1;
-  if (g_dev) {
-    // the window table is tiny; wait so the scratch block can be handed out again safely
-    cudaStreamSynchronize(e->stream);
-    scratch_put(e, g_dev);
-  }
   if (ce != cudaSuccess) return e->cuda_fail(ce, "launch reduce");
   return finish(e, flags);
+}
+
+int iu_engine_reduce(iu_engine* e, const float* p0, const float* p1, const float* p2, const int* order, int n_axes,
+                     int n, int t, int z0, int num_classes, const float* g1d_host, float gmax, float lo,
+                     uint8_t* out_u8, uint8_t* out_labels, float* out_mean, unsigned flags) {
+  return iu_engine_reduce_planes(e, p0, p1, p2, order, n_axes, n, t, z0, 0, t, num_classes, g1d_host, gmax, lo, out_u8,
+                                 out_labels, out_mean, flags);
 }
 
 int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n, const int* axes, int n_axes,

@@ -98,7 +98,7 @@ def exchange_strips(slab, axes, group=None):
 
 
 def predict_volume_sharded(engine, volume=None, axes=(0, 1, 2), window=None, want_u8=True, want_labels=True,
-                           want_mean=False, group=None, slab=None):
+                           want_mean=False, group=None, slab=None, host_u8=None, host_labels=None):
     """Predict this rank's z-slab of a cubic volume of edge N.
 
     engine : an `Engine` (or any object with `predict_slices`, `reduce`, `auto_batch`, `num_classes`, `device`)
@@ -106,6 +106,9 @@ def predict_volume_sharded(engine, volume=None, axes=(0, 1, 2), window=None, wan
              off-slab axes are exchanged between the ranks (uint8 all-to-all);
     volume : alternatively the WHOLE volume `[N,N,N]`, identical on every rank (device tensor or numpy): every rank
              reads its slab and strips out of it in place, no input exchange.
+    host_u8 / host_labels : optional (pinned) host tensors `[T,N,N,C]` / `[T,N,N]`: the slab's results are also
+             copied there, part by part -- axis 0 (always computed last) runs one network pass at a time, each pass's z
+             range is reduced as soon as it is predicted and copied out on a side stream under the next pass.
     Returns dict(z0, t, u8=[T,N,N,C] uint8, labels=[T,N,N] uint8, mean=[T,N,N,C] fp32) of device tensors.
     """
     world = dist.get_world_size(group)
@@ -140,6 +143,7 @@ def predict_volume_sharded(engine, volume=None, axes=(0, 1, 2), window=None, wan
     z0 = rank * t
 
     probs, in_flight, keep = {}, [], []
+    pipelined = (host_u8 is not None or host_labels is not None) and 0 in axes and dev.type == "cuda"
     _order(engine, "wait_torch")                  # uploads / strip exchange queued on torch's stream come first
     # the off-slab axes run first so that their last exchanges overlap with axis 0's network passes; the order in
     # which axes are COMPUTED does not enter the arithmetic (K4 adds the buffers in the caller's order)
@@ -147,7 +151,8 @@ def predict_volume_sharded(engine, volume=None, axes=(0, 1, 2), window=None, wan
         src, off, strides = sources[axis]
         if axis == 0:
             probs[0] = torch.empty((t, n, n, c), dtype=torch.float32, device=dev)
-            engine.predict_slices(src, off, t, n, n, strides, probs[0], asynchronous=True, sync=False)
+            if not pipelined:
+                engine.predict_slices(src, off, t, n, n, strides, probs[0], asynchronous=True, sync=False)
             continue
         dst = torch.empty((n, t, n, c), dtype=torch.float32, device=dev)     # [y | x][z local][col][C]
         probs[axis] = dst
@@ -170,31 +175,58 @@ def predict_volume_sharded(engine, volume=None, axes=(0, 1, 2), window=None, wan
             outs = [dst[g * t + s0:g * t + s0 + cnt] for g in range(world)]
             pending[k % 2] = _exchange(outs, list(buf.unbind(0)), group, rank, world)
             in_flight.append(pending[k % 2])
-    for w in in_flight:
-        _wait(w)
-    _order(engine, "wait_torch")
     out = dict(z0=z0, t=t)
-    out["u8"] = torch.empty((t, n, n, c), dtype=torch.uint8, device=dev) if want_u8 else None
-    out["labels"] = torch.empty((t, n, n), dtype=torch.uint8, device=dev) if want_labels else None
+    out["u8"] = torch.empty((t, n, n, c), dtype=torch.uint8, device=dev) if (want_u8 or host_u8 is not None) else None
+    out["labels"] = torch.empty((t, n, n), dtype=torch.uint8, device=dev) if (want_labels or host_labels is not None) else None
     out["mean"] = torch.empty((t, n, n, c), dtype=torch.float32, device=dev) if want_mean else None
-    engine.reduce(probs, list(axes), n, t=t, z0=z0, window=window, out_u8=out["u8"], out_labels=out["labels"],
-                  out_mean=out["mean"])
+    if not pipelined:
+        for w in in_flight:
+            _wait(w)
+        _order(engine, "wait_torch")
+        engine.reduce(probs, list(axes), n, t=t, z0=z0, window=window, out_u8=out["u8"], out_labels=out["labels"],
+                      out_mean=out["mean"])
+        if host_u8 is not None:
+            host_u8.copy_(out["u8"], non_blocking=True)
+        if host_labels is not None:
+            host_labels.copy_(out["labels"], non_blocking=True)
+        if host_u8 is not None or host_labels is not None:
+            torch.cuda.current_stream(dev).synchronize()
+        return out
+    # ---- axis 0 one network pass at a time; each pass's planes are reduced and copied out under the next pass
+    src, off, strides = sources[0]
+    chunk = max(1, min(t, int(engine.auto_batch(n, n, t))))
+    copy_stream = torch.cuda.Stream(device=dev)
+    ext = engine._ext_stream()
+    for k, s0 in enumerate(range(0, t, chunk)):
+        cnt = min(chunk, t - s0)
+        engine.predict_slices(src, off + s0 * strides[0], cnt, n, n, strides, probs[0], slice_offset=s0, slice_total=t,
+                              asynchronous=True, sync=False)
+        if k == 0:                                # every off-slab exchange must have landed before the first reduce
+            for w in in_flight:
+                _wait(w)
+            _order(engine, "wait_torch")
+        engine.reduce(probs, list(axes), n, t=t, z0=z0, window=window, out_u8=out["u8"], out_labels=out["labels"],
+                      out_mean=out["mean"], asynchronous=True, zoff=s0, zcount=cnt, sync=False)
+        copy_stream.wait_event(ext.record_event())
+        with torch.cuda.stream(copy_stream):
+            if host_u8 is not None:
+                host_u8[s0:s0 + cnt].copy_(out["u8"][s0:s0 + cnt], non_blocking=True)
+            if host_labels is not None:
+                host_labels[s0:s0 + cnt].copy_(out["labels"][s0:s0 + cnt], non_blocking=True)
+    engine.synchronize()
+    copy_stream.synchronize()
     return out
 
 
 def predict_slab_from_host(engine, slab_host, axes=(0, 1, 2), window=None, out_u8=None, out_labels=None, group=None):
     """End-to-end form of `predict_volume_sharded` for host data: `slab_host` is this rank's `[T,N,N]` part of the
     volume in (pinned) host memory; the uint8 probabilities / labels of the slab are copied into the (pinned) host
-    tensors `out_u8` `[T,N,N,C]` / `out_labels` `[T,N,N]`.  Per rank N^3/G bytes go up and (C+1) N^3/G come back."""
+    tensors `out_u8` `[T,N,N,C]` / `out_labels` `[T,N,N]`, overlapped with axis 0's network passes.  Per rank N^3/G
+    bytes go up and (C+1) N^3/G come back."""
     dev = engine.device
     slab = torch.as_tensor(slab_host).to(dev, non_blocking=True)
-    res = predict_volume_sharded(engine, slab=slab, axes=axes, window=window, want_u8=out_u8 is not None,
-                                 want_labels=out_labels is not None, group=group)
-    if out_u8 is not None:
-        out_u8.copy_(res["u8"], non_blocking=True)
-    if out_labels is not None:
-        out_labels.copy_(res["labels"], non_blocking=True)
-    torch.cuda.current_stream(dev).synchronize()
+    res = predict_volume_sharded(engine, slab=slab, axes=axes, window=window, want_u8=False, want_labels=False,
+                                 group=group, host_u8=out_u8, host_labels=out_labels)
     return res["z0"], res["t"]
 
 

@@ -274,20 +274,23 @@ class Engine:
         return out
 
     def reduce(self, probs, order, n, t=None, z0=0, window=None, out_u8=None, out_labels=None, out_mean=None,
-               asynchronous=False):
+               asynchronous=False, zoff=0, zcount=None, sync=True):
         """K4.  `probs`: dict axis -> device fp32 tensor; `order`: accumulation order (`predict.py:87`);
-        `window`: None or (g1d, gmax, lo) from `gaussian_window_1d`."""
+        `window`: None or (g1d, gmax, lo) from `gaussian_window_1d`; `zoff` / `zcount`: reduce only these planes of the
+        slab; `sync=False`: the caller orders the streams itself."""
         t = n if t is None else t
+        zcount = t - zoff if zcount is None else zcount
         ptrs = [ctypes.c_void_p(probs[a].data_ptr()) if a in probs and probs[a] is not None else None
                 for a in (0, 1, 2)]
         c_order = (ctypes.c_int * len(order))(*[int(a) for a in order])
         g, gmax, lo = (None, 1.0, 0.0) if window is None else window
         gp, _g = _ptr(g)
         with self._lock:
-            self._sync_torch(*[p for p in probs.values() if p is not None], out_u8, out_labels, out_mean)
-            self._check(self._lib.iu_engine_reduce(
-                self._h, ptrs[0], ptrs[1], ptrs[2], c_order, len(order), int(n), int(t), int(z0),
-                int(self.num_classes), gp, float(gmax), float(lo), _ptr(out_u8)[0], _ptr(out_labels)[0],
+            if sync:
+                self._sync_torch(*[p for p in probs.values() if p is not None], out_u8, out_labels, out_mean)
+            self._check(self._lib.iu_engine_reduce_planes(
+                self._h, ptrs[0], ptrs[1], ptrs[2], c_order, len(order), int(n), int(t), int(z0), int(zoff),
+                int(zcount), int(self.num_classes), gp, float(gmax), float(lo), _ptr(out_u8)[0], _ptr(out_labels)[0],
                 _ptr(out_mean)[0], _lib.FLAG_ASYNC if asynchronous else 0))
 
     def predict_volume(self, volume, axes=(0, 1, 2), window=None, out_u8=None, out_labels=None, out_mean=None):

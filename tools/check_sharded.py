@@ -52,6 +52,20 @@ def main():
                 print(f"edge {n} classes {c} world {world} input {mode} exchange chunks {chunks}: slabs bit-identical on "
                       f"every rank = {bool(flag.item())}, gathered volume identical = {whole}", flush=True)
                 ok = ok and bool(flag.item()) and whole
+        # end-to-end form: pinned host slab in, pinned host results out, axis 0 reduced and copied out part by part
+        h_u8 = torch.empty((t, n, n, c), dtype=torch.uint8).pin_memory()
+        h_lab = torch.empty((t, n, n), dtype=torch.uint8).pin_memory()
+        with eng.limit_batch(max_batch):
+            iud.predict_slab_from_host(eng, vol[rank * t:(rank + 1) * t].cpu().pin_memory(), axes=(0, 1, 2), window=window,
+                                       out_u8=h_u8, out_labels=h_lab)
+        same = torch.equal(h_u8, want_u8[rank * t:(rank + 1) * t].cpu()) and \
+            torch.equal(h_lab, want_lab[rank * t:(rank + 1) * t].cpu())
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"edge {n} classes {c} world {world} host slab -> host results (pipelined tail): bit-identical on "
+                  f"every rank = {bool(flag.item())}", flush=True)
+            ok = ok and bool(flag.item())
     if rank == 0:
         print("SHARDED_CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()
