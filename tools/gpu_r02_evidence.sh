@@ -17,7 +17,7 @@ ncu -i $O/r02_full_pass.ncu-rep --page raw --csv > $O/r02_full_pass_raw.csv 2>/d
 python tools/ncu_table.py $O/r02_full_pass_raw.csv > $O/r02_ncu_full_conv_pass.txt 2>&1; tail -4 $O/r02_ncu_full_conv_pass.txt
 # HBM-bound kernels of a 256^3 volume (second prediction = warm): gather x3 orientations, reduce, pool, stem
 python tools/profile_volume.py > $O/pv_plain.log 2>&1 &&
-ncu --set full --clock-control none -k regex:'gather_|reduce_|maxpool|conv_stem' -s 13 -c 13 -o $O/r02_full_hbm \
+ncu --set full --clock-control none -k regex:'gather_|reduce_|maxpool|conv_stem' -s 10 -c 10 -o $O/r02_full_hbm \
     python tools/profile_volume.py > $O/ncu_full_hbm.log 2>&1; echo "ncu hbm rc=$?"
 ncu -i $O/r02_full_hbm.ncu-rep --page raw --csv > $O/r02_full_hbm_raw.csv 2>/dev/null; rm -f $O/r02_full_hbm.ncu-rep
 python tools/ncu_table.py $O/r02_full_hbm_raw.csv > $O/r02_ncu_full_hbm_kernels.txt 2>&1; cat $O/r02_ncu_full_hbm_kernels.txt
