@@ -276,7 +276,8 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
     }
     if (a.blend_pred != nullptr) {
       if (z >= a.l0[0] && z < a.l1[0] && y >= a.l0[1] && y < a.l1[1] && x >= a.l0[2] && x < a.l1[2]) {
-        const size_t g = ((size_t)(a.b0[0] + z) * a.gh + (a.b0[1] + y)) * a.gw + (a.b0[2] + x);
+        const int gz = a.gd_ring > 0 ? (a.b0[0] + z) % a.gd_ring : a.b0[0] + z;
+        const size_t g = ((size_t)gz * a.gh + (a.b0[1] + y)) * a.gw + (a.b0[2] + x);
         float acc[C];
         load_classes<C, false>(a.blend_pred + g * C, acc);
 #pragma unroll

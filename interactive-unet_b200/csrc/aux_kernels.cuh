@@ -49,6 +49,8 @@ struct ReduceArgs {
   float* blend_pred;    // [gd][gh][gw][C]
   float* blend_weight;  // [gd][gh][gw]
   int gd, gh, gw;
+  int gd_ring;          // > 0: the accumulators hold only gd_ring z planes, plane z of the volume lives at z % gd_ring
+                        // (the tiled mode streams finished z ranges out instead of holding the whole volume in fp32)
   int b0[3];            // volume coordinates of the block's voxel (0,0,0); may be negative (padding)
   int l0[3], l1[3];     // local crop of the block that lies inside the volume
 };

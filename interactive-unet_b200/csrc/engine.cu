@@ -1688,8 +1688,15 @@ int iu_engine_predict_tiled(iu_engine* e, const uint8_t* volume, int d, int h, i
   const int c = e->num_classes;
   const size_t vox = (size_t)d * h * w, bvox = (size_t)s * s * s;
   std::vector<void*> held;
+  std::vector<cudaEvent_t> events;  // one per z range handed to the copy stream
+  auto drop_events = [&]() {
+    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+    events.clear();
+  };
   auto release = [&]() {
     cudaStreamSynchronize(e->stream);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    drop_events();
     for (void* p : held) scratch_put(e, p);
   };
   auto grab = [&](size_t bytes, void** out) {
@@ -1717,19 +1724,74 @@ int iu_engine_predict_tiled(iu_engine* e, const uint8_t* volume, int d, int h, i
     IU_TILED_CUDA(cudaMemcpyAsync(staged, volume, vox, cudaMemcpyHostToDevice, e->stream), "cudaMemcpyAsync(volume)");
     vol_dev = (const uint8_t*)staged;
   }
+  // The fp32 accumulators of predict.py:181-198 (`pred`, `weight`; on disk in the reference) cover a RING of z planes,
+  // not the volume: blocks arrive layer by layer in z (the reference's nested i, j, k order), so once a layer's first
+  // block starts at plane c0 every plane below c0 is final -- it is normalised, written to the uint8 output (and copied
+  // to the host on a second stream) and its ring planes are zeroed for the next layer.  One block edge of planes
+  // suffices; a caller whose blocks are not ordered by z gets a ring as deep as the volume (no early hand-back).
+  bool z_ordered = true;
+  for (int b = 1; b < n_blocks; ++b) z_ordered &= origins[3 * b] >= origins[3 * (b - 1)];
+  const int zring = z_ordered ? std::min(d, s) : d;
+  const size_t plane = (size_t)h * w;
   float *pred = nullptr, *weight = nullptr, *g_dev = nullptr;
   uint8_t* block = nullptr;
   float* p[3] = {nullptr, nullptr, nullptr};
-  IU_TILED_TRY(grab(vox * c * 4, (void**)&pred));
-  IU_TILED_TRY(grab(vox * 4, (void**)&weight));
+  IU_TILED_TRY(grab((size_t)zring * plane * c * 4, (void**)&pred));
+  IU_TILED_TRY(grab((size_t)zring * plane * 4, (void**)&weight));
   IU_TILED_TRY(grab(bvox, (void**)&block));
   IU_TILED_TRY(grab((size_t)s * 4, (void**)&g_dev));
   for (int i = 0; i < n_axes; ++i) IU_TILED_TRY(grab(bvox * c * 4, (void**)&p[axes[i]]));
-  IU_TILED_CUDA(cudaMemsetAsync(pred, 0, vox * c * 4, e->stream), "cudaMemsetAsync(pred)");
-  IU_TILED_CUDA(cudaMemsetAsync(weight, 0, vox * 4, e->stream), "cudaMemsetAsync(weight)");
+  const bool u8_dev = out_u8 && is_device_ptr(out_u8), lab_dev = out_labels && is_device_ptr(out_labels);
+  uint8_t *d_u8 = out_u8, *d_lab = out_labels;
+  if (out_u8 && !u8_dev) IU_TILED_TRY(grab(vox * c, (void**)&d_u8));
+  if (out_labels && !lab_dev) IU_TILED_TRY(grab(vox, (void**)&d_lab));
+  const bool to_host = (out_u8 && !u8_dev) || (out_labels && !lab_dev);
+  if (to_host && !e->copy_stream)
+    IU_TILED_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+  IU_TILED_CUDA(cudaMemsetAsync(pred, 0, (size_t)zring * plane * c * 4, e->stream), "cudaMemsetAsync(pred)");
+  IU_TILED_CUDA(cudaMemsetAsync(weight, 0, (size_t)zring * plane * 4, e->stream), "cudaMemsetAsync(weight)");
   IU_TILED_CUDA(cudaMemcpyAsync(g_dev, g1d_host, (size_t)s * 4, cudaMemcpyHostToDevice, e->stream), "cudaMemcpyAsync(window)");
+  // planes [za, zb) are final: normalise (predict.py:252-255), hand the ring planes back, copy the range out
+  auto finish_planes = [&](int za, int zb) -> cudaError_t {
+    cudaError_t ce = cudaSuccess;
+    for (int z = za; z < zb && ce == cudaSuccess;) {
+      const int r0 = z % zring;
+      const int cnt = std::min(zb - z, zring - r0);        // contiguous in the ring
+      const size_t vx = (size_t)cnt * plane;
+      ce = launch_finalise(pred + (size_t)r0 * plane * c, weight + (size_t)r0 * plane, vx, c,
+                           d_u8 ? d_u8 + (size_t)z * plane * c : nullptr, d_lab ? d_lab + (size_t)z * plane : nullptr, e->stream);
+      e->launches += 1;
+      if (ce == cudaSuccess) ce = cudaMemsetAsync(pred + (size_t)r0 * plane * c, 0, vx * c * 4, e->stream);
+      if (ce == cudaSuccess) ce = cudaMemsetAsync(weight + (size_t)r0 * plane, 0, vx * 4, e->stream);
+      z += cnt;
+    }
+    if (ce == cudaSuccess && to_host && zb > za) {
+      cudaEvent_t ev = nullptr;
+      ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (ce != cudaSuccess) return ce;
+      events.push_back(ev);
+      ce = cudaEventRecord(ev, e->stream);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(e->copy_stream, ev, 0);
+      const size_t off = (size_t)za * plane, len = (size_t)(zb - za) * plane;
+      if (ce == cudaSuccess && out_u8 && !u8_dev)
+        ce = cudaMemcpyAsync(out_u8 + off * c, d_u8 + off * c, len * c, cudaMemcpyDeviceToHost, e->copy_stream);
+      if (ce == cudaSuccess && out_labels && !lab_dev)
+        ce = cudaMemcpyAsync(out_labels + off, d_lab + off, len, cudaMemcpyDeviceToHost, e->copy_stream);
+    }
+    return ce;
+  };
+  int zlo = 0;                                             // first plane that is not final yet
   for (int b = 0; b < n_blocks; ++b) {                     // the reference's block order (predict.py:235)
     const int i0 = origins[3 * b], j0 = origins[3 * b + 1], k0 = origins[3 * b + 2];
+    if (z_ordered && std::min(std::max(i0, 0), d) > zlo) {
+      const int c0 = std::min(std::max(i0, 0), d);
+      cudaError_t ce = finish_planes(zlo, c0);
+      if (ce != cudaSuccess) {
+        release();
+        return e->cuda_fail(ce, "finalise (streamed z range)");
+      }
+      zlo = c0;
+    }
     IU_TILED_CUDA(launch_extract_block(vol_dev, d, h, w, i0, j0, k0, s, block, e->stream), "launch extract_block");
     e->launches += 1;
     for (int i = 0; i < n_axes; ++i)
@@ -1751,6 +1813,7 @@ int iu_engine_predict_tiled(iu_engine* e, const uint8_t* volume, int d, int h, i
     a.gd = d;
     a.gh = h;
     a.gw = w;
+    a.gd_ring = zring;
     const int org[3] = {i0, j0, k0}, dims[3] = {d, h, w};
     for (int k = 0; k < 3; ++k) {
       a.b0[k] = org[k];
@@ -1763,18 +1826,22 @@ int iu_engine_predict_tiled(iu_engine* e, const uint8_t* volume, int d, int h, i
     e->launches += 1;
     IU_TILED_CUDA(ce, "launch reduce (blend)");
   }
-  const bool u8_dev = out_u8 && is_device_ptr(out_u8), lab_dev = out_labels && is_device_ptr(out_labels);
-  uint8_t *d_u8 = out_u8, *d_lab = out_labels;
-  if (out_u8 && !u8_dev) IU_TILED_TRY(grab(vox * c, (void**)&d_u8));
-  if (out_labels && !lab_dev) IU_TILED_TRY(grab(vox, (void**)&d_lab));
-  IU_TILED_CUDA(launch_finalise(pred, weight, vox, c, d_u8, d_lab, e->stream), "launch finalise");
-  e->launches += 1;
-  if (out_u8 && !u8_dev) IU_TILED_CUDA(cudaMemcpyAsync(out_u8, d_u8, vox * c, cudaMemcpyDeviceToHost, e->stream), "copy u8");
-  if (out_labels && !lab_dev) IU_TILED_CUDA(cudaMemcpyAsync(out_labels, d_lab, vox, cudaMemcpyDeviceToHost, e->stream), "copy labels");
+  {
+    cudaError_t ce = finish_planes(zlo, d);
+    if (ce != cudaSuccess) {
+      release();
+      return e->cuda_fail(ce, "finalise");
+    }
+  }
 #undef IU_TILED_TRY
 #undef IU_TILED_CUDA
-  (void)flags;  // host outputs and the scratch hand-back need the stream drained: always synchronous
+  (void)flags;  // host outputs and the scratch hand-back need the streams drained: always synchronous
   cudaError_t ce = cudaStreamSynchronize(e->stream);
+  if (to_host) {
+    const cudaError_t ce2 = cudaStreamSynchronize(e->copy_stream);
+    if (ce == cudaSuccess) ce = ce2;
+  }
+  drop_events();
   for (void* q : held) scratch_put(e, q);
   scratch_trim(e);
   if (ce != cudaSuccess) return e->cuda_fail(ce, "predict_tiled");

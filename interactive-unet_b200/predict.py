@@ -178,11 +178,13 @@ def get_shard_coordinates(volume_shape, shard_size=128):
 
 def tiled_device_bytes(shape, input_size, num_classes, n_axes=3, volume_on_device=True, out_on_device=True):
     """Device bytes the tiled mode holds for a `[D,H,W]` volume beyond what the caller already keeps there: the fp32
-    `pred` / `weight` accumulators of `predict.py:181-198` (in HBM here, on disk in the reference), the uint8 outputs
-    and the volume itself when they arrive from / go to the host, one block and its per-axis probabilities."""
+    `pred` / `weight` accumulators of `predict.py:181-198` (on disk in the reference; here a ring of `input_size` z
+    planes in HBM -- finished z ranges are normalised and handed out while later blocks are still being predicted), the
+    uint8 outputs and the volume itself when they arrive from / go to the host, one block and its per-axis probabilities."""
     vox = int(np.prod(shape, dtype=np.int64))
     bvox = int(input_size) ** 3
-    total = vox * (4 * num_classes + 4) + bvox * (1 + 4 * num_classes * n_axes)
+    ring = min(int(shape[0]), int(input_size)) * int(shape[1]) * int(shape[2])
+    total = ring * (4 * num_classes + 4) + bvox * (1 + 4 * num_classes * n_axes)
     if not volume_on_device:
         total += vox
     if not out_on_device:
@@ -191,8 +193,9 @@ def tiled_device_bytes(shape, input_size, num_classes, n_axes=3, volume_on_devic
 
 
 def _check_tiled_fits(eng, shape, input_size, num_classes, n_axes, volume_on_device, out_on_device):
-    """The reference streams blocks through on-disk accumulators and handles any volume size; this engine keeps them
-    in HBM.  Fail before allocating anything, with the numbers, rather than with an allocator error half way."""
+    """The reference streams blocks through on-disk accumulators and handles any volume size; this engine keeps a ring
+    of `input_size` planes of them in HBM plus the uint8 volume and result.  Fail before allocating anything, with the
+    numbers, rather than with an allocator error half way."""
     need = tiled_device_bytes(shape, input_size, num_classes, n_axes, volume_on_device, out_on_device)
     need += eng.workspace_bytes(eng.auto_batch(input_size, input_size, input_size), input_size, input_size)
     free, _total = torch.cuda.mem_get_info(eng.device)
@@ -200,9 +203,10 @@ def _check_tiled_fits(eng, shape, input_size, num_classes, n_axes, volume_on_dev
     if need > avail:
         raise RuntimeError(
             f"CUDA out of memory: predicting a {shape[0]}x{shape[1]}x{shape[2]} volume in the tiled mode keeps "
-            f"{need / 2**30:.1f} GiB on the device ({4 * num_classes + 4} B per voxel of fp32 accumulators), "
-            f"{avail / 2**30:.1f} GiB are available; split the volume (for example into z ranges that overlap by "
-            f"input_size * overlap) and predict the parts separately")
+            f"{need / 2**30:.1f} GiB on the device (the uint8 volume and result, and {4 * num_classes + 4} B per voxel "
+            f"of fp32 accumulators for {min(shape[0], input_size)} z planes), {avail / 2**30:.1f} GiB are available; "
+            f"split the volume (for example into z ranges that overlap by input_size * overlap) and predict the parts "
+            f"separately")
 
 
 def predict_volume_array(model, volume, input_size=None, num_classes=2, overlap=0.25, batch_size=None,

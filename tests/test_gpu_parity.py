@@ -466,6 +466,35 @@ def test_tiled_blend_matches_reference_predict_volumes_golden(dev, iu, golden_di
     assert np.array_equal(out.cpu().numpy(), g["out_u8"])
 
 
+def test_tiled_mode_streams_z_ranges_bit_identically(dev, fitted, iu):
+    """`iu_engine_predict_tiled` keeps its fp32 accumulators in a ring of `input_size` z planes and hands finished z
+    ranges out while later block layers are still being predicted: on a tall volume (five block layers, the ring wraps
+    several times) the result must equal, bit for bit, the same blocks blended into whole-volume accumulators with the
+    single-step entry points (extract_block -> predict_axis -> blend_block -> finalise), for device and host outputs."""
+    from oracle import synth
+    _, model = fitted[2]
+    eng = model.engine()
+    s, c = 64, 2
+    vol = np.tile(synth.blob_volume(64, 33)[0], (4, 2, 1))[:230, :80, :64].copy()
+    vol_d = torch.from_numpy(vol).to(dev)
+    _, padded, _ = iu.predict.get_block_coordinates(np.array(vol.shape), input_size=s, overlap=0.25)
+    assert len(np.unique(padded[:, 0])) >= 5
+    window = iu.gaussian_window_1d(s)
+    pred = torch.zeros(vol.shape + (c,), dtype=torch.float32, device=dev)
+    weight = torch.zeros(vol.shape, dtype=torch.float32, device=dev)
+    for p in padded:
+        block = eng.extract_block(vol_d, p[:3], s)
+        probs = {a: eng.predict_axis(block, a) for a in (0, 1, 2)}
+        eng.blend_block(probs, [0, 1, 2], s, window, pred, weight, p[:3])
+    want_u8 = torch.empty(vol.shape + (c,), dtype=torch.uint8, device=dev)
+    want_lab = torch.empty(vol.shape, dtype=torch.uint8, device=dev)
+    eng.finalise(pred, weight, out_u8=want_u8, out_labels=want_lab)
+    got_u8, got_lab = iu.predict.predict_volume_array(model, vol_d, input_size=s, num_classes=c, return_labels=True)
+    assert torch.equal(got_u8, want_u8) and torch.equal(got_lab, want_lab)
+    host_u8, host_lab = iu.predict.predict_volume_array(model, vol, input_size=s, num_classes=c, return_labels=True)
+    assert np.array_equal(host_u8, want_u8.cpu().numpy()) and np.array_equal(host_lab, want_lab.cpu().numpy())
+
+
 def test_tiled_prediction_matches_reference_algorithm(dev, fitted, iu):
     """Drop-in tiled `predict_volume_array` (non-cubic volume, input_size 64) vs the port of predict.py:201,235-256
     driven by the fp32 oracle network; host and device entries agree bit for bit."""
@@ -859,7 +888,9 @@ def test_tiled_mode_refuses_volumes_that_cannot_fit(dev, fitted, iu):
     from interactive_unet_b200 import predict as P
     _, model = fitted[2]
     with pytest.raises(RuntimeError, match="out of memory.*split the volume"):
-        P._check_tiled_fits(model.engine(), (4096, 4096, 4096), 256, 2, 3, True, True)
+        P._check_tiled_fits(model.engine(), (8192, 8192, 8192), 256, 2, 3, False, False)
+    # the accumulators are a ring of input_size planes: a tall volume needs no more of them than a flat one
+    assert P.tiled_device_bytes((4096, 512, 512), 256, 2) == P.tiled_device_bytes((256, 512, 512), 256, 2)
     P._check_tiled_fits(model.engine(), (512, 512, 384), 256, 2, 3, False, False)
 
 
