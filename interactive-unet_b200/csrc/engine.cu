@@ -143,6 +143,8 @@ struct iu_engine {
   uint64_t use_clock = 0;
   int use_graph = 1;         // env IU_GRAPH=0: never capture the single-batch forward
   int conv_chain = 1;        // env IU_CONV_CHAIN=0: decoder block 4 + head as three separate row-folded launches
+  int conv_small_bn = 1;     // env IU_CONV_SMALL_BN=0: keep the wide Cout tiles even when they leave most SMs idle
+  int num_sms = 148;
   int conv_pair2 = 0;        // env IU_CONV_PAIR2: per-tap kernel on CTA pairs; bit 0: Cout >= 256 layers, bit 1: Cout 128
   std::vector<Scratch> scratch;
   size_t scratch_keep = ~(size_t)0;  // env IU_SCRATCH_KEEP_MB: idle scratch above this is returned to the driver when a
@@ -926,6 +928,19 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
     if (((bn2 == 256 && (e->conv_pair2 & 1)) || (bn2 == 128 && (e->conv_pair2 & 2))) && conv_tc2_applicable(a, bn2))
       return launch_conv_tc2(a, bn2, e->stream);
   }
+  // Latency path: when the wide-tile shapes would give a handful of CTA tiles (one 256^2 slice: 2 pixel tiles in
+  // layer3, 1 in layer4), every CTA streams its whole share of the layer's weights through ONE SM's TMA ring and the
+  // launch takes ~25 us whatever the math.  64-wide Cout tiles spread the same weights over 4x as many SMs.
+  if (e->conv_small_bn && kc == 64 && bn == 128 && a.mode == kEpiBf16 && a.cout % 128 == 0) {
+    const int mtiles = a.tiles_x * a.tiles_y * ((a.batch + a.nb - 1) / a.nb);
+    const int wide = (a.use_bn256 && e->conv_bn256) ? 256 : 128;
+    if (mtiles * (a.cout / wide) * 4 <= e->num_sms) {
+      ConvArgs n = a;
+      n.bmap = a.bmap2;  // the same weights boxed (64, 64)
+      n.use_bn256 = 0;
+      return launch_conv_tc(n, kc, 64, e->stream, 1, 1);
+    }
+  }
   const int bm = (kc == 64 && a.mode == kEpiBf16) ? e->conv_bm : 1;
   // weight multicast across CTA pairs: layers whose Cout is ONE tile (Cout 256 with 256-wide tiles, Cout 128 with
   // paired pixel tiles)
@@ -1075,6 +1090,8 @@ int iu_engine_create(int device, iu_engine** out) {
   if (const char* v = getenv("IU_GRAPH")) e->use_graph = atoi(v);
   if (const char* v = getenv("IU_CONV_CHAIN")) e->conv_chain = atoi(v);
   if (const char* v = getenv("IU_CONV_PAIR2")) e->conv_pair2 = atoi(v);
+  if (const char* v = getenv("IU_CONV_SMALL_BN")) e->conv_small_bn = atoi(v);
+  e->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   if (const char* v = getenv("IU_SCRATCH_KEEP_MB")) e->scratch_keep = (size_t)std::max(0, atoi(v)) << 20;
   if (const char* v = getenv("IU_CONV_DEBUG")) {
     if (atoi(v) != 0 && cudaMalloc(&e->d_debug, 64 * 16 * sizeof(unsigned long long)) == cudaSuccess)
