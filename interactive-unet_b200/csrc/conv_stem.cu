@@ -11,6 +11,12 @@
 //   * one thread issues 2 x 4 tcgen05.mma (M=128, N=64, K=16) into double-buffered TMEM accumulators,
 //   * 8 epilogue warps apply bias + ReLU and store 16-bit NHWC (conv_epilogue.cuh).
 // The [64 x 64] weight tile is loaded once per CTA.  Persistent over the tile list like the other conv kernels.
+//
+// Fused max-pool (`encoder.maxpool`, 3x3 / stride 2 / padding 1): the tile's 16x16 outputs sit in the epilogue's
+// staging buffers anyway (for the TMA store), so the epilogue warps also reduce them to the 9x9 pooled pixels the tile
+// touches.  The 7x7 interior windows lie wholly inside the tile and are stored directly; the windows along the
+// tile's edges also cover a neighbouring tile's last row / column, so both tiles contribute their partial maximum
+// with `red.global.max` on packed 16-bit pairs (post-ReLU values are >= 0, the pooled tensor is zeroed beforehand).
 #include "conv_epilogue.cuh"
 #include "conv_tc.cuh"
 #include "ptx.cuh"
@@ -35,6 +41,8 @@ struct StemArgs {
   CUtensorMap omap;  // 4-D map (64, W/2, H/2, N) over the output, box (64, 8, 16, 1), 128B swizzle: the epilogue's TMA store
   CUtensorMap bmap;  // 2-D map (K = 64, Cout = 64) over the packed weights, box = (64, 64), 128B swizzle
   const float* x;    // [batch][h][w] fp32 in [0, 1]
+  __nv_bfloat16* pool_out;  // optional: the 3x3 / stride-2 / pad-1 max-pool of the output, [batch][h/4][w/4][64], ZEROED
+                            // by the caller before the launch (tiles combine their border windows with red.max)
   int batch, h, w;
   ConvArgs epi;      // epilogue description (mode kEpiBf16, out, relu, fp16, cout = 64, out_h = h / 2, out_w = w / 2)
 };
@@ -186,6 +194,43 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
         tma_store_4d(&s.omap, stg, 0, tx * kStemTileEdge + 8 * j, ty * kStemTileEdge, n);
         bulk_commit();
       }
+      if (s.pool_out != nullptr) {
+        // both groups' halves of the tile are staged: pool the 9 x 9 windows this tile touches, 8 channels per item
+        asm volatile("bar.sync 4, 256;" ::: "memory");
+        const int ph = a.out_h >> 1, pw = a.out_w >> 1;
+        const uint32_t stg_it = stg_base + (it & 1u) * kStemStage;
+        for (int item = (warp - 2) * 32 + lane; item < 81 * 8; item += 256) {
+          const int chunk = item & 7, pp = item >> 3;
+          const int py = pp / 9, px = pp - py * 9;
+          const int gy = ty * (kStemTileEdge / 2) + py, gx = tx * (kStemTileEdge / 2) + px;
+          if (gy >= ph || gx >= pw) continue;
+          const int r_lo = py == 0 ? 0 : 2 * py - 1, r_hi = py == 8 ? 15 : 2 * py + 1;
+          const int c_lo = px == 0 ? 0 : 2 * px - 1, c_hi = px == 8 ? 15 : 2 * px + 1;
+          uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;   // +0.0: identity of max over non-negative values
+          for (int r = r_lo; r <= r_hi; ++r)
+            for (int cc = c_lo; cc <= c_hi; ++cc) {
+              const int cg = cc & 7;
+              const uint32_t src = stg_it + (uint32_t)(cc >> 3) * (2 * kStemStage) + (uint32_t)(r * 8 + cg) * 128u +
+                                   (((uint32_t)chunk ^ (uint32_t)cg) << 4);
+              uint32_t v0, v1, v2, v3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(src));
+              m0 = __vmaxu2(m0, v0);   // unsigned order of the 16-bit patterns == numeric order for values >= 0
+              m1 = __vmaxu2(m1, v1);
+              m2 = __vmaxu2(m2, v2);
+              m3 = __vmaxu2(m3, v3);
+            }
+          uint32_t* dst = reinterpret_cast<uint32_t*>(s.pool_out + (((size_t)n * ph + gy) * pw + gx) * 64 + chunk * 8);
+          if (py >= 1 && py <= 7 && px >= 1 && px <= 7) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(m0, m1, m2, m3);
+          } else if (a.fp16) {
+            asm volatile("red.global.max.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+                         : "memory");
+          } else {
+            asm volatile("red.global.max.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+                         : "memory");
+          }
+        }
+      }
     }
     if (lead) bulk_wait_all();
   } else {
@@ -268,7 +313,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) conv_stem_kernel(const __grid
 }
 
 cudaError_t launch_conv_stem(const CUtensorMap& bmap, const CUtensorMap& omap, const float* x, int batch, int h, int w,
-                             const ConvArgs& epi, cudaStream_t stream) {
+                             const ConvArgs& epi, cudaStream_t stream, __nv_bfloat16* pool_out) {
   static_assert(kStemSmem <= 227 * 1024, "stem kernel exceeds the shared memory of an SM");
   static int configured_dev = -1;
   static int num_sms = 148;
@@ -284,6 +329,7 @@ cudaError_t launch_conv_stem(const CUtensorMap& bmap, const CUtensorMap& omap, c
   s.bmap = bmap;
   s.omap = omap;
   s.x = x;
+  s.pool_out = pool_out;
   s.batch = batch;
   s.h = h;
   s.w = w;

@@ -35,6 +35,10 @@ struct alignas(64) ConvArgs {
   CUtensorMap bmap2;    // the same weights with box = (64, 64): one CTA's half tile in the CTA-pair kernel
   CUtensorMap bmap256;  // the same weights with box = (64, 256): per-tap kernel with BN = 256 (valid when use_bn256)
   int use_bn256;
+  // Latency shapes (a handful of pixel tiles): the same weights boxed (64, small_bn) with small_bn = 64 or 32, so that
+  // the layer's Cout is spread over 2-8x as many CTAs (each streams that much less of the weights); 0 = not planned.
+  CUtensorMap bmap_small;
+  int small_bn;
   // row-folded kernel (conv_row.cu), valid when use_row != 0:
   CUtensorMap bmapf;    // 2-D map (3*sum(cin), 3*Cout_pad) over the fold-packed weights, box = (row KC, 3*Cout_pad)
   CUtensorMap bmapu;    // 2-D map (3*cin0, 4*Cout_pad) over the four-slot weights of an upsampled segment 0,
@@ -127,7 +131,9 @@ cudaError_t launch_conv_chain(const ChainArgs& args, cudaStream_t stream);
 //         k >= 56 are zero), box (64, 64), 128-byte swizzle;  x: fp32 [batch][h][w];
 //   omap: 4-D map (64, w/2, h/2, batch) over the output, box (64, 8, 16, 1), 128-byte swizzle (the epilogue's TMA store);
 //   epi:  epilogue description (mode kEpiBf16, out = [batch][h/2][w/2][64], bias, relu, fp16, cout = 64, out_h, out_w).
+//   pool_out: optional [batch][h/4][w/4][64], zeroed by the caller: the 3x3/s2/p1 max-pool of the output, fused into
+//         the epilogue (interior windows stored, windows shared with a neighbouring tile combined with red.max).
 cudaError_t launch_conv_stem(const CUtensorMap& bmap, const CUtensorMap& omap, const float* x, int batch, int h, int w,
-                             const ConvArgs& epi, cudaStream_t stream);
+                             const ConvArgs& epi, cudaStream_t stream, __nv_bfloat16* pool_out = nullptr);
 
 }  // namespace iu

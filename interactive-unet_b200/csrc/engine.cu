@@ -143,6 +143,8 @@ struct iu_engine {
   uint64_t use_clock = 0;
   int use_graph = 1;         // env IU_GRAPH=0: never capture the single-batch forward
   int conv_chain = 1;        // env IU_CONV_CHAIN=0: decoder block 4 + head as three separate row-folded launches
+  int stem_pool = 0;         // env IU_STEM_POOL=1: max-pool inside the stem's epilogue (measured slower: 9.7 ms against
+                             // 4.1 + 4.3 ms per 512^3 -- 40 % of a tile's pooled pixels go through red.max)
   int conv_small_bn = 1;     // env IU_CONV_SMALL_BN=0: keep the wide Cout tiles even when they leave most SMs idle
   int num_sms = 148;
   int conv_pair2 = 0;        // env IU_CONV_PAIR2: per-tap kernel on CTA pairs; bit 0: Cout >= 256 layers, bit 1: Cout 128
@@ -696,6 +698,16 @@ size_t plan_bytes(const iu_engine* e, int batch_pad, int h, int w) {
   return total;
 }
 
+// Cout tile width for layers whose pixel count gives only a few CTA tiles (the latency path): 0 = keep the default.
+int plan_small_bn(const iu_engine* e, const ConvArgs& a, int kc, int cout_pad) {
+  if (kc != 64 || a.mode != kEpiBf16 || cout_pad % 128) return 0;
+  const long pixels = (long)a.batch * a.out_h * a.out_w;
+  const int mtiles = (int)((pixels + kTileM - 1) / kTileM);
+  if (mtiles * (cout_pad / 64) * 2 <= e->num_sms) return 32;   // even 64-wide tiles would fill under half the SMs
+  if (mtiles * (cout_pad / 128) * 4 <= e->num_sms) return 64;
+  return 0;
+}
+
 // Allocate and describe the workspace of (batch, h, w) in e->plan (which must be empty).
 int build_plan(iu_engine* e, int batch, int h, int w) {
   Plan& p = e->plan;
@@ -751,6 +763,9 @@ int build_plan(iu_engine* e, int batch, int h, int w) {
       free_plan(e);
       return rc;
     }
+    a.mode = L.mode;
+    a.small_bn = plan_small_bn(e, a, L.kc, L.cout_pad);
+    if (a.small_bn && encode_weight_map(e, &a.bmap_small, L.d_w, L.ktot, L.cout_pad, 64, a.small_bn) != IU_OK) a.small_bn = 0;
     a.cout = L.cout;
     a.bias = L.d_b;
     a.residual = L.residual >= 0 ? p.bufs[L.residual] : nullptr;
@@ -922,7 +937,14 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
   if (e->conv_variant == 1) halo = has_up;
   else if (e->conv_variant == 2) halo = applicable;
   else halo = has_up || (applicable && (kc <= 32 || bn <= 64) && a.out_h >= kHaloTile && a.out_w >= kHaloTile);
-  if (halo) return launch_conv_halo(a, kc, bn, e->stream);
+  if (halo) {
+    if (a.small_bn && e->conv_small_bn && a.small_bn <= bn) {
+      ConvArgs n = a;
+      n.bmap = a.bmap_small;
+      return launch_conv_halo(n, kc, a.small_bn, e->stream);
+    }
+    return launch_conv_halo(a, kc, bn, e->stream);
+  }
   if (e->conv_pair2 && kc == 64 && a.mode == kEpiBf16) {
     const int bn2 = (a.use_bn256 && e->conv_bn256) ? 256 : bn;
     if (((bn2 == 256 && (e->conv_pair2 & 1)) || (bn2 == 128 && (e->conv_pair2 & 2))) && conv_tc2_applicable(a, bn2))
@@ -930,16 +952,12 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
   }
   // Latency path: when the wide-tile shapes would give a handful of CTA tiles (one 256^2 slice: 2 pixel tiles in
   // layer3, 1 in layer4), every CTA streams its whole share of the layer's weights through ONE SM's TMA ring and the
-  // launch takes ~25 us whatever the math.  64-wide Cout tiles spread the same weights over 4x as many SMs.
-  if (e->conv_small_bn && kc == 64 && bn == 128 && a.mode == kEpiBf16 && a.cout % 128 == 0) {
-    const int mtiles = a.tiles_x * a.tiles_y * ((a.batch + a.nb - 1) / a.nb);
-    const int wide = (a.use_bn256 && e->conv_bn256) ? 256 : 128;
-    if (mtiles * (a.cout / wide) * 4 <= e->num_sms) {
-      ConvArgs n = a;
-      n.bmap = a.bmap2;  // the same weights boxed (64, 64)
-      n.use_bn256 = 0;
-      return launch_conv_tc(n, kc, 64, e->stream, 1, 1);
-    }
+  // launch takes ~25 us whatever the math.  The plan picked 64- or 32-wide Cout tiles for such layers (plan_small_bn).
+  if (a.small_bn && e->conv_small_bn) {
+    ConvArgs n = a;
+    n.bmap = a.bmap_small;
+    n.use_bn256 = 0;
+    return launch_conv_tc(n, kc, a.small_bn, e->stream, 1, 1);
   }
   const int bm = (kc == 64 && a.mode == kEpiBf16) ? e->conv_bm : 1;
   // weight multicast across CTA pairs: layers whose Cout is ONE tile (Cout 256 with 256-wide tiles, Cout 128 with
@@ -957,12 +975,24 @@ cudaError_t launch_conv(iu_engine* e, const ConvArgs& a, int kc, int bn) {
 // Run the network on the `batch` slices already in plan.x_in; the head writes according to (mode, out, ...).
 int run_network(iu_engine* e, int batch, int head_mode, float* head_out, int slice0, int slice_count, int row_block) {
   Plan& p = e->plan;
-  prof_begin(e, IU_PROF_STEM);
-  IU_CUDA(e, launch_conv_stem(e->stem_bmap, p.stem_omap, p.x_in, batch, p.h, p.w, p.stem_epi, e->stream));
-  prof_end(e);
-  prof_begin(e, IU_PROF_POOL);
-  IU_CUDA(e, launch_maxpool(p.bufs[e->t_f1], batch, p.h / 2, p.w / 2, 64, p.bufs[e->t_p1], e->stream));
-  prof_end(e);
+  if (e->stem_pool) {
+    // fused max-pool: the stem's epilogue pools its own tile; tiles combine their shared border windows with red.max
+    // into the zeroed pooled tensor
+    const size_t pooled = (size_t)batch * (p.h / 4) * (p.w / 4) * 64 * 2;
+    prof_begin(e, IU_PROF_STEM);
+    IU_CUDA(e, cudaMemsetAsync(p.bufs[e->t_p1], 0, pooled, e->stream));
+    IU_CUDA(e, launch_conv_stem(e->stem_bmap, p.stem_omap, p.x_in, batch, p.h, p.w, p.stem_epi, e->stream,
+                                p.bufs[e->t_p1]));
+    prof_end(e);
+    e->launches -= 1;  // one kernel where there were two
+  } else {
+    prof_begin(e, IU_PROF_STEM);
+    IU_CUDA(e, launch_conv_stem(e->stem_bmap, p.stem_omap, p.x_in, batch, p.h, p.w, p.stem_epi, e->stream));
+    prof_end(e);
+    prof_begin(e, IU_PROF_POOL);
+    IU_CUDA(e, launch_maxpool(p.bufs[e->t_f1], batch, p.h / 2, p.w / 2, 64, p.bufs[e->t_p1], e->stream));
+    prof_end(e);
+  }
   e->launches += 2;
   for (size_t i = 0; i < e->convs.size(); ++i) {
     const ConvLayer& L = e->convs[i];
@@ -1091,6 +1121,7 @@ int iu_engine_create(int device, iu_engine** out) {
   if (const char* v = getenv("IU_CONV_CHAIN")) e->conv_chain = atoi(v);
   if (const char* v = getenv("IU_CONV_PAIR2")) e->conv_pair2 = atoi(v);
   if (const char* v = getenv("IU_CONV_SMALL_BN")) e->conv_small_bn = atoi(v);
+  if (const char* v = getenv("IU_STEM_POOL")) e->stem_pool = atoi(v);
   e->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   if (const char* v = getenv("IU_SCRATCH_KEEP_MB")) e->scratch_keep = (size_t)std::max(0, atoi(v)) << 20;
   if (const char* v = getenv("IU_CONV_DEBUG")) {

@@ -1002,3 +1002,30 @@ def test_fp16_range_stress(dev, fitted, iu):
         sat = model(x)
     assert torch.isfinite(sat).all()
     assert torch.allclose(sat.sum(1), torch.ones_like(sat[:, 0]), atol=1e-5)
+
+
+# --------------------------------------------------------------------------- max-pool fused into the stem's epilogue
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("h,w,batch", [(64, 64, 3), (96, 160, 2), (512, 512, 2), (32, 32, 1)])
+def test_stem_fused_maxpool_is_bit_identical(dev, iu, monkeypatch, precision, h, w, batch):
+    """`encoder.maxpool` inside the stem kernel (opt-in, IU_STEM_POOL=1: interior windows stored, windows shared between
+    tiles combined with red.max on packed 16-bit pairs) against the separate pooling kernel: max is exact, so the whole
+    network's output must be the same bits."""
+    from oracle import synth
+    ref = synth.make_model(2)
+    x = torch.rand(batch, 1, h, w, generator=torch.Generator().manual_seed(h + w)).to(dev)
+    outs = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("IU_STEM_POOL", fused)
+        model = iu.UNet(num_classes=2)
+        model.precision = precision
+        model.load_state_dict(ref.state_dict())
+        model = model.to(dev).eval()
+        n0 = model.engine().launch_count()
+        with torch.inference_mode():
+            outs[fused] = model(x).clone()
+            again = model(x)                      # second call: graph capture / replay on the small shapes
+        assert torch.equal(again, outs[fused])
+        outs[fused + "_n"] = model.engine().launch_count() - n0
+    assert torch.equal(outs["1"], outs["0"])
+    assert outs["0_n"] - outs["1_n"] == 2         # one launch fewer per forward, two forwards
