@@ -143,12 +143,19 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
   // staging hand-off between an epilogue group and its store thread: full (4 warp arrivals) / empty (store thread)
   auto stg_full = [&](int g, int b) { return b_full + 48u + 8u * (g * 2 + b); };
   auto stg_empty = [&](int g, int b) { return b_full + 80u + 8u * (g * 2 + b); };
+  auto res_full = [&](int g) { return b_full + 112u + 8u * g; };  // residual row landed in group g's staging buffer
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - raw));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool has_res = a.residual != nullptr;
+  // The residual (ResNet shortcut) is added either by the tensor core -- one more K segment against an identity tile,
+  // gathered like any other source -- or, when `res_tma` is set, by the epilogue: the store thread TMA-loads the
+  // residual row into the output staging buffer (same box, same swizzle as the store), the epilogue adds it to the
+  // accumulator in fp32 and overwrites it in place.  The second form halves the gather volume and drops 4*R MMAs per
+  // block of the Cout-64 layers (layer1's conv2: 172 -> conv1's ~120 us per 74-slice pass).
+  const bool res_tma = a.residual != nullptr && a.res_tma != 0;
+  const bool has_res = a.residual != nullptr && !res_tma;
   constexpr int RES_CHUNKS = CO / KC;    // A stages of the identity (residual) segment
   constexpr int RES_BTILES = CO / KCB;   // its weight tiles
   constexpr int CPB = KCB / KC;          // A chunks per weight tile
@@ -172,6 +179,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         mbar_init(stg_full(g, b), 4);
         mbar_init(stg_empty(g, b), 1);
       }
+    for (int g = 0; g < 2; ++g) mbar_init(res_full(g), 1);
+    if (res_tma) tma_prefetch_desc(&a.rmap);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -412,6 +421,45 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         for (int rb = 0; rb < R / 2; rb += RB) {
           const int r0 = g * (R / 2) + rb;             // first row of this store box
           if (tc.y0 + r0 >= a.out_h) break;            // ragged last block (uniform over the group)
+          if (res_tma) {
+            // residual in the epilogue: the store thread has TMA-loaded the residual row(s) of this box into the
+            // staging buffer (which also says the buffer is free); add in fp32, pack, overwrite in place
+            const uint32_t stg_px = stg_g + px_off;
+            row_warp_wait(res_full(g), nstore & 1u, lane);
+            ++nstore;
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+              const uint32_t taddr = tacc + (uint32_t)((r0 + i) * CO);
+#pragma unroll
+              for (int ch = 0; ch < CO / Cfg::CH; ++ch) {
+                uint32_t acc[Cfg::CH];
+                if constexpr (Cfg::CH == 32) tmem_ld_32x32(taddr + ch * 32, reinterpret_cast<uint32_t(&)[32]>(acc));
+                else tmem_ld_32x16(taddr + ch * 16, reinterpret_cast<uint32_t(&)[16]>(acc));
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < Cfg::CH; j += 8) {
+                  const uint32_t c = (uint32_t)((ch * Cfg::CH + j) / 8);
+                  const uint32_t addr = stg_px + (uint32_t)i * (kRowSeg * CO * 2) + ((c ^ swz) << 4);
+                  uint32_t rv[4], o[4];
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv[0]), "=r"(rv[1]), "=r"(rv[2]), "=r"(rv[3]) : "r"(addr));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 b2 = *reinterpret_cast<const float2*>(bias_s + ch * Cfg::CH + j + 2 * k);
+                    const float2 r2 = unpack16(rv[k], a.fp16);
+                    o[k] = pack16_sat(__uint_as_float(acc[j + 2 * k]) + b2.x + r2.x,
+                                      __uint_as_float(acc[j + 2 * k + 1]) + b2.y + r2.y, a.fp16);
+                    if (a.relu) o[k] = relu16x2(o[k], a.fp16);
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                               : "memory");
+                }
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stg_full(g, 0));
+            continue;
+          }
           // 1. TMEM -> registers -> bias / ReLU / 16-bit pack for the whole box, BEFORE touching the staging buffer:
           //    this part overlaps with the previous box's TMA store still draining
           uint4 pk[RB][CO / 8];
@@ -509,6 +557,18 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         for (int rb = 0; rb < R / 2; rb += RB) {
           const int r0 = g * (R / 2) + rb;
           if (tc.y0 + r0 >= a.out_h) break;
+          if (res_tma) {
+            // the buffer is free (the previous box's store has been read out below): fetch this box's residual rows into
+            // it, then store the finished box from the same place
+            mbar_arrive_expect_tx(res_full(g), Cfg::STG);
+            tma_load_4d(stg_g, &a.rmap, res_full(g), 0, tc.x0, tc.y0 + r0, tc.n);
+            mbar_wait(stg_full(g, 0), nstore & 1u);
+            tma_store_4d(&a.omap, stg_g, 0, tc.x0, tc.y0 + r0, tc.n);
+            bulk_commit();
+            bulk_wait_read_0();
+            ++nstore;
+            continue;
+          }
           const uint32_t sb = NSTG == 2 ? (nstore & 1u) : 0u;
           const uint32_t use = nstore / NSTG;
           mbar_wait(stg_full(g, sb), use & 1u);

@@ -46,6 +46,10 @@ struct alignas(64) ConvArgs {
   CUtensorMap bmapi;    // 2-D map over the [Cout][Cout] identity (residual segment), box = (row KC, Cout)
   CUtensorMap omap;     // 4-D map (Cout, W, H, N) over the output tensor, box = (Cout, 128, store rows, 1): TMA store
   int use_row;
+  // row-folded kernel, Cout 64 with a residual: 4-D map over the RESIDUAL tensor with the output map's box, and
+  // res_tma != 0 to add the residual in the epilogue from a TMA-loaded staging buffer instead of as an identity K segment
+  CUtensorMap rmap;
+  int res_tma;
   ConvSegment seg[2];
   const __nv_bfloat16* src_ptr[2];  // raw pointers of the segment sources (halo kernel: cp.async gathers)
   int nseg;
