@@ -1644,14 +1644,21 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
     a.out_u8 = out_u8 ? d_u8 : nullptr;
     a.out_labels = out_labels ? d_lab : nullptr;
     a.out_mean = out_mean ? d_mean : nullptr;
-    // parts of half an internal batch, run as partial batches on the same activation plan as the other axes
+    // Parts: whole internal batches (full kernel efficiency), except that the LAST batch is split in two so that the
+    // result copy left exposed at the very end is half a batch's worth; all run on the activation plan of the other axes.
     const int plan_batch = auto_batch(e, n, n, n);
-    const int zc = plan_batch >= 64 ? (plan_batch + 1) / 2 : plan_batch;
-    const int kParts = (n + zc - 1) / zc;
+    std::vector<int> part_begin;
+    for (int zs = 0; zs < n;) {
+      part_begin.push_back(zs);
+      const int left = n - zs;
+      zs += (left <= plan_batch && plan_batch >= 64 && left > plan_batch / 2) ? (left + 1) / 2 : std::min(plan_batch, left);
+    }
+    part_begin.push_back(n);
+    const int kParts = (int)part_begin.size() - 1;
     std::vector<cudaEvent_t> done((size_t)kParts, nullptr);
     cudaError_t ce = cudaSuccess;
     auto copy_part = [&](int k) {
-      const int zs = k * zc, cnt = (zs + zc > n ? n - zs : zc);
+      const int zs = part_begin[k], cnt = part_begin[k + 1] - zs;
       const size_t plane = (size_t)n * n, off = (size_t)zs * plane, len = (size_t)cnt * plane;
       cudaError_t r = cudaStreamWaitEvent(e->copy_stream, done[k], 0);
       if (r == cudaSuccess && out_u8 && !u8_dev)
@@ -1663,8 +1670,8 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
       return r;
     };
     int parts = 0;
-    for (int k = 0; k < kParts && k * zc < n && rc == IU_OK && ce == cudaSuccess; ++k, ++parts) {
-      const int zs = k * zc, cnt = (zs + zc > n ? n - zs : zc);
+    for (int k = 0; k < kParts && rc == IU_OK && ce == cudaSuccess; ++k, ++parts) {
+      const int zs = part_begin[k], cnt = part_begin[k + 1] - zs;
       rc = predict_axis_impl(e, vol_dev, dtype, n, 0, zs, cnt, p[0], zs, n, n, IU_FLAG_ASYNC, plan_batch);
       if (rc != IU_OK) break;
       a.zoff = zs;
