@@ -1589,12 +1589,11 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
     return r;
   };
   const void* vol_dev = volume;
-  if (!is_device_ptr(volume)) {
-    void* staged = nullptr;
+  const bool vol_host = !is_device_ptr(volume);
+  void* staged = nullptr;
+  if (vol_host) {
     if ((rc = grab(vox * esz, &staged)) != IU_OK) { release(); return rc; }
-    cudaError_t ce = cudaMemcpyAsync(staged, volume, vox * esz, cudaMemcpyHostToDevice, e->stream);
-    if (ce != cudaSuccess) { release(); return e->cuda_fail(ce, "cudaMemcpyAsync(volume)"); }
-    vol_dev = staged;
+    vol_dev = staged;     // uploaded below, once the schedule is known
   }
   float* p[3] = {nullptr, nullptr, nullptr};
   for (int i = 0; i < n_axes; ++i) {
@@ -1618,11 +1617,6 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
     if (!e->copy_stream) {
       cudaError_t ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
       if (ce != cudaSuccess) { release(); return e->cuda_fail(ce, "cudaStreamCreate(copy)"); }
-    }
-    for (int i = 0; i < n_axes; ++i) {
-      if (axes[i] == 0) continue;
-      rc = iu_engine_predict_axis(e, vol_dev, dtype, n, axes[i], 0, n, p[axes[i]], 0, n, n, IU_FLAG_ASYNC);
-      if (rc != IU_OK) { release(); return rc; }
     }
     float* g_dev = nullptr;
     if (g1d_host) {
@@ -1669,11 +1663,33 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
         r = cudaMemcpyAsync(out_mean + off * c, d_mean + off * c, len * c * 4, cudaMemcpyDeviceToHost, e->copy_stream);
       return r;
     };
+    // Upload: the planes of the FIRST part on the compute stream, the rest on the copy stream under that part's
+    // network passes (axis-0 slices are z planes: part 0 needs only its own); then axis 0 part 0, the other axes, and
+    // the remaining parts of axis 0, each reduced and copied out under the next one.
+    cudaEvent_t uploaded = nullptr;
+    if (vol_host) {
+      const size_t first = (size_t)part_begin[1] * n * n * esz;
+      ce = cudaMemcpyAsync(staged, volume, first, cudaMemcpyHostToDevice, e->stream);
+      if (ce == cudaSuccess && first < vox * esz) {
+        ce = cudaMemcpyAsync(static_cast<char*>(staged) + first, static_cast<const char*>(volume) + first, vox * esz - first,
+                             cudaMemcpyHostToDevice, e->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventRecord(uploaded, e->copy_stream);
+      }
+    }
     int parts = 0;
     for (int k = 0; k < kParts && rc == IU_OK && ce == cudaSuccess; ++k, ++parts) {
       const int zs = part_begin[k], cnt = part_begin[k + 1] - zs;
       rc = predict_axis_impl(e, vol_dev, dtype, n, 0, zs, cnt, p[0], zs, n, n, IU_FLAG_ASYNC, plan_batch);
       if (rc != IU_OK) break;
+      if (k == 0) {
+        if (uploaded) ce = cudaStreamWaitEvent(e->stream, uploaded, 0);
+        for (int i = 0; i < n_axes && rc == IU_OK && ce == cudaSuccess; ++i) {
+          if (axes[i] == 0) continue;
+          rc = iu_engine_predict_axis(e, vol_dev, dtype, n, axes[i], 0, n, p[axes[i]], 0, n, n, IU_FLAG_ASYNC);
+        }
+        if (rc != IU_OK || ce != cudaSuccess) break;
+      }
       a.zoff = zs;
       a.zcount = cnt;
       prof_begin(e, IU_PROF_REDUCE);
@@ -1691,6 +1707,7 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
     cudaError_t ce3 = cudaStreamSynchronize(e->copy_stream);
     for (int k = 0; k < kParts; ++k)
       if (done[k]) cudaEventDestroy(done[k]);
+    if (uploaded) cudaEventDestroy(uploaded);
     for (void* q : held) scratch_put(e, q);
     scratch_trim(e);
     if (rc != IU_OK) return rc;
@@ -1700,6 +1717,10 @@ int iu_engine_predict_volume(iu_engine* e, const void* volume, int dtype, int n,
     return IU_OK;
   }
 
+  if (vol_host) {
+    cudaError_t ce = cudaMemcpyAsync(staged, volume, vox * esz, cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) { release(); return e->cuda_fail(ce, "cudaMemcpyAsync(volume)"); }
+  }
   for (int i = 0; i < n_axes; ++i) {
     rc = iu_engine_predict_axis(e, vol_dev, dtype, n, axes[i], 0, n, p[axes[i]], 0, n, n, IU_FLAG_ASYNC);
     if (rc != IU_OK) { release(); return rc; }
