@@ -16,6 +16,13 @@
 //     of 130 pixels: input row i, filter column kx is the same buffer through a descriptor shifted by
 //     i * pitch + kx * 16 bytes (SBO = 128 B: the eight-pixel core matrices of a row are contiguous).  The 2x nearest
 //     upsample of the decoder (`src = dst >> 1`) and the channel concat are folded into the gather as before;
+//   * Cout-64 layers fed by ONE identity 64-channel tensor (layer1, decoder block 2 conv2) fill the A ring by TMA instead:
+//     a stage is three input rows x 130 pixels in the 128B-swizzled K-major layout (one pixel = one 128-byte row),
+//     and input row j / filter column kx is the stage read through a descriptor whose START ADDRESS is shifted by
+//     (j * 130 + kx) * 128 bytes -- the tensor core applies the swizzle to address bits, so an operand may begin at
+//     any 128-byte row of a swizzled buffer (base offset field 0; verified bit for bit against the planar path).
+//     One thread issues two 50 KB boxes per block where eight warps issued 6400 cp.async: the MMA issuer's wait for
+//     operands drops from 60k to 11k cycles per CTA and pass, the layer from 184k to 110k (RowCfg TMA_A);
 //   * an UPSAMPLED source (decoder conv1: `F.interpolate(x, 2x nearest)`) is never expanded vertically: the block
 //     gathers its R/2+2 SOURCE rows (each pixel still written twice along x), and because upsampled rows 2s and 2s+1
 //     are the same data, source row s feeds output rows 2s-1 .. 2s+2 with the pre-summed weights
@@ -56,12 +63,23 @@ constexpr int kRowSmemMax = 227 * 1024;
 //      Direct 16-byte global stores from the epilogue lanes were measured SLOWER even for 32 / 64 bytes per pixel
 //      (dec3/dec4 layers +7..14 %): they share the LSU / L1 wavefront queue with the gather's cp.async traffic,
 //      which is the scarcer resource; the TMA store bypasses it.
-template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM>
+// TMA_A: the A ring is filled by TMA in the 128B-swizzled K-major layout (one 64-channel pixel = one 128-byte row):
+//      a stage is TROWS = 3 input rows x 130 pixels, a block's R + 2 input rows are (R + 2) / 3 stages, and input row
+//      j, filter column kx is the stage read through a descriptor whose start address is shifted by
+//      (j * 130 + kx) * 128 bytes (the tensor core swizzles on address bits, so any 128-byte row may start an operand).
+//      Only identity (not upsampled) 64-channel sources; the gather warps idle.
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM, bool TMA_A = false>
 struct RowCfg {
   static constexpr int PLANES = KC / 8;
   static constexpr int ROWS = R + 2;
   static constexpr int PLANE_STRIDE = ROWS * kRowPitch + 16;  // (stride / 16) odd: planes start 16 B apart mod 32 banks
-  static constexpr int A_STAGE = PLANES * PLANE_STRIDE;  // no-swizzle operand: 16-byte alignment is enough
+  static constexpr int TROWS = 3;                              // TMA_A: input rows per stage
+  static constexpr int TSUB = ROWS / TROWS;                    //        stages per block
+  static constexpr int T_ROW = kRowHaloPx * KC * 2;            //        bytes per input row in a stage (130 x 128)
+  static constexpr int T_STAGE = TROWS * T_ROW;                //        bytes one TMA box lands
+  // no-swizzle operand: 16-byte alignment is enough; the swizzled TMA stages stay 1024-aligned
+  static constexpr int A_STAGE = TMA_A ? (T_STAGE + 1023) / 1024 * 1024 : PLANES * PLANE_STRIDE;
+  static_assert(!TMA_A || (KC == 64 && KCB == 64 && !STREAM && ROWS % TROWS == 0), "TMA-filled A ring: 64-channel chunks");
   static constexpr int A_STAGES = STAGES;
   static constexpr int NF = 3 * CO;         // N of a full-width (three-slot) MMA
   static constexpr int SWB = KCB * 2;       // bytes per weight row = TMA / UMMA swizzle span
@@ -122,9 +140,9 @@ __device__ __forceinline__ RowTile row_decode(const ConvArgs& a, int tile, int r
   return t;
 }
 
-template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM>
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM, bool TMA_A = false>
 __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_constant__ ConvArgs a) {
-  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM>;
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM, TMA_A>;
   const long long t_cta = (a.debug != nullptr && threadIdx.x == 0) ? clock64() : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -155,7 +173,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
   // accumulator in fp32 and overwrites it in place.  The second form halves the gather volume and drops 4*R MMAs per
   // block of the Cout-64 layers (layer1's conv2: 172 -> conv1's ~120 us per 74-slice pass).
   const bool res_tma = a.residual != nullptr && a.res_tma != 0;
-  const bool has_res = a.residual != nullptr && !res_tma;
+  const bool has_res = !TMA_A && a.residual != nullptr && !res_tma;
   constexpr int RES_CHUNKS = CO / KC;    // A stages of the identity (residual) segment
   constexpr int RES_BTILES = CO / KCB;   // its weight tiles
   constexpr int CPB = KCB / KC;          // A chunks per weight tile
@@ -166,7 +184,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     if (has_res) tma_prefetch_desc(&a.bmapi);
     if (a.mode == kEpiBf16) tma_prefetch_desc(&a.omap);
     for (int s = 0; s < Cfg::A_STAGES; ++s) {
-      mbar_init(a_full(s), kRowGatherThreads / 32 + (STREAM ? 1 : 0));  // gather warps (+ the weight TMA's expect_tx)
+      // gather warps (+ the weight TMA's expect_tx), or the A TMA's expect_tx alone
+      mbar_init(a_full(s), TMA_A ? 1 : kRowGatherThreads / 32 + (STREAM ? 1 : 0));
       mbar_init(a_empty(s), 1);
     }
     mbar_init(b_full, 1);
@@ -181,6 +200,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
       }
     for (int g = 0; g < 2; ++g) mbar_init(res_full(g), 1);
     if (res_tma) tma_prefetch_desc(&a.rmap);
+    if (TMA_A) tma_prefetch_desc(&a.rowmap);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -242,6 +262,21 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
       if (has_res)
         for (int cb = 0; cb < RES_BTILES; ++cb)
           tma_load_2d(w_base + off + cb * Cfg::I_TILE, &a.bmapi, b_full, cb * KCB, 0);
+      if constexpr (TMA_A) {
+        // ---------------------------------------------------------- A ring by TMA: three input rows per stage
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+          const RowTile tc = row_decode(a, tile, R);
+          for (int hs = 0; hs < Cfg::TSUB; ++hs, ++it) {
+            const int st = it % Cfg::A_STAGES;
+            mbar_wait(a_empty(st), ((it / Cfg::A_STAGES) & 1) ^ 1u);
+            mbar_arrive_expect_tx(a_full(st), Cfg::T_STAGE);
+            // pixels x0-1 .. x0+128, rows y0-1+3hs .. +2: whatever lies outside the image arrives as zeros
+            tma_load_4d(a_base + st * Cfg::STAGE_BYTES, &a.rowmap, a_full(st), 0, tc.x0 - 1,
+                        tc.y0 - 1 + Cfg::TROWS * hs, tc.n);
+          }
+        }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
@@ -289,9 +324,50 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         umma_f16_lohi(dbase + (uint32_t)((r_lo + lo_slot) * CO), a_lo + (uint32_t)((js * kRowPitch) >> 4), a_hi,
                       b_lo + (uint32_t)((lo_slot * CO * Cfg::SWB) >> 4), b_hi, idesc, accumulate);
       };
+      if constexpr (TMA_A) {
+        // one 64-channel chunk per block, in TSUB stages of three input rows.  Stage hs holds block rows 3hs .. 3hs+2;
+        // its last row is the first to touch the output rows no earlier stage has written (3hs .. 3hs+2 minus the
+        // block's edges), so it goes first and overwrites; everything after accumulates.
+        for (int hs = 0; hs < Cfg::TSUB; ++hs, ++ita) {
+          const int sta = ita % Cfg::A_STAGES;
+          if (dbg) t0 = clock64();
+          row_warp_wait(a_full(sta), (ita / Cfg::A_STAGES) & 1, lane);
+          if (dbg) w_a += clock64() - t0;
+          operand_ready_fence();
+          const uint32_t a_addr = a_base + sta * Cfg::STAGE_BYTES;
+          const uint64_t adesc = umma_smem_desc<128>(a_addr);
+          const uint32_t a_lo = (uint32_t)adesc, a_hi0 = (uint32_t)(adesc >> 32);
+          if (elect_one()) {
+            auto issue_t = [&](int jj, uint32_t kx, uint32_t kk, uint32_t accumulate) {
+              const int j = Cfg::TROWS * hs + jj;
+              const int lo_slot = j >= 2 ? 0 : 2 - j;
+              const int hi_slot = j <= R - 1 ? 2 : R + 1 - j;
+              const int nslots = hi_slot - lo_slot + 1;
+              const uint32_t idesc = nslots == 3 ? idesc3 : (nslots == 2 ? idesc2 : idesc1);
+              const uint32_t off = (uint32_t)(jj * Cfg::T_ROW) + kx * 128u + kk * 32u;  // bytes into the stage
+              // development switch (row_tma == 2): matrix base offset = 128-byte row phase of the start address
+              const uint32_t a_hi = a.row_tma == 2 ? (a_hi0 | ((((a_addr + off) >> 7) & 7u) << 17)) : a_hi0;
+              umma_f16_lohi(dbase + (uint32_t)((j - 2 + lo_slot) * CO), a_lo + (off >> 4), a_hi,
+                            b_lo_base + kx * (Cfg::B_TILE >> 4) + 2u * kk + (uint32_t)((lo_slot * CO * Cfg::SWB) >> 4), b_hi,
+                            idesc, accumulate);
+            };
+#pragma unroll
+            for (uint32_t kx = 0; kx < 3; ++kx) {
+#pragma unroll
+              for (uint32_t kk = 0; kk < KC / 16; ++kk) {
+                issue_t(Cfg::TROWS - 1, kx, kk, (kx | kk) ? 1u : 0u);
+#pragma unroll
+                for (int jj = 0; jj < Cfg::TROWS - 1; ++jj) issue_t(jj, kx, kk, 1u);
+              }
+            }
+            umma_commit(a_empty(sta));
+          }
+          __syncwarp();
+        }
+      }
       uint32_t chunk = 0;
       uint32_t tile_off = 0;  // byte offset of the current segment's first weight tile
-      for (int s = 0; s < a.nseg; ++s) {
+      for (int s = 0; s < (TMA_A ? 0 : a.nseg); ++s) {
         const bool upseg = s == 0 && up0;
         const uint32_t tile_bytes = upseg ? Cfg::U_TILE : Cfg::B_TILE;
         for (int cc = 0; cc < a.seg[s].cin / KC; ++cc, ++ita, ++chunk) {
@@ -562,6 +638,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
             // it, then store the finished box from the same place
             mbar_arrive_expect_tx(res_full(g), Cfg::STG);
             tma_load_4d(stg_g, &a.rmap, res_full(g), 0, tc.x0, tc.y0 + r0, tc.n);
+            if (a.res_tma > 1) {
+              // this group's NEXT box (same block, or the first one of the CTA's next block) into L2 now: its load
+              // sits between two stores of a one-buffer group and would otherwise pay the DRAM latency in full
+              if (rb + RB < R / 2 && tc.y0 + r0 + RB < a.out_h) {
+                tma_prefetch_4d(&a.rmap, 0, tc.x0, tc.y0 + r0 + RB, tc.n);
+              } else if (tile + (int)gridDim.x < a.total_tiles) {
+                const RowTile tn = row_decode(a, tile + (int)gridDim.x, R);
+                tma_prefetch_4d(&a.rmap, 0, tn.x0, tn.y0 + g * (R / 2), tn.n);
+              }
+            }
             mbar_wait(stg_full(g, 0), nstore & 1u);
             tma_store_4d(&a.omap, stg_g, 0, tc.x0, tc.y0 + r0, tc.n);
             bulk_commit();
@@ -589,7 +675,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
       }
       bulk_wait_all();
     }
-  } else {
+  } else if (!TMA_A) {
     // ------------------------------------------------------------ gather: (R+2) rows x 130 pixels x KC channels per stage
     // Thread t owns fixed (plane, pixel) columns of the stage and walks the rows: per copy one bounds test and one
     // pointer add.  Lanes run over the planes of consecutive pixels, so a warp reads contiguous global memory.
@@ -704,6 +790,9 @@ int conv_row_mode(const ConvArgs& a);
 //                                            (conv1's four-slot + three-slot weight tiles take 84 KB)
 //   Cout 16 (decoder block 4, head):         16-channel A stages x 4, 8-row blocks, 2 rows per TMA store
 #define IU_ROW_CFG64 32, 64, 64, 4, 2, 1, 1, false
+//   Cout 64 from ONE identity 64-channel source (layer1, decoder block 2 conv2), A ring filled by TMA: 64-channel
+//                                            stages of three input rows x 2, 128B-swizzled
+#define IU_ROW_CFG64T 64, 64, 64, 4, 2, 1, 1, false, true
 #define IU_ROW_CFG64S 16, 16, 64, 4, 3, 1, 2, true
 #define IU_ROW_CFG32 16, 16, 32, 8, 3, 1, 1, false
 #define IU_ROW_CFG16 16, 16, 16, 8, 4, 2, 2, false
@@ -751,15 +840,22 @@ int conv_row_mode(const ConvArgs& a) {
   return (a.residual == nullptr && a.num_classes <= 16 && row_fits<IU_ROW_CFG16>(a)) ? 1 : 0;
 }
 
-template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM>
+// The TMA-filled variant takes the Cout-64 layers whose only source is an identity 64-channel tensor (the engine
+// encodes `rowmap` and sets `row_tma` for exactly those); a shortcut must then come through the epilogue (`res_tma`).
+bool conv_row_tma_applicable(const ConvArgs& a) {
+  return a.mode == kEpiBf16 && a.cout == 64 && a.nseg == 1 && a.seg[0].cin == 64 && !a.seg[0].up &&
+         (a.residual == nullptr || a.res_tma != 0) && conv_row_mode(a) == 1;
+}
+
+template <int KC, int KCB, int CO, int R, int STAGES, int RB, int NSTG, bool STREAM, bool TMA_A = false>
 static cudaError_t launch_row_one(const ConvArgs& args_in, cudaStream_t stream) {
-  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM>;
+  using Cfg = RowCfg<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM, TMA_A>;
   static int configured_dev = -1;
   static int num_sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM>,
+    cudaError_t e = cudaFuncSetAttribute(conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM, TMA_A>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -771,7 +867,7 @@ static cudaError_t launch_row_one(const ConvArgs& args_in, cudaStream_t stream) 
   args.ntiles_n = 1;
   args.total_tiles = args.tiles_x * args.tiles_y * args.batch;
   const int grid = args.total_tiles < num_sms ? args.total_tiles : num_sms;
-  conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM><<<grid, kRowThreads, Cfg::SMEM_BYTES, stream>>>(args);
+  conv_row_kernel<KC, KCB, CO, R, STAGES, RB, NSTG, STREAM, TMA_A><<<grid, kRowThreads, Cfg::SMEM_BYTES, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -780,6 +876,7 @@ cudaError_t launch_conv_row(const ConvArgs& args, cudaStream_t stream) {
   if (mode == 0) return cudaErrorInvalidValue;
   const int co = args.mode == kEpiBf16 ? args.cout : 16;
   if (co == 64 && mode == 2) return launch_row_one<IU_ROW_CFG64S>(args, stream);
+  if (co == 64 && args.row_tma && conv_row_tma_applicable(args)) return launch_row_one<IU_ROW_CFG64T>(args, stream);
   if (co == 64) return launch_row_one<IU_ROW_CFG64>(args, stream);
   if (co == 32) return launch_row_one<IU_ROW_CFG32>(args, stream);
   return launch_row_one<IU_ROW_CFG16>(args, stream);

@@ -50,6 +50,11 @@ struct alignas(64) ConvArgs {
   // res_tma != 0 to add the residual in the epilogue from a TMA-loaded staging buffer instead of as an identity K segment
   CUtensorMap rmap;
   int res_tma;
+  // row-folded kernel, Cin = Cout = 64 identity source: 4-D map (64, W, H, N) over the SOURCE, box (64, 130, 3, 1),
+  // 128B swizzle -- the A ring is filled by TMA (zero fill outside the image = the conv's padding) instead of by the
+  // gather warps' cp.async; row_tma != 0 selects that variant (2: descriptors carry a base offset, development switch)
+  CUtensorMap rowmap;
+  int row_tma;
   ConvSegment seg[2];
   const __nv_bfloat16* src_ptr[2];  // raw pointers of the segment sources (halo kernel: cp.async gathers)
   int nseg;
@@ -109,6 +114,7 @@ cudaError_t launch_conv_tc2(const ConvArgs& args, int bn, cudaStream_t stream);
 bool conv_row_applicable(const ConvArgs& args);
 int conv_row_mode(const ConvArgs& args);   // 0 = not applicable, 1 = resident weights, 2 = streamed weights
 int conv_row_kc(int cout_pad, int mode);
+bool conv_row_tma_applicable(const ConvArgs& args);  // Cout 64 from one identity 64-channel source: A ring by TMA
 int conv_row_store_rows(int cout_pad);  // output rows per TMA store box (the `omap` box height)
 cudaError_t launch_conv_row(const ConvArgs& args, cudaStream_t stream);
 

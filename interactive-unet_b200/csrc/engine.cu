@@ -143,6 +143,7 @@ struct iu_engine {
   uint64_t use_clock = 0;
   int use_graph = 1;         // env IU_GRAPH=0: never capture the single-batch forward
   int conv_chain = 1;        // env IU_CONV_CHAIN=0: decoder block 4 + head as three separate row-folded launches
+  int row_tma = 1;           // env IU_ROW_TMA=0: the Cout-64 row layers with one identity source gather with cp.async again
   int row_res_tma = 1;       // env IU_ROW_RES_TMA=0: the Cout-64 row layers add their shortcut as an identity K segment
   int stem_pool = 0;         // env IU_STEM_POOL=1: max-pool inside the stem's epilogue (measured slower: 9.7 ms against
                              // 4.1 + 4.3 ms per 512^3 -- 40 % of a tile's pooled pixels go through red.max)
@@ -797,7 +798,13 @@ int build_plan(iu_engine* e, int batch, int h, int w) {
         if (rc == IU_OK && L.residual >= 0 && L.cout_pad == 64 && row_mode == 1 && e->row_res_tma) {
           rc = encode_act_map(e, &a.rmap, p.bufs[L.residual], L.cout_pad, w / to.hdiv, h / to.hdiv, bp, L.cout_pad, 128,
                               conv_row_store_rows(L.cout_pad), 1, 1);
-          a.res_tma = rc == IU_OK;
+          a.res_tma = rc == IU_OK ? e->row_res_tma : 0;
+        }
+        // ... and those fed by ONE identity 64-channel tensor have their A ring filled by TMA (conv_row.cu, TMA_A)
+        if (rc == IU_OK && e->row_tma && conv_row_tma_applicable(a)) {
+          const TensorSpec& ts = e->tensors[L.src[0]];
+          rc = encode_act_map(e, &a.rowmap, p.bufs[L.src[0]], ts.c, w / ts.hdiv, h / ts.hdiv, bp, 64, 130, 3, 1, 1);
+          a.row_tma = rc == IU_OK ? e->row_tma : 0;
         }
       }
       if (rc == IU_OK) a.use_row = 1;
@@ -1131,6 +1138,7 @@ int iu_engine_create(int device, iu_engine** out) {
   if (const char* v = getenv("IU_CONV_SMALL_BN")) e->conv_small_bn = atoi(v);
   if (const char* v = getenv("IU_STEM_POOL")) e->stem_pool = atoi(v);
   if (const char* v = getenv("IU_ROW_RES_TMA")) e->row_res_tma = atoi(v);
+  if (const char* v = getenv("IU_ROW_TMA")) e->row_tma = atoi(v);
   e->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   if (const char* v = getenv("IU_SCRATCH_KEEP_MB")) e->scratch_keep = (size_t)std::max(0, atoi(v)) << 20;
   if (const char* v = getenv("IU_CONV_DEBUG")) {
@@ -2156,7 +2164,11 @@ int iu_engine_conv_test(iu_engine* e, const void* src0, int cin0, const void* sr
           rc = encode_act_map(e, &a.omap, out, cout, out_w, out_h, batch, cout, 128, conv_row_store_rows(cout), 1, 1);
         if (rc == IU_OK && residual && cout == 64 && row_mode == 1 && e->row_res_tma) {
           rc = encode_act_map(e, &a.rmap, residual, cout, out_w, out_h, batch, cout, 128, conv_row_store_rows(cout), 1, 1);
-          a.res_tma = rc == IU_OK;
+          a.res_tma = rc == IU_OK ? e->row_res_tma : 0;
+        }
+        if (rc == IU_OK && e->row_tma && conv_row_tma_applicable(a)) {
+          rc = encode_act_map(e, &a.rowmap, a.src_ptr[0], 64, out_w, out_h, batch, 64, 130, 3, 1, 1);
+          a.row_tma = rc == IU_OK ? e->row_tma : 0;
         }
         if (rc == IU_OK) a.use_row = 1;
       }

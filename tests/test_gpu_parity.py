@@ -82,6 +82,9 @@ CONV_CASES = [
     ("row_k64n64", 8, 12, 128, 64, 0, 64, 3, 1, False, True, False),
     ("row_k64n64_res", 8, 10, 128, 64, 0, 64, 3, 1, True, True, False),
     ("row_k64n64_norelu", 8, 4, 128, 64, 0, 64, 3, 1, True, False, False),
+    # two / three row segments: the TMA-filled A ring takes its halo pixels from the neighbouring segment
+    ("row_k64n64_w256_res", 8, 9, 256, 64, 0, 64, 3, 1, True, True, False),
+    ("row_k64n64_w384", 8, 21, 384, 64, 0, 64, 3, 1, False, True, False),
     ("row_upsrc_cat_k64n32", 8, 16, 128, 64, 64, 32, 3, 1, False, True, "src"),
     ("row_k32n32", 8, 10, 128, 32, 0, 32, 3, 1, False, True, False),
     ("row_upsrc_k32n16", 8, 12, 256, 32, 0, 16, 3, 1, False, True, "src"),
