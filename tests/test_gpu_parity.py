@@ -85,6 +85,8 @@ CONV_CASES = [
     # two / three row segments: the TMA-filled A ring takes its halo pixels from the neighbouring segment
     ("row_k64n64_w256_res", 8, 9, 256, 64, 0, 64, 3, 1, True, True, False),
     ("row_k64n64_w384", 8, 21, 384, 64, 0, 64, 3, 1, False, True, False),
+    ("row_k64n64_w192_res", 8, 6, 192, 64, 0, 64, 3, 1, True, True, False),     # ragged second segment
+    ("row_k64n64_h2", 8, 2, 128, 64, 0, 64, 3, 1, False, True, False),          # fewer rows than one TMA stage
     ("row_upsrc_cat_k64n32", 8, 16, 128, 64, 64, 32, 3, 1, False, True, "src"),
     ("row_k32n32", 8, 10, 128, 32, 0, 32, 3, 1, False, True, False),
     ("row_upsrc_k32n16", 8, 12, 256, 32, 0, 16, 3, 1, False, True, "src"),
