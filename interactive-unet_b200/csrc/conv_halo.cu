@@ -43,18 +43,28 @@ constexpr int kMaxBias = 512;
 // STAT: the layer's whole weight matrix stays resident in shared memory (loaded once per CTA) -- every layer with
 // <= 32-channel chunks, and the 64-channel layers whose [BN x K] matrix fits beside the activation ring
 // (64 -> 64 and 64+64 -> 32: 72 KB).  Otherwise weights stream per (chunk, tap) through a TMA ring.
-template <int KC, int BN, bool STAT>
+// TMA_A (identity sources, 64-channel chunks, streamed weights): the halo tile is ONE TMA box -- 18 x 18 pixels x 64
+// channels in the 128B-swizzled K-major layout (a pixel = one 128-byte row, 41,472 B) -- and filter tap (r,q) of
+// M tile j is that buffer read from start address + ((r * 18 + q + 8j) * 128) bytes with SBO = one halo row
+// (18 * 128 B): the tensor core swizzles on address bits, so an operand may start at any 128-byte row (measured on
+// the row-folded kernel, profiles/r02_findings.md 1c).  One thread issues one box per chunk where eight warps issued
+// 2592 cp.async; two A stages are enough then, and the shared memory they free deepens the weight ring to 7 tiles.
+template <int KC, int BN, bool STAT, bool TMA_A = false>
 struct HaloCfg {
   static constexpr int CTAS = KC <= 32 ? 2 : 1;
-  static constexpr int GATHER_THREADS = KC <= 32 ? 128 : 256;  // 4 gather warps per CTA (two CTAs per SM) or 8
+  static constexpr int GATHER_THREADS = TMA_A ? 32 : (KC <= 32 ? 128 : 256);  // 4 gather warps per CTA (two CTAs per SM) or 8
   static constexpr int THREADS = kHaloBaseThreads + GATHER_THREADS;
   static constexpr int PLANES = KC / 8;
-  static constexpr int A_STAGE = (PLANES * kPlaneStride + 1023) / 1024 * 1024;
-  static constexpr int A_STAGES = KC == 64 ? (STAT ? 3 : IU_HALO_A64_STAGES) : 4;
+  static constexpr int T_PITCH_MAX = 24;             // TMA_A: halo pixels per row of the box (ConvArgs::halo_tma: 18, or
+                                                     //        24 = every 8-row group starts a fresh swizzle period)
+  static constexpr int T_BYTES = kHaloW * T_PITCH_MAX * KC * 2;  //  bytes the largest box lands
+  static constexpr int A_STAGE = ((TMA_A ? T_BYTES : PLANES * kPlaneStride) + 1023) / 1024 * 1024;
+  static constexpr int A_STAGES = TMA_A ? 2 : (KC == 64 ? (STAT ? 3 : IU_HALO_A64_STAGES) : 4);
+  static_assert(!TMA_A || (KC == 64 && !STAT), "TMA-filled halo tiles: 64-channel chunks, streamed weights");
   static constexpr int SW = KC * 2;
   static constexpr int B_BYTES = BN * KC * 2;
   static constexpr int B_ALLOC = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int B_RAW = (kHaloSmemBudget - A_STAGES * A_STAGE) / B_ALLOC;
+  static constexpr int B_RAW = ((TMA_A ? 220 * 1024 : kHaloSmemBudget) - A_STAGES * A_STAGE) / B_ALLOC;
   // STAT: number of resident [BN x KC] weight tiles; streaming: depth of the weight ring
   static constexpr int B_STAGES = STAT ? (KC <= 32 ? 9 : (B_RAW > 18 ? 18 : B_RAW)) : (B_RAW > 9 ? 9 : (B_RAW < 3 ? 3 : B_RAW));
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
@@ -85,10 +95,16 @@ __device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity, int lan
   __syncwarp();
 }
 
-template <int KC, int BN, bool STAT>
-__global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN, STAT>::CTAS)
+// K-major 128B-swizzled descriptor whose 8-row groups are `sbo` bytes apart (a halo row instead of the dense 1024)
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (uint64_t)1 << 16 | (uint64_t)(sbo >> 4) << 32 | (uint64_t)1 << 46 |
+         (uint64_t)2 << 61;
+}
+
+template <int KC, int BN, bool STAT, bool TMA_A = false>
+__global__ void __launch_bounds__(HaloCfg<KC, BN, STAT, TMA_A>::THREADS, HaloCfg<KC, BN, STAT, TMA_A>::CTAS)
     conv_halo_kernel(const __grid_constant__ ConvArgs a) {
-  using Cfg = HaloCfg<KC, BN, STAT>;
+  using Cfg = HaloCfg<KC, BN, STAT, TMA_A>;
   const long long t_cta = (a.debug != nullptr && threadIdx.x == 0) ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -114,8 +130,11 @@ __global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN
   for (int i = threadIdx.x; i < a.ntiles_n * BN; i += Cfg::THREADS) bias_s[i] = a.bias[i];
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.bmap);
+    if (TMA_A)
+      for (int s = 0; s < a.nseg; ++s) tma_prefetch_desc(&a.hmap[s]);
     for (int s = 0; s < Cfg::A_STAGES; ++s) {
-      mbar_init(a_full(s), Cfg::GATHER_THREADS / 32);  // one arrival per gather warp (after every lane fenced its copies)
+      // one arrival per gather warp (after every lane fenced its copies), or the A box's expect_tx alone
+      mbar_init(a_full(s), TMA_A ? 1 : Cfg::GATHER_THREADS / 32);
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < Cfg::B_STAGES; ++s) {
@@ -209,8 +228,12 @@ __global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN
           operand_ready_fence();
           // Descriptors: one base per stage; every (tap, k-step, M tile) is base.lo + a compile-time constant
           // (in 16-byte units), so issuing an MMA costs one integer add instead of a bit-field rebuild.
-          const uint64_t adesc_base = umma_smem_desc_planar(a_base + sta * Cfg::A_STAGE, kPlaneStride, kHaloW * 16);
+          const uint32_t pitch = TMA_A ? (uint32_t)a.halo_tma : (uint32_t)kHaloW;  // halo pixels per buffer row
+          const uint64_t adesc_base = TMA_A ? umma_smem_desc_sw128(a_base + sta * Cfg::A_STAGE, pitch * 128u)
+                                            : umma_smem_desc_planar(a_base + sta * Cfg::A_STAGE, kPlaneStride, kHaloW * 16);
           const uint32_t a_lo = (uint32_t)adesc_base, a_hi = (uint32_t)(adesc_base >> 32);
+          // 16-byte units per halo pixel / per 16-channel k-step / between the two M tiles (8 pixels)
+          constexpr uint32_t PX = TMA_A ? 8u : 1u, KSTEP = TMA_A ? 2u : 2u * (kPlaneStride >> 4), MT = 8u * PX;
           if constexpr (STAT) {
             const uint32_t b_lo_chunk = b_lo_base + chunk * 9u * (Cfg::B_ALLOC >> 4);
             if (elect_one()) {
@@ -239,13 +262,13 @@ __global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN
               operand_ready_fence();
               const int r = tap / 3, q = tap - 3 * r;
               const uint32_t b_lo = b_lo_base + stb * (Cfg::B_ALLOC >> 4);
-              const uint32_t a_tap = a_lo + (uint32_t)(r * kHaloW + q);
+              const uint32_t a_tap = a_lo + ((uint32_t)r * pitch + (uint32_t)q) * PX;
               if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < KC / 16; ++kk) {
-                  const uint32_t a_off = (uint32_t)(2 * kk) * (kPlaneStride >> 4);
+                  const uint32_t a_off = (uint32_t)kk * KSTEP;
                   umma_f16_lohi(tmem_d0, a_tap + a_off, a_hi, b_lo + 2u * kk, b_hi, idesc, accumulate);
-                  umma_f16_lohi(tmem_d1, a_tap + a_off + 8u, a_hi, b_lo + 2u * kk, b_hi, idesc, accumulate);
+                  umma_f16_lohi(tmem_d1, a_tap + a_off + MT, a_hi, b_lo + 2u * kk, b_hi, idesc, accumulate);
                   accumulate = 1;
                 }
                 umma_commit(b_empty(stb));
@@ -296,7 +319,24 @@ __global__ void __launch_bounds__(HaloCfg<KC, BN, STAT>::THREADS, HaloCfg<KC, BN
       atomicAdd(a.debug + 8, (unsigned long long)w_full);
       atomicAdd(a.debug + 9, (unsigned long long)t_body);
     }
-  } else {
+  } else if (TMA_A) {
+    // ------------------------------------------------------------ halo tiles by TMA: one 18 x 18 x 64 box per chunk
+    if (warp == 10 && lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(a, tile);
+        for (int s = 0; s < a.nseg; ++s) {
+          for (int cc = 0; cc < a.seg[s].cin / KC; ++cc, ++it) {
+            const int st = it % Cfg::A_STAGES;
+            mbar_wait(a_empty(st), ((it / Cfg::A_STAGES) & 1) ^ 1u);
+            mbar_arrive_expect_tx(a_full(st), (uint32_t)(kHaloW * a.halo_tma * KC * 2));
+            // pixels outside the image arrive as zeros: the convolution's padding
+            tma_load_4d(a_base + st * Cfg::A_STAGE, &a.hmap[s], a_full(st), cc * KC, tc.x0 - 1, tc.y0 - 1, tc.n0);
+          }
+        }
+      }
+    }
+  } else if constexpr (!TMA_A) {
     // ------------------------------------------------------------ halo gather (4 warps, cp.async)
     // Thread t copies channel octet kc = t % PLANES of the halo pixels p0, p0 + STEP, ...: a warp reads whole
     // pixel rows (coalesced) and the (row, col) of the next pixel follows incrementally, no divisions.
@@ -728,17 +768,17 @@ bool conv_halo_applicable(const ConvArgs& a) {
   return true;
 }
 
-template <int KC, int BN, bool STAT>
+template <int KC, int BN, bool STAT, bool TMA_A = false>
 static cudaError_t launch_halo_one(const ConvArgs& args_in, cudaStream_t stream) {
-  using Cfg = HaloCfg<KC, BN, STAT>;
+  using Cfg = HaloCfg<KC, BN, STAT, TMA_A>;
   static_assert(Cfg::SMEM_BYTES * Cfg::CTAS <= 227 * 1024, "halo kernel exceeds the shared memory of an SM");
   static int configured_dev = -1;
   static int num_sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_dev != dev) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC, BN, STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC, BN, STAT, TMA_A>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     configured_dev = dev;
@@ -754,7 +794,7 @@ static cudaError_t launch_halo_one(const ConvArgs& args_in, cudaStream_t stream)
   args.total_tiles = args.tiles_x * args.tiles_y * args.batch * args.ntiles_n;
   const int slots = num_sms * Cfg::CTAS;
   const int grid = args.total_tiles < slots ? args.total_tiles : slots;
-  conv_halo_kernel<KC, BN, STAT><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(args);
+  conv_halo_kernel<KC, BN, STAT, TMA_A><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -772,6 +812,19 @@ static cudaError_t launch_halo_pick(const ConvArgs& args, cudaStream_t stream) {
   for (int s = 0; s < args.nseg; ++s)
     if (args.seg[s].up) return cudaErrorInvalidValue;
   return launch_conv_tc(args, KC, BN, stream);
+}
+
+// Halo tiles filled by TMA (`hmap`): stride-1 3x3 layers whose sources are all identity tensors with 64-channel
+// chunks and whose Cout is a multiple of 128 -- the layers the per-tap kernel serves otherwise.
+bool conv_halo_tma_applicable(const ConvArgs& a) {
+  if (!conv_halo_applicable(a) || a.mode != kEpiBf16 || a.cout % 128 != 0 || a.cout > kMaxBias || a.up2x) return false;
+  for (int s = 0; s < a.nseg; ++s)
+    if (a.seg[s].up || a.seg[s].cin % 64 != 0) return false;
+  return true;
+}
+cudaError_t launch_conv_halo_tma(const ConvArgs& args, cudaStream_t stream) {
+  if (!conv_halo_tma_applicable(args)) return cudaErrorInvalidValue;
+  return launch_halo_one<64, 128, false, true>(args, stream);
 }
 
 #define IU_HALO_DISPATCH(KC_, BN_) \

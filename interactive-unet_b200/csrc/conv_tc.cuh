@@ -55,6 +55,11 @@ struct alignas(64) ConvArgs {
   // gather warps' cp.async; row_tma != 0 selects that variant (2: descriptors carry a base offset, development switch)
   CUtensorMap rowmap;
   int row_tma;
+  // halo kernel with TMA-filled tiles (identity sources, 64-channel chunks, Cout % 128 == 0): 4-D maps (C, W, H, N)
+  // over the segment sources, box (64, 18, 18, 1), 128B swizzle; halo_tma != 0 selects that variant and is the number
+  // of halo pixels per buffer row (the box width: 18, or 24 as a development switch)
+  CUtensorMap hmap[2];
+  int halo_tma;
   ConvSegment seg[2];
   const __nv_bfloat16* src_ptr[2];  // raw pointers of the segment sources (halo kernel: cp.async gathers)
   int nseg;
@@ -96,6 +101,10 @@ int conv_tc_smem_bytes(int kc, int bn);
 constexpr int kHaloTile = 16;
 bool conv_halo_applicable(const ConvArgs& args);
 cudaError_t launch_conv_halo(const ConvArgs& args, int kc, int bn, cudaStream_t stream);
+// ... with the halo tile fetched by ONE TMA box per chunk into a 128B-swizzled buffer (needs `hmap`); for the layers
+// the per-tap kernel serves otherwise: identity sources, 64-channel chunks, Cout a multiple of 128
+bool conv_halo_tma_applicable(const ConvArgs& args);
+cudaError_t launch_conv_halo_tma(const ConvArgs& args, cudaStream_t stream);
 
 // CTA-pair variant (tcgen05 cta_group::2, M = 256, N = 128) for stride-1 3x3 convs with 64-channel chunks and
 // Cout a multiple of 128; needs `bmap2`.

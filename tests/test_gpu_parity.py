@@ -102,16 +102,20 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", ["pertap", "pertap_bm2", "pertap_cluster", "pertap_pair2", "halo", "pair", "row"])
+@pytest.mark.parametrize("variant", ["pertap", "pertap_bm2", "pertap_cluster", "pertap_pair2", "halo", "halo_tma", "pair", "row"])
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_matches_fp32_reference(dev, iu, case, precision, variant, monkeypatch):
-    """The tensor-core kernels (per-tap TMA boxes; halo tile with shifted no-swizzle descriptors; CTA-pair halo
+    """The tensor-core kernels (per-tap TMA boxes; halo tile with shifted no-swizzle descriptors, or -- `halo_tma` --
+    filled by TMA and read through shifted 128B-swizzled descriptors; CTA-pair halo
     kernel with tcgen05 cta_group::2 on the Cout >= 128 cases; row-folded kernel on the `row_*` cases), forced via
     IU_CONV_VARIANT / IU_CONV_PAIR / IU_CONV_ROW; each variant falls back to the next one where it does not apply."""
     _, b, h, w, c0, c1, cout, k, stride, residual, relu, up2x = case
     act = torch.float16 if precision == "fp16" else torch.bfloat16
-    monkeypatch.setenv("IU_CONV_VARIANT", "1" if variant.startswith("pertap") else "2")
+    # "halo_tma": automatic choice with the row kernel off -- the Cout >= 128 stride-1 cases then take the halo kernel
+    # whose tiles are filled by TMA (shifted swizzled descriptors), everything else its usual kernel
+    monkeypatch.setenv("IU_CONV_VARIANT", "1" if variant.startswith("pertap") else ("0" if variant == "halo_tma" else "2"))
+    monkeypatch.setenv("IU_HALO_TMA", os.environ.get("IU_HALO_TMA_TEST", "1") if variant == "halo_tma" else "0")
     monkeypatch.setenv("IU_CONV_BM2", "3" if variant == "pertap_bm2" else ("1" if variant == "pertap_cluster" else "0"))
     monkeypatch.setenv("IU_CONV_CLUSTER", "1" if variant == "pertap_cluster" else "0")
     monkeypatch.setenv("IU_CONV_PAIR", "1" if variant == "pair" else "0")
