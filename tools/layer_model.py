@@ -1,9 +1,9 @@
 """Per-layer bound model of the conv stack against a measured launch list (development aid, runs on the CPU).
 
-    python tools/layer_model.py [profiles/r01_launches_v12.txt] [--ghz 1.65]
+    python tools/layer_model.py [profiles/r02_launches_final.txt] [--ghz 1.65]
 
-For each of the 43 tensor-core conv launches of one pass (74 slices of 512 x 512, resnet34) it derives from the layer's
-shape and the kernel variant that runs it:
+For each tensor-core conv launch of one pass (74 slices of 512 x 512, resnet34: 43 launches in round 1's lists, 41 since
+decoder block 4 + head became one fused launch) it derives from the layer's shape and the kernel variant that runs it:
 
   t_mma   the MMA issue floor: number of tcgen05.mma (M = 128, K = 16) x the measured cycles per MMA of that N
           (`profiles/r01_pipe_probe.txt`: 42 cycles up to N = 32, N/2 from N = 128 on);
@@ -26,12 +26,14 @@ MMA_CYC = {16: 41.9, 32: 42.2, 48: 44.2, 64: 48.2, 96: 56.2, 128: 64.2, 192: 96.
 BATCH = 74
 
 
-def layers():
-    """(name, kind, out_hw, cout, [(cin, ksize, upsampled)], stride, residual)"""
+def layers(r02=False):
+    """(name, kind, out_hw, cout, [(cin, ksize, upsampled)], stride, residual)
+    r02: the Cout-64 row layers add their shortcut in the epilogue (kind "rowepi": no identity K segment, the shortcut
+    is read once from HBM) and decoder block 4 + head are one launch (their three models are summed by `main`)."""
     L = []
     for i in range(3):
         L.append((f"layer1.{i}.conv1", "row", 128, 64, [(64, 3, False)], 1, False))
-        L.append((f"layer1.{i}.conv2", "row", 128, 64, [(64, 3, False)], 1, True))
+        L.append((f"layer1.{i}.conv2", "rowepi" if r02 else "row", 128, 64, [(64, 3, False)], 1, True))
     for li, (c, hw, nb, kind) in enumerate([(128, 64, 4, "tap128x2"), (256, 32, 6, "tap256"), (512, 16, 3, "tap256")]):
         cin = c // 2
         L.append((f"layer{li + 2}.0.conv1 s2", kind, hw, c, [(cin, 3, False)], 2, False))
@@ -64,7 +66,7 @@ def model(layer, ghz):
     for cin, k, up in segs:
         src_px = px / 4.0 if up else px * stride * stride
         halo = 1.0
-        if kind == "row":
+        if kind in ("row", "rowepi"):
             rows = {64: 4, 32: 8, 16: 8}[cout]
             halo = (rows / 2 + 2) / (rows / 2) if up else (rows + 2) / rows      # input rows read per output row block
         in_bytes += src_px * cin * 2 * halo
@@ -74,7 +76,7 @@ def model(layer, ghz):
     hbm = in_bytes + out_bytes + w_bytes
     # ---- MMAs and shared-memory traffic
     n_mma = smem = cyc = 0.0
-    if kind == "row":
+    if kind in ("row", "rowepi"):
         rows = {64: 4, 32: 8, 16: 8}[cout]
         for cin, k, up in segs:
             n = (4 if up else 3) * cout                      # vertical taps folded into N
@@ -83,7 +85,7 @@ def model(layer, ghz):
             n_mma += m
             cyc += m * MMA_CYC[min(MMA_CYC, key=lambda v: abs(v - n))]
             smem += m * (4096 + n * 32)
-        if residual:
+        if residual and kind == "row":
             m = mtiles * (cout / 16.0)                       # identity K segment
             n_mma += m
             cyc += m * MMA_CYC[cout if cout in MMA_CYC else 64]
@@ -115,20 +117,30 @@ def model(layer, ghz):
 def measured(path):
     out = []
     for line in open(path):
-        m = re.match(r"\s*(\d+)\s+(.*?)\s+(conv_\w+_kernel.*?)\s+\(\d+, 1, 1\)\s+([\d.]+) us", line)
-        if m and "stem" not in m.group(3):
-            out.append(float(m.group(4)))
+        m = re.search(r"(conv_\w+_kernel).*?([\d.]+) us\s*$", line)
+        if m and "stem" not in m.group(1):
+            out.append(float(m.group(2)))
     return out
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("launches", nargs="?", default="profiles/r01_launches_v12.txt")
+    ap.add_argument("launches", nargs="?", default="profiles/r02_launches_final.txt")
     ap.add_argument("--ghz", type=float, default=1.65, help="SM clock under the power cap")
     args = ap.parse_args()
     meas = measured(args.launches)
-    rows = [model(l, args.ghz) for l in layers()]
-    assert len(meas) == len(rows) == 43, (len(meas), len(rows))
+    r02 = len(meas) == 41
+    rows = [model(l, args.ghz) for l in layers(r02)]
+    if r02:
+        # the fused tail: one launch; MMA and shared-memory work of its three layers add up, the two 16-channel
+        # intermediates never reach HBM (input of conv1 + output of the head + weights remain)
+        tail = rows[-3:]
+        px = BATCH * 512 * 512
+        fused = dict(name="dec4.conv1+conv2+head", kind="chain", gflop=sum(r["gflop"] for r in tail),
+                     t_mma=sum(r["t_mma"] for r in tail) * 128 / 124, t_smem=sum(r["t_smem"] for r in tail) * 128 / 124,
+                     t_hbm=(px / 4.0 * 32 * 2 * 10 / 8 + px * 2 * 4) / HBM * 1e6, n_mma=sum(r["n_mma"] for r in tail))
+        rows = rows[:-3] + [fused]
+    assert len(meas) == len(rows) and len(rows) in (41, 43), (len(meas), len(rows))
     print(f"one pass of {BATCH} slices of 512x512 at {args.ghz} GHz; times in us; '*' marks the model's largest bound")
     print(f"{'layer':22s} {'kernel':9s} {'GFLOP':>7s} {'t_mma':>7s} {'t_smem':>7s} {'t_hbm':>7s} {'meas':>7s} {'meas/bound':>10s}")
     tot = dict(t_mma=0.0, t_smem=0.0, t_hbm=0.0, bound=0.0, meas=0.0)
