@@ -89,7 +89,7 @@ class ClockSampler:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.lines:
             f = [x.strip() for x in line.split(",")]
@@ -100,12 +100,19 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                power.append(float(f[2]))                  # board power: the step sits on the cap
+            except ValueError:
+                pass
             for name, val in zip(names, f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if power:
+            out["power_w"] = float(np.median(power))
+        return out
 
 
 # ------------------------------------------------------------------------------------------- synthetic inputs
